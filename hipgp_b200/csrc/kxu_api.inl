@@ -1,0 +1,62 @@
+// kxu_api.inl -- C ABI for the on-the-fly cross-covariance kernels.
+namespace hipgp {
+template <class T>
+static void kxu_launch(const KxuParams& P, const void* x, const void* grids, const void* alphas, void* out, cudaStream_t s) {
+    if (P.B <= 0 || P.M <= 0) return;
+    auto k = kxu_kernel<T>;
+    dim3 grid((unsigned)((P.M + 1023) / 1024), (unsigned)P.B);
+    HIPGP_LAUNCH(k, grid, dim3(256), 0, s, P, (const T*)x, (const T*)grids, (const T*)alphas, (T*)out);
+    CK_LAUNCH();
+}
+}  // namespace hipgp
+
+extern "C" {
+int hipgp_kxu(int dtype, int kernel_id, int mode, double sig2, const double* ell, int n_ell, double gneiting_alpha,
+              const void* x, int64_t B, int ndim, const int64_t* m, const void* grids, const void* mc_alphas, int npts,
+              void* out, void* stream) {
+    API_BEGIN
+    if (ndim < 1 || ndim > 3) throw Error("hipgp_kxu: ndim must be 1..3");
+    if (kernel_id < 0 || kernel_id > 4) throw Error("hipgp_kxu: unknown kernel id");
+    if (n_ell != 1 && n_ell != ndim) throw Error("hipgp_kxu: ell must have 1 or ndim entries");
+    if (mode == HIPGP_KXU_SEMI_ANALYTIC && kernel_id != HIPGP_K_SQEXP) throw Error("hipgp_kxu: analytic line integral exists for SqExp only");
+    if ((mode == HIPGP_KXU_DERIV || mode == 4) && ndim != 1) throw Error("hipgp_kxu: derivative kernels are 1-D");
+    if (mode == HIPGP_KXU_SEMI_MC && (npts < 1 || !mc_alphas)) throw Error("hipgp_kxu: SEMI_MC needs npts >= 1 and mc_alphas");
+    if ((kernel_id >= 1 && kernel_id <= 3) && n_ell != 1) throw Error("hipgp_kxu: Matern takes a scalar ell");
+    KxuParams P{};
+    P.kernel_id = kernel_id; P.mode = mode; P.ndim = ndim; P.npts = npts; P.sig2 = sig2; P.alpha = gneiting_alpha;
+    P.B = (long)B; P.M = 1;
+    int off = 0;
+    for (int d = 0; d < 3; ++d) { P.m[d] = 1; P.goff[d] = 0; P.ell[d] = 1.0; }
+    for (int d = 0; d < ndim; ++d) {
+        P.m[d] = (int)m[d]; P.goff[d] = off; off += (int)m[d]; P.M *= m[d];
+        P.ell[d] = n_ell == 1 ? ell[0] : ell[d];
+    }
+    P.ell0 = ell[0];
+    if (dtype == HIPGP_F32) kxu_launch<float>(P, x, grids, mc_alphas, out, (cudaStream_t)stream);
+    else if (dtype == HIPGP_F64) kxu_launch<double>(P, x, grids, mc_alphas, out, (cudaStream_t)stream);
+    else throw Error("bad dtype");
+    API_END
+}
+
+int hipgp_doubly_diag(int dtype, const void* x, int64_t B, int ndim, double sig2, const double* ell, int n_ell,
+                      const void* dgrid, const void* slopes, const void* knn, int ntab, void* out, void* stream) {
+    API_BEGIN
+    if (ndim < 1 || ndim > 3) throw Error("hipgp_doubly_diag: ndim must be 1..3");
+    if (B <= 0) return 0;
+    double e[3] = {1, 1, 1};
+    for (int d = 0; d < ndim; ++d) e[d] = n_ell == 1 ? ell[0] : ell[d];
+    const unsigned nb = (unsigned)((B + 127) / 128);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (dtype == HIPGP_F32) {
+        auto k = doubly_diag_kernel<float>;
+        HIPGP_LAUNCH(k, dim3(nb), dim3(128), 0, s, (const float*)x, (long)B, ndim, sig2, ell[0], (const float*)dgrid,
+                     (const float*)slopes, (const float*)knn, ntab, (float*)out, e[0], e[1], e[2]);
+    } else {
+        auto k = doubly_diag_kernel<double>;
+        HIPGP_LAUNCH(k, dim3(nb), dim3(128), 0, s, (const double*)x, (long)B, ndim, sig2, ell[0], (const double*)dgrid,
+                     (const double*)slopes, (const double*)knn, ntab, (double*)out, e[0], e[1], e[2]);
+    }
+    CK_LAUNCH();
+    API_END
+}
+}

@@ -1,0 +1,776 @@
+// plan.cu -- host side of libhipgp_b200: plan construction, spectrum set-up, matvec pipelines, PCG
+// driver and the C ABI (include/hipgp_b200.h).
+#include "../../include/hipgp_b200.h"
+#include "conv_kernels.cuh"
+#include "setup_kernels.cuh"
+#include "kxu_kernels.cuh"
+
+#include <string>
+#include <stdexcept>
+
+namespace hipgp {
+
+static thread_local std::string g_err;
+struct Error : std::runtime_error { using std::runtime_error::runtime_error; };
+
+#define CK(expr)                                                                                     \
+    do {                                                                                             \
+        cudaError_t e__ = (expr);                                                                    \
+        if (e__ != cudaSuccess)                                                                      \
+            throw Error(std::string(#expr) + ": " + cudaGetErrorString(e__));                        \
+    } while (0)
+#define CK_LAUNCH() CK(cudaGetLastError())
+
+// ---------------------------------------------------------------------------------------------
+struct DevBuf {
+    void* p = nullptr; size_t bytes = 0;
+    void ensure(size_t n, size_t* total) {
+        if (n <= bytes) return;
+        if (p) { cudaFree(p); *total -= bytes; }
+        p = nullptr; bytes = 0;
+        if (cudaMalloc(&p, n) != cudaSuccess) { p = nullptr; throw Error("cudaMalloc of " + std::to_string(n) + " bytes failed"); }
+        bytes = n; *total += n;
+    }
+    void release(size_t* total) { if (p) { cudaFree(p); *total -= bytes; } p = nullptr; bytes = 0; }
+    template <class U> U* as() const { return reinterpret_cast<U*>(p); }
+};
+
+// ---------------------------------------------------------------------------------------------
+// line FFT descriptors
+static std::vector<int> choose_radices(int Ln) {
+    std::vector<int> r;
+    int n = Ln;
+    while (n % 5 == 0) { r.push_back(5); n /= 5; }
+    while (n % 3 == 0) { r.push_back(3); n /= 3; }
+    int e = 0;
+    while (n % 2 == 0) { ++e; n /= 2; }
+    if (n != 1) throw Error("FFT length " + std::to_string(Ln) + " is not 2^a 3^b 5^c");
+    // as many radix-8 stages as possible; a remainder of 2 with at least one 8 becomes 4*4
+    int n8 = e / 3, rem = e % 3;
+    if (rem == 1 && n8 >= 1) { n8 -= 1; for (int i = 0; i < n8; ++i) r.push_back(8); r.push_back(4); r.push_back(4); }
+    else { for (int i = 0; i < n8; ++i) r.push_back(8); if (rem == 2) r.push_back(4); else if (rem == 1) r.push_back(2); }
+    return r;
+}
+
+static double fft_cost(int Ln) {
+    std::vector<int> r = choose_radices(Ln);
+    double c = 0;
+    for (int x : r) c += (x == 3 || x == 5) ? 1.3 : 1.0;
+    return (double)Ln * (c + 0.5);
+}
+
+static bool is_smooth(long n) {
+    for (int p : {2, 3, 5}) while (n % p == 0) n /= p;
+    return n == 1;
+}
+
+// smallest-cost 2^a 3^b 5^c length >= n (even when `even`), searched in [n, 2n]
+static int choose_length(long n, bool even, bool pow2_only) {
+    if (n < 2) n = 2;
+    long best = -1; double bc = 0;
+    for (long L = n; L <= 2 * n + 2; ++L) {
+        if (even && (L & 1)) continue;
+        if (pow2_only ? ((L & (L - 1)) != 0) : !is_smooth(L)) continue;
+        const double c = even ? 2.0 * fft_cost((int)(L / 2)) : fft_cost((int)L);
+        if (best < 0 || c < bc) { best = L; bc = c; }
+    }
+    if (best < 0) throw Error("no embedding length found");
+    return (int)best;
+}
+
+template <class T>
+struct LineFftHost {
+    LineFft<T> dev{};
+    DevBuf tw, rev, pos;
+    void build(int Ln, size_t* total) {
+        std::vector<int> r = Ln > 1 ? choose_radices(Ln) : std::vector<int>();
+        if ((int)r.size() > kMaxStages) throw Error("too many FFT stages");
+        dev.Ln = Ln; dev.nst = (int)r.size();
+        for (size_t i = 0; i < r.size(); ++i) dev.radix[i] = r[i];
+        std::vector<cplx<T>> htw(Ln);
+        for (int k = 0; k < Ln; ++k) {
+            // exact argument reduction: angle = -2 pi k / Ln
+            const double a = -2.0 * M_PI * (double)k / (double)Ln;
+            htw[k].x = (T)std::cos(a); htw[k].y = (T)std::sin(a);
+        }
+        // position of frequency k after DIF with radices r[0..]: k = q0 + r0 (q1 + r1 (q2 + ...)),
+        // p = q0 Ln/r0 + q1 Ln/(r0 r1) + ...
+        std::vector<int> hrev(Ln), hpos(Ln);
+        for (int k = 0; k < Ln; ++k) {
+            int kk = k, p = 0, span = Ln;
+            for (size_t i = 0; i < r.size(); ++i) { span /= r[i]; p += (kk % r[i]) * span; kk /= r[i]; }
+            hpos[k] = p; hrev[p] = k;
+        }
+        tw.ensure(sizeof(cplx<T>) * Ln, total); rev.ensure(sizeof(int) * Ln, total); pos.ensure(sizeof(int) * Ln, total);
+        CK(cudaMemcpy(tw.p, htw.data(), sizeof(cplx<T>) * Ln, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(rev.p, hrev.data(), sizeof(int) * Ln, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(pos.p, hpos.data(), sizeof(int) * Ln, cudaMemcpyHostToDevice));
+        dev.tw = tw.as<cplx<T>>(); dev.rev = rev.as<int>(); dev.pos = pos.as<int>();
+    }
+    void release(size_t* total) { tw.release(total); rev.release(total); pos.release(total); }
+};
+
+// geometry of one embedding: D active axes with lengths L[d]; the last axis is the real (row) axis
+template <class T>
+struct Geom {
+    int D = 0;
+    int L[3] = {1, 1, 1};
+    int H = 1;          // L[D-1] / 2
+    long P = 0;         // row pitch in complex elements (>= H + 1)
+    LineFftHost<T> fcol[2];
+    LineFftHost<T> frow;
+    DevBuf twL;
+    bool built = false;
+    void build(int D_, const int* L_, size_t* total) {
+        D = D_;
+        for (int d = 0; d < D; ++d) L[d] = L_[d];
+        H = L[D - 1] / 2;
+        P = ((long)H + 1 + 7) / 8 * 8;
+        for (int d = 0; d + 1 < D; ++d) fcol[d].build(L[d], total);
+        frow.build(H, total);
+        std::vector<cplx<T>> w(H);
+        for (int k = 0; k < H; ++k) {
+            const double a = -2.0 * M_PI * (double)k / (double)L[D - 1];
+            w[k].x = (T)std::cos(a); w[k].y = (T)std::sin(a);
+        }
+        twL.ensure(sizeof(cplx<T>) * H, total);
+        CK(cudaMemcpy(twL.p, w.data(), sizeof(cplx<T>) * H, cudaMemcpyHostToDevice));
+        built = true;
+    }
+    long spec_elems() const { long n = P; for (int d = 0; d + 1 < D; ++d) n *= L[d]; return n; }
+    void release(size_t* total) { for (auto& f : fcol) f.release(total); frow.release(total); twL.release(total); built = false; }
+};
+
+struct RowsFusion {
+    int mode = 0, dot_kind = 0, do_fft = 1;
+    const void* in = nullptr; void* out = nullptr; void* v0 = nullptr; void* v1 = nullptr; const void* v2 = nullptr;
+};
+
+}  // namespace hipgp
+
+using namespace hipgp;
+
+// ---------------------------------------------------------------------------------------------
+struct hipgp_plan {
+    int dtype = 0, device = 0;
+    int ndim_user = 0;
+    std::vector<long> m_user;
+    int D = 0;                 // active axes (m > 1); at least 1
+    int m[3] = {1, 1, 1}, N[3] = {1, 1, 1};
+    long M = 1, E = 1;
+    int Ln[3] = {1, 1, 1}, Lw[3] = {1, 1, 1};
+    size_t dev_bytes = 0;
+    long launches = 0;
+    bool have_spec = false, have_wide = false;
+    double clampv = 1e-6;
+    long nclamped = 0;
+
+    Geom<float> gn32, gw32;    // narrow (K, Cinv) / wide (RT, R) geometries in the plan dtype
+    Geom<double> gn64, gw64;   // fp64 geometries (set-up always runs in fp64; also the fp64 plan's own)
+    DevBuf specK, specCinv, specW;         // stored spectra (plan dtype; specW complex)
+    DevBuf Dm, Dinv, Dsqrt, colK, colG, colS, tmpA, tmpB, costab, counts;   // fp64 set-up arrays (M each)
+    DevBuf W1, W2;                         // frequency-domain workspace
+    DevBuf vr, vp, vz, vAp, partial, scal, cnt, flags;   // PCG state
+    DevBuf stage_in, stage_out;            // device staging for the *_host entry points
+    void* pinned = nullptr;                // host flags mirror
+    long pcg_B = 0;
+};
+
+namespace hipgp {
+
+template <class T> struct Tag {};
+static Geom<float>& geom(hipgp_plan* p, bool wide, Tag<float>) { return wide ? p->gw32 : p->gn32; }
+static Geom<double>& geom(hipgp_plan* p, bool wide, Tag<double>) { return wide ? p->gw64 : p->gn64; }
+
+template <class T> static size_t rows_smem(int H, int RBP) { return sizeof(cplx<T>) * (size_t)(H + 1) * RBP; }
+
+template <class T>
+static void pick_rows_tiling(long total_rows, int H, int* RB, int* RBP, int* nthreads) {
+    int rb = 8;
+    while (rb > 1 && (rows_smem<T>(H, rb + 1) > 96 * 1024 || total_rows < (long)rb * 148)) rb >>= 1;
+    if (rows_smem<T>(H, rb + 1) > 200 * 1024) throw Error("row axis too long for the shared-memory FFT (L = " + std::to_string(2 * H) + ")");
+    *RB = rb; *RBP = rb == 1 ? 1 : rb + 1;
+    long work = (long)H * rb / 8;
+    *nthreads = work >= 256 ? 256 : (work >= 128 ? 128 : (work >= 64 ? 64 : 32));
+}
+
+template <class T>
+static void launch_rows(hipgp_plan* pl, bool inverse, RowsParams<T>& P, cudaStream_t st) {
+    int nth;
+    pick_rows_tiling<T>(P.total_rows, P.H, &P.RB, &P.RBP, &nth);
+    const size_t smem = rows_smem<T>(P.H, P.RBP);
+    dim3 grid((unsigned)((P.total_rows + P.RB - 1) / P.RB));
+    if (inverse) {
+        auto k = rows_inv_kernel<T>;
+        if (smem > 48 * 1024) HIPGP_SET_MAX_SMEM(k, smem);
+        HIPGP_LAUNCH(k, grid, dim3(nth), smem, st, P);
+    } else {
+        auto k = rows_fwd_kernel<T>;
+        if (smem > 48 * 1024) HIPGP_SET_MAX_SMEM(k, smem);
+        HIPGP_LAUNCH(k, grid, dim3(nth), smem, st, P);
+    }
+    CK_LAUNCH();
+    pl->launches++;
+}
+
+template <class T>
+static void launch_cols(hipgp_plan* pl, ColsParams<T>& P, long n_outer, long B, cudaStream_t st) {
+    const int L = P.f.Ln;
+    int tb = sizeof(T) == 4 ? 16 : 8;
+    while (tb > 1 && sizeof(cplx<T>) * (size_t)L * (tb + 1) > 100 * 1024) tb >>= 1;
+    while (tb > 1 && (long)tb > P.inner) tb >>= 1;
+    const int tbp = tb == 1 ? 1 : tb + 1;
+    const size_t smem = sizeof(cplx<T>) * (size_t)L * tbp;
+    if (smem > 220 * 1024) throw Error("grid axis too long for the shared-memory FFT (L = " + std::to_string(L) + ")");
+    P.TB = tb; P.TBP = tbp;
+    long work = (long)L * tb / 8;
+    int nth = work >= 512 ? 512 : (work >= 256 ? 256 : (work >= 128 ? 128 : (work >= 64 ? 64 : 32)));
+    dim3 grid((unsigned)((P.inner + tb - 1) / tb), (unsigned)n_outer, (unsigned)B);
+    auto k = cols_pass_kernel<T>;
+    if (smem > 48 * 1024) HIPGP_SET_MAX_SMEM(k, smem);
+    HIPGP_LAUNCH(k, grid, dim3(nth), smem, st, P);
+    CK_LAUNCH();
+    pl->launches++;
+}
+
+// workspace requirement (complex elements) for a pipeline with the given extents
+static void ws_elems(int D, const int* L, long P, const int* n_in, const int* n_out, long B, long* w1, long* w2) {
+    if (D == 1) { *w1 = B * P; *w2 = 0; return; }
+    if (D == 2) { *w1 = B * std::max(n_in[0], n_out[0]) * P; *w2 = 0; return; }
+    const long R01 = std::max((long)n_in[0] * n_in[1], (long)n_out[0] * n_out[1]);
+    const long R0 = std::max(n_in[0], n_out[0]);
+    *w1 = B * R01 * P; *w2 = B * R0 * (long)L[1] * P;
+}
+
+// The pruned D-dimensional circular convolution:  out = crop_{n_out} IFFT( spec * FFT pad_{n_in} in ).
+template <class T>
+static void run_pipeline(hipgp_plan* pl, Geom<T>& g, const int* n_in, const int* n_out, const void* spec, int spec_kind,
+                         long B, const RowsFusion& ff, const RowsFusion& fi, const PcgDev& st, bool gated, cudaStream_t s) {
+    const int D = g.D;
+    long w1, w2;
+    ws_elems(D, g.L, g.P, n_in, n_out, B, &w1, &w2);
+    pl->W1.ensure(sizeof(cplx<T>) * (size_t)w1, &pl->dev_bytes);
+    if (w2) pl->W2.ensure(sizeof(cplx<T>) * (size_t)w2, &pl->dev_bytes);
+    cplx<T>* W1 = pl->W1.as<cplx<T>>();
+    cplx<T>* W2 = pl->W2.as<cplx<T>>();
+    const long P = g.P;
+    const int* done = gated ? st.flags : nullptr;
+
+    long rows_in = 1, rows_out = 1;
+    for (int d = 0; d + 1 < D; ++d) { rows_in *= n_in[d]; rows_out *= n_out[d]; }
+    const long Wrows = std::max(rows_in, rows_out);
+
+    RowsParams<T> R{};
+    R.W = W1; R.L = g.L[D - 1]; R.H = g.H; R.W_pitch = P; R.W_rows = (int)Wrows;
+    R.f = g.frow.dev; R.twL = g.twL.template as<cplx<T>>(); R.st = st;
+    // forward rows
+    R.in = (const T*)ff.in; R.v0 = (T*)ff.v0; R.v1 = (T*)ff.v1; R.v2 = (const T*)ff.v2;
+    R.mode = ff.mode; R.do_fft = 1; R.total_rows = B * rows_in; R.nrows = (int)rows_in; R.n_real = n_in[D - 1];
+    R.spec = nullptr; R.spec_kind = SPEC_NONE;
+    launch_rows<T>(pl, false, R, s);
+
+    if (D == 2) {
+        ColsParams<T> C{};
+        C.in = W1; C.out = W1; C.n_in = n_in[0]; C.n_out = n_out[0]; C.inner = g.H + 1; C.pitch = P;
+        C.in_ostride = C.out_ostride = 0; C.in_bstride = C.out_bstride = Wrows * P;
+        C.f = g.fcol[0].dev; C.mode = CM_FUSED; C.spec = spec; C.spec_kind = spec_kind; C.done_flag = done;
+        launch_cols<T>(pl, C, 1, B, s);
+    } else if (D == 3) {
+        const long R0 = std::max(n_in[0], n_out[0]);
+        const long L1 = g.L[1];
+        ColsParams<T> C{};
+        C.done_flag = done; C.spec = nullptr; C.spec_kind = SPEC_NONE;
+        // axis 1 forward: W1[b][i0][n_in1][P] -> W2[b][i0][L1][P]
+        C.in = W1; C.out = W2; C.n_in = n_in[1]; C.n_out = n_in[1]; C.inner = g.H + 1; C.pitch = P;
+        C.in_ostride = (long)n_in[1] * P; C.in_bstride = Wrows * P; C.out_ostride = L1 * P; C.out_bstride = R0 * L1 * P;
+        C.f = g.fcol[1].dev; C.mode = CM_FWD;
+        launch_cols<T>(pl, C, n_in[0], B, s);
+        // axis 0 fused, in place on W2
+        C.in = W2; C.out = W2; C.n_in = n_in[0]; C.n_out = n_out[0]; C.inner = L1 * P; C.pitch = L1 * P;
+        C.in_ostride = C.out_ostride = 0; C.in_bstride = C.out_bstride = R0 * L1 * P;
+        C.f = g.fcol[0].dev; C.mode = CM_FUSED; C.spec = spec; C.spec_kind = spec_kind;
+        launch_cols<T>(pl, C, 1, B, s);
+        // axis 1 inverse: W2 -> W1[b][i0][n_out1][P]
+        C.in = W2; C.out = W1; C.n_in = n_out[1]; C.n_out = n_out[1]; C.inner = g.H + 1; C.pitch = P;
+        C.in_ostride = L1 * P; C.in_bstride = R0 * L1 * P; C.out_ostride = (long)n_out[1] * P; C.out_bstride = Wrows * P;
+        C.f = g.fcol[1].dev; C.mode = CM_INV; C.spec = nullptr; C.spec_kind = SPEC_NONE;
+        launch_cols<T>(pl, C, n_out[0], B, s);
+    }
+
+    // inverse rows
+    R.out = (T*)fi.out; R.v0 = (T*)fi.v0; R.mode = fi.mode; R.dot_kind = fi.dot_kind;
+    R.total_rows = B * rows_out; R.nrows = (int)rows_out; R.n_real = n_out[D - 1];
+    if (D == 1) { R.spec = spec; R.spec_kind = spec_kind; }
+    launch_rows<T>(pl, true, R, s);
+}
+
+// forward-only transform of a real (L_0..L_{D-1}) fp64 array into W1 (raw spectrum, pipeline layout)
+static void forward_full(hipgp_plan* pl, Geom<double>& g, const double* h, cudaStream_t s) {
+    const int D = g.D;
+    long rows = 1;
+    for (int d = 0; d + 1 < D; ++d) rows *= g.L[d];
+    pl->W1.ensure(sizeof(cplx<double>) * (size_t)rows * g.P, &pl->dev_bytes);
+    cplx<double>* W = pl->W1.as<cplx<double>>();
+    RowsParams<double> R{};
+    R.in = h; R.W = W; R.L = g.L[D - 1]; R.H = g.H; R.W_pitch = g.P; R.W_rows = (int)rows;
+    R.f = g.frow.dev; R.twL = g.twL.as<cplx<double>>(); R.mode = RF_PLAIN; R.do_fft = 1;
+    R.total_rows = rows; R.nrows = (int)rows; R.n_real = g.L[D - 1];
+    launch_rows<double>(pl, false, R, s);
+    if (D >= 2) {
+        ColsParams<double> C{};
+        C.in = W; C.out = W; C.mode = CM_FWD; C.done_flag = nullptr; C.spec_kind = SPEC_NONE;
+        if (D == 3) {
+            C.n_in = C.n_out = g.L[1]; C.inner = g.H + 1; C.pitch = g.P;
+            C.in_ostride = C.out_ostride = (long)g.L[1] * g.P; C.in_bstride = C.out_bstride = 0;
+            C.f = g.fcol[1].dev;
+            launch_cols<double>(pl, C, g.L[0], 1, s);
+            C.n_in = C.n_out = g.L[0]; C.inner = (long)g.L[1] * g.P; C.pitch = (long)g.L[1] * g.P;
+            C.in_ostride = C.out_ostride = 0; C.f = g.fcol[0].dev;
+            launch_cols<double>(pl, C, 1, 1, s);
+        } else {
+            C.n_in = C.n_out = g.L[0]; C.inner = g.H + 1; C.pitch = g.P;
+            C.in_ostride = C.out_ostride = 0; C.in_bstride = C.out_bstride = 0; C.f = g.fcol[0].dev;
+            launch_cols<double>(pl, C, 1, 1, s);
+        }
+    }
+}
+
+static void dct_all_axes(hipgp_plan* pl, const double* in, double* out, double* tmp, bool normalise, cudaStream_t s) {
+    // separable DCT-I over the active axes; result always lands in `out`
+    const double* src = in;
+    const int D = pl->D;
+    double* bufs[2] = {out, tmp};
+    int which = (D % 2 == 1) ? 0 : 1;   // so that the last axis writes `out`
+    for (int d = 0; d < D; ++d) {
+        const int md = pl->m[d];
+        long inner = 1, outer = 1;
+        for (int e = d + 1; e < D; ++e) inner *= pl->m[e];
+        for (int e = 0; e < d; ++e) outer *= pl->m[e];
+        // cos table for this axis
+        const int Nn = md > 1 ? 2 * (md - 1) : 1;
+        std::vector<double> tab(Nn);
+        for (int t = 0; t < Nn; ++t) {
+            // exact symmetry reduction keeps cos(pi t/(m-1)) accurate to the last bit pattern-wise
+            tab[t] = md > 1 ? std::cos(M_PI * (double)t / (double)(md - 1)) : 1.0;
+        }
+        pl->costab.ensure(sizeof(double) * Nn, &pl->dev_bytes);
+        CK(cudaMemcpyAsync(pl->costab.p, tab.data(), sizeof(double) * Nn, cudaMemcpyHostToDevice, s));
+        CK(cudaStreamSynchronize(s));
+        double* dst = bufs[which];
+        dim3 block(64, 4);
+        dim3 grid((unsigned)((inner + 63) / 64), (unsigned)((md + 3) / 4), (unsigned)outer);
+        const double scale = normalise ? 1.0 / (double)Nn : 1.0;
+        auto k = dct1_axis_kernel;
+        HIPGP_LAUNCH(k, grid, block, 0, s, src, dst, pl->costab.as<double>(), md, inner, scale);
+        CK_LAUNCH();
+        pl->launches++;
+        src = dst; which ^= 1;
+    }
+}
+
+template <class T>
+static void build_spectrum(hipgp_plan* pl, bool wide, const double* col, DevBuf& dst, bool complex_spec, cudaStream_t s) {
+    Geom<double>& g = wide ? pl->gw64 : pl->gn64;
+    EmbedDims e{};
+    e.D = g.D;
+    long total = 1;
+    for (int d = 0; d < 3; ++d) { e.m[d] = 1; e.N[d] = 1; e.L[d] = 1; e.wide[d] = 0; }
+    // right-align the D active axes into the 3 slots of EmbedDims
+    for (int d = 0; d < g.D; ++d) {
+        const int slot = 3 - g.D + d;
+        e.m[slot] = pl->m[d]; e.N[slot] = pl->N[d]; e.L[slot] = g.L[d]; e.wide[slot] = wide ? 1 : 0;
+        total *= g.L[d];
+    }
+    pl->tmpB.ensure(sizeof(double) * (size_t)total, &pl->dev_bytes);
+    {
+        auto k = embed_kernel;
+        const int nb = (int)std::min<long>((total + 255) / 256, 148 * 8);
+        HIPGP_LAUNCH(k, dim3(nb), dim3(256), 0, s, col, pl->tmpB.as<double>(), e);
+        CK_LAUNCH(); pl->launches++;
+    }
+    forward_full(pl, g, pl->tmpB.as<double>(), s);
+    const long n = g.spec_elems();
+    double scale = 0.25;
+    for (int d = 0; d < g.D; ++d) scale /= (double)g.L[d];
+    if (complex_spec) {
+        dst.ensure(sizeof(cplx<T>) * (size_t)n, &pl->dev_bytes);
+        auto k = store_spec_cplx_kernel<T>;
+        HIPGP_LAUNCH(k, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, s, pl->W1.as<cplx<double>>(), dst.as<cplx<T>>(), n, scale);
+    } else {
+        dst.ensure(sizeof(T) * (size_t)n, &pl->dev_bytes);
+        auto k = store_spec_real_kernel<T>;
+        HIPGP_LAUNCH(k, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, s, pl->W1.as<cplx<double>>(), dst.as<T>(), n, scale);
+    }
+    CK_LAUNCH(); pl->launches++;
+}
+
+template <class T>
+static void ensure_geoms(hipgp_plan* pl, bool wide) {
+    Geom<double>& g64 = wide ? pl->gw64 : pl->gn64;
+    const int* L = wide ? pl->Lw : pl->Ln;
+    if (!g64.built) g64.build(pl->D, L, &pl->dev_bytes);
+    if (sizeof(T) == 4) {
+        Geom<float>& g32 = wide ? pl->gw32 : pl->gn32;
+        if (!g32.built) g32.build(pl->D, L, &pl->dev_bytes);
+    }
+}
+
+template <class T>
+static void set_first_row(hipgp_plan* pl, const void* column, double clampv, cudaStream_t s) {
+    const long M = pl->M;
+    pl->clampv = clampv;
+    ensure_geoms<T>(pl, false);
+    for (DevBuf* b : {&pl->Dm, &pl->Dinv, &pl->Dsqrt, &pl->colK, &pl->colG, &pl->colS, &pl->tmpA})
+        b->ensure(sizeof(double) * (size_t)M, &pl->dev_bytes);
+    pl->tmpB.ensure(sizeof(double) * (size_t)M, &pl->dev_bytes);
+    pl->counts.ensure(sizeof(unsigned) * 4, &pl->dev_bytes);
+    CK(cudaMemsetAsync(pl->counts.p, 0, sizeof(unsigned) * 4, s));
+    const unsigned nb = (unsigned)((M + 255) / 256);
+    {
+        auto k = to_double_kernel<T>;
+        HIPGP_LAUNCH(k, dim3(nb), dim3(256), 0, s, (const T*)column, pl->colK.as<double>(), M);
+        CK_LAUNCH(); pl->launches++;
+    }
+    // D = DCT-I(column), clamp, derive
+    dct_all_axes(pl, pl->colK.as<double>(), pl->tmpA.as<double>(), pl->tmpB.as<double>(), false, s);
+    {
+        auto k = clamp_derive_kernel<T>;
+        HIPGP_LAUNCH(k, dim3(nb), dim3(256), 0, s, pl->tmpA.as<double>(), pl->Dm.as<double>(), pl->Dinv.as<double>(),
+                     pl->Dsqrt.as<double>(), M, clampv, pl->counts.as<unsigned>());
+        CK_LAUNCH(); pl->launches++;
+    }
+    unsigned hc[4] = {0, 0, 0, 0};
+    CK(cudaMemcpyAsync(hc, pl->counts.p, sizeof(hc), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    pl->nclamped = hc[0];
+    // first columns of C' (only when something was clamped or rounded: otherwise the column itself), C'^-1, C'^1/2
+    if (pl->nclamped != 0 || sizeof(T) == 4)
+        dct_all_axes(pl, pl->Dm.as<double>(), pl->colK.as<double>(), pl->tmpB.as<double>(), true, s);
+    dct_all_axes(pl, pl->Dinv.as<double>(), pl->colG.as<double>(), pl->tmpB.as<double>(), true, s);
+    dct_all_axes(pl, pl->Dsqrt.as<double>(), pl->colS.as<double>(), pl->tmpB.as<double>(), true, s);
+    build_spectrum<T>(pl, false, pl->colK.as<double>(), pl->specK, false, s);
+    build_spectrum<T>(pl, false, pl->colG.as<double>(), pl->specCinv, false, s);
+    pl->have_spec = true; pl->have_wide = false;
+}
+
+template <class T>
+static void ensure_wide(hipgp_plan* pl, cudaStream_t s) {
+    if (pl->have_wide) return;
+    ensure_geoms<T>(pl, true);
+    build_spectrum<T>(pl, true, pl->colS.as<double>(), pl->specW, true, s);
+    pl->have_wide = true;
+}
+
+static PcgDev null_state() { PcgDev st{}; return st; }
+
+template <class T>
+static void matvec(hipgp_plan* pl, int mode, const void* in, void* out, long B, cudaStream_t s) {
+    if (!pl->have_spec) throw Error("plan has no spectrum: call hipgp_plan_set_first_row first");
+    if (B <= 0) return;
+    RowsFusion ff, fi;
+    ff.mode = RF_PLAIN; ff.in = in; fi.mode = RI_PLAIN; fi.out = out;
+    const bool wide = (mode == HIPGP_MV_RT || mode == HIPGP_MV_R);
+    if (wide) ensure_wide<T>(pl, s);
+    Geom<T>& g = geom(pl, wide, Tag<T>());
+    int n_in[3], n_out[3];
+    for (int d = 0; d < pl->D; ++d) {
+        n_in[d] = mode == HIPGP_MV_R ? pl->N[d] : pl->m[d];
+        n_out[d] = mode == HIPGP_MV_RT ? pl->N[d] : pl->m[d];
+    }
+    const void* spec; int kind;
+    switch (mode) {
+        case HIPGP_MV_K: spec = pl->specK.p; kind = SPEC_REAL; break;
+        case HIPGP_MV_CINV: spec = pl->specCinv.p; kind = SPEC_REAL; break;
+        case HIPGP_MV_RT: spec = pl->specW.p; kind = SPEC_CPLX; break;
+        case HIPGP_MV_R: spec = pl->specW.p; kind = SPEC_CPLX_CONJ; break;
+        default: throw Error("unknown matvec mode");
+    }
+    run_pipeline<T>(pl, g, n_in, n_out, spec, kind, B, ff, fi, null_state(), false, s);
+}
+
+template <class T>
+static PcgDev pcg_state(hipgp_plan* pl, long B, double tol, bool cg_mode) {
+    const long M = pl->M;
+    long nrows = 1;
+    for (int d = 0; d + 1 < pl->D; ++d) nrows *= pl->m[d];
+    for (DevBuf* b : {&pl->vr, &pl->vp, &pl->vz, &pl->vAp}) b->ensure(sizeof(T) * (size_t)(B * M), &pl->dev_bytes);
+    pl->partial.ensure(sizeof(double) * (size_t)(B * nrows), &pl->dev_bytes);
+    pl->scal.ensure(sizeof(double) * (size_t)(4 * B), &pl->dev_bytes);
+    const bool fresh = pl->cnt.bytes < sizeof(unsigned) * (size_t)(B + 1);
+    pl->cnt.ensure(sizeof(unsigned) * (size_t)(B + 1), &pl->dev_bytes);
+    pl->flags.ensure(sizeof(int) * 4, &pl->dev_bytes);
+    if (fresh) CK(cudaMemset(pl->cnt.p, 0, pl->cnt.bytes));
+    PcgDev st{};
+    double* sc = pl->scal.as<double>();
+    st.zr = sc; st.zr_prev = sc + B; st.pAp = sc + 2 * B; st.rr = sc + 3 * B;
+    st.partial = pl->partial.as<double>();
+    st.row_cnt = pl->cnt.as<unsigned>(); st.rhs_cnt = pl->cnt.as<unsigned>() + B;
+    st.flags = pl->flags.as<int>();
+    st.tol = tol; st.B = (int)B; st.cg_mode = cg_mode ? 1 : 0;
+    return st;
+}
+
+// plain (no FFT) fused vector kernels reuse rows_fwd_kernel with do_fft = 0
+template <class T>
+static void launch_vec(hipgp_plan* pl, int mode, const PcgDev& st, long B, const void* in, void* v0, void* v1, const void* v2,
+                       cudaStream_t s) {
+    long nrows = 1;
+    for (int d = 0; d + 1 < pl->D; ++d) nrows *= pl->m[d];
+    RowsParams<T> R{};
+    R.in = (const T*)in; R.v0 = (T*)v0; R.v1 = (T*)v1; R.v2 = (const T*)v2;
+    R.mode = mode; R.do_fft = 0; R.total_rows = B * nrows; R.nrows = (int)nrows; R.n_real = pl->m[pl->D - 1];
+    R.H = (R.n_real + 1) / 2; R.L = 2 * R.H; R.st = st;
+    R.RB = 8; R.RBP = 9;
+    dim3 grid((unsigned)((R.total_rows + R.RB - 1) / R.RB));
+    auto k = rows_fwd_kernel<T>;
+    HIPGP_LAUNCH(k, grid, dim3(256), 0, s, R);
+    CK_LAUNCH(); pl->launches++;
+}
+
+template <class T>
+static void pcg(hipgp_plan* pl, const void* b, void* x, long B, int maxiter, double tol, bool precond, int* iters_out,
+                int* callbacks_out, double* resid_out, hipgp_iter_cb cb, void* user, cudaStream_t s) {
+    if (!pl->have_spec) throw Error("plan has no spectrum: call hipgp_plan_set_first_row first");
+    if (iters_out) *iters_out = 0;
+    if (callbacks_out) *callbacks_out = 0;
+    if (B <= 0) return;
+    const long M = pl->M;
+    PcgDev st = pcg_state<T>(pl, B, tol, !precond);
+    if (!pl->pinned) CK(cudaMallocHost(&pl->pinned, 64));
+    int* hflags = reinterpret_cast<int*>(pl->pinned);
+    Geom<T>& g = geom(pl, false, Tag<T>());
+    int nn[3];
+    for (int d = 0; d < pl->D; ++d) nn[d] = pl->m[d];
+    T* r = pl->vr.as<T>(); T* p = pl->vp.as<T>(); T* z = precond ? pl->vz.as<T>() : r; T* Ap = pl->vAp.as<T>();
+
+    // x = 0 ; r = b - A(0) = b   (cg.py:58-59; the reference spends a matvec on the zero vector)
+    CK(cudaMemsetAsync(x, 0, sizeof(T) * (size_t)(B * M), s));
+    CK(cudaMemcpyAsync(r, b, sizeof(T) * (size_t)(B * M), cudaMemcpyDeviceToDevice, s));
+    const int init_flags[4] = {0, 0, 1, 0};
+    CK(cudaMemcpyAsync(st.flags, init_flags, sizeof(init_flags), cudaMemcpyHostToDevice, s));
+    RowsFusion ff, fi;
+    if (precond) {   // z = P r ; zr = z.r
+        ff.mode = RF_PLAIN; ff.in = r; fi.mode = RI_DOT; fi.dot_kind = DOT_ZR; fi.out = z; fi.v0 = r;
+        run_pipeline<T>(pl, g, nn, nn, pl->specCinv.p, SPEC_REAL, B, ff, fi, st, false, s);
+    } else {         // z = r ; zr = r.r
+        launch_vec<T>(pl, RF_SELFDOT, st, B, r, nullptr, nullptr, nullptr, s);
+    }
+    const int check_every = cb ? 1 : 8;
+    int done = 0, iters = 0, n = 0;
+    while (n < maxiter && !done) {
+        const int chunk = std::min(check_every, maxiter - n);
+        for (int c = 0; c < chunk; ++c) {
+            // p = z + beta p ; Ap = K p ; pAp
+            ff = RowsFusion(); fi = RowsFusion();
+            ff.mode = RF_PUPDATE; ff.in = z; ff.v0 = p;
+            fi.mode = RI_DOT; fi.dot_kind = DOT_PAP; fi.out = Ap; fi.v0 = p;
+            run_pipeline<T>(pl, g, nn, nn, pl->specK.p, SPEC_REAL, B, ff, fi, st, true, s);
+            if (precond) {   // x += a p ; r -= a Ap ; rr ; stop test ; z = P r ; zr
+                ff = RowsFusion(); fi = RowsFusion();
+                ff.mode = RF_XRUPDATE; ff.in = Ap; ff.v0 = r; ff.v1 = x; ff.v2 = p;
+                fi.mode = RI_DOT; fi.dot_kind = DOT_ZR; fi.out = z; fi.v0 = r;
+                run_pipeline<T>(pl, g, nn, nn, pl->specCinv.p, SPEC_REAL, B, ff, fi, st, true, s);
+            } else {
+                launch_vec<T>(pl, RF_XRUPDATE, st, B, Ap, r, x, p, s);
+            }
+        }
+        CK(cudaMemcpyAsync(hflags, st.flags, sizeof(int) * 4, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        done = hflags[0]; iters = hflags[1];
+        n += chunk;
+        if (cb && !done) cb(n - 1, x, user);
+    }
+    if (iters_out) *iters_out = iters;
+    if (callbacks_out) *callbacks_out = done ? iters - 1 : iters;
+    if (resid_out) {
+        std::vector<double> rr(B);
+        CK(cudaMemcpyAsync(rr.data(), st.rr, sizeof(double) * B, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        for (long i = 0; i < B; ++i) resid_out[i] = std::sqrt(rr[i]);
+    }
+}
+
+}  // namespace hipgp
+
+// ---------------------------------------------------------------------------------------------
+// C ABI
+#define API_BEGIN try {
+#define API_END                                                                          \
+    } catch (const std::exception& e) { hipgp::g_err = e.what(); return -1; }            \
+      catch (...) { hipgp::g_err = "unknown error"; return -2; }                         \
+    return 0;
+
+#define DISPATCH(pl, call_f32, call_f64) do { if ((pl)->dtype == HIPGP_F32) { call_f32; } else { call_f64; } } while (0)
+
+static void set_device(const hipgp_plan* pl) { CK(cudaSetDevice(pl->device)); }
+
+extern "C" {
+
+const char* hipgp_last_error(void) { return hipgp::g_err.c_str(); }
+int hipgp_version(void) { return 100; }
+
+int hipgp_plan_create(int ndim, const int64_t* m, int dtype, int device, hipgp_plan** out) {
+    API_BEGIN
+    if (!out || !m || ndim < 1) throw Error("bad arguments");
+    if (dtype != HIPGP_F32 && dtype != HIPGP_F64) throw Error("dtype must be HIPGP_F32 or HIPGP_F64");
+    hipgp_plan* pl = new hipgp_plan();
+    pl->dtype = dtype; pl->device = device; pl->ndim_user = ndim;
+    int D = 0;
+    for (int d = 0; d < ndim; ++d) {
+        if (m[d] < 1) { delete pl; throw Error("grid extents must be >= 1"); }
+        pl->m_user.push_back((long)m[d]);
+        pl->M *= m[d];
+        if (m[d] > 1) {
+            if (D == 3) { delete pl; throw Error("at most 3 grid axes of extent > 1 are supported"); }
+            pl->m[D] = (int)m[d]; pl->N[D] = 2 * (int)m[d] - 2; pl->E *= pl->N[D]; ++D;
+        }
+    }
+    if (D == 0) { D = 1; pl->m[0] = 1; pl->N[0] = 1; }
+    pl->D = D;
+    const char* env = getenv("HIPGP_POW2_ONLY");
+    const bool pow2 = env && env[0] == '1';
+    for (int d = 0; d < D; ++d) {
+        const bool row = (d == D - 1);
+        pl->Ln[d] = choose_length(2L * pl->m[d] - 1, row, pow2);
+        pl->Lw[d] = choose_length((long)pl->N[d] + pl->m[d] - 1, row, pow2);
+    }
+    *out = pl;
+    API_END
+}
+
+int hipgp_plan_destroy(hipgp_plan* pl) {
+    API_BEGIN
+    if (!pl) return 0;
+    size_t* t = &pl->dev_bytes;
+    pl->gn32.release(t); pl->gw32.release(t); pl->gn64.release(t); pl->gw64.release(t);
+    for (DevBuf* b : {&pl->specK, &pl->specCinv, &pl->specW, &pl->Dm, &pl->Dinv, &pl->Dsqrt, &pl->colK, &pl->colG, &pl->colS,
+                      &pl->tmpA, &pl->tmpB, &pl->costab, &pl->counts, &pl->W1, &pl->W2, &pl->vr, &pl->vp, &pl->vz, &pl->vAp,
+                      &pl->partial, &pl->scal, &pl->cnt, &pl->flags, &pl->stage_in, &pl->stage_out})
+        b->release(t);
+    if (pl->pinned) cudaFreeHost(pl->pinned);
+    delete pl;
+    API_END
+}
+
+int hipgp_plan_sizes(const hipgp_plan* pl, int64_t* M, int64_t* Mprime) {
+    API_BEGIN
+    if (M) *M = pl->M;
+    if (Mprime) *Mprime = pl->E;
+    API_END
+}
+
+int hipgp_plan_embedding(const hipgp_plan* pl, int64_t* Ln, int64_t* Lw) {
+    API_BEGIN
+    int a = 0;
+    for (int d = 0; d < pl->ndim_user; ++d) {
+        const bool active = pl->m_user[d] > 1 || (pl->D == 1 && pl->M == 1 && d == 0);
+        if (Ln) Ln[d] = active ? pl->Ln[a] : 1;
+        if (Lw) Lw[d] = active ? pl->Lw[a] : 1;
+        if (active) ++a;
+    }
+    API_END
+}
+
+int hipgp_plan_set_first_row(hipgp_plan* pl, const void* column, double clampv, int64_t* clamped_out, void* stream) {
+    API_BEGIN
+    set_device(pl);
+    DISPATCH(pl, set_first_row<float>(pl, column, clampv, (cudaStream_t)stream), set_first_row<double>(pl, column, clampv, (cudaStream_t)stream));
+    if (clamped_out) *clamped_out = pl->nclamped;
+    API_END
+}
+
+int hipgp_plan_spectrum(hipgp_plan* pl, int which, void* out, void* stream) {
+    API_BEGIN
+    set_device(pl);
+    if (!pl->have_spec) throw Error("plan has no spectrum");
+    if (which < 0 || which > 3) throw Error("bad spectrum selector");
+    EmbedDims e{};
+    for (int d = 0; d < 3; ++d) { e.m[d] = 1; e.N[d] = 1; e.L[d] = 1; e.wide[d] = 0; }
+    for (int d = 0; d < pl->D; ++d) { const int slot = 3 - pl->D + d; e.m[slot] = pl->m[d]; e.N[slot] = pl->N[d]; }
+    const int nb = (int)std::min<long>((pl->E + 255) / 256, 148 * 8);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (pl->dtype == HIPGP_F32) { auto k = expand_even_kernel<float>; HIPGP_LAUNCH(k, dim3(nb), dim3(256), 0, s, pl->Dm.as<double>(), (float*)out, e, which); }
+    else { auto k = expand_even_kernel<double>; HIPGP_LAUNCH(k, dim3(nb), dim3(256), 0, s, pl->Dm.as<double>(), (double*)out, e, which); }
+    CK_LAUNCH(); pl->launches++;
+    API_END
+}
+
+int hipgp_matvec(hipgp_plan* pl, int mode, const void* in, void* out, int64_t B, void* stream) {
+    API_BEGIN
+    set_device(pl);
+    DISPATCH(pl, matvec<float>(pl, mode, in, out, (long)B, (cudaStream_t)stream), matvec<double>(pl, mode, in, out, (long)B, (cudaStream_t)stream));
+    API_END
+}
+
+static size_t elem_size(const hipgp_plan* pl) { return pl->dtype == HIPGP_F32 ? 4 : 8; }
+
+int hipgp_matvec_host(hipgp_plan* pl, int mode, const void* in_host, void* out_host, int64_t B, void* stream) {
+    API_BEGIN
+    set_device(pl);
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t nin = (size_t)B * (mode == HIPGP_MV_R ? pl->E : pl->M) * elem_size(pl);
+    const size_t nout = (size_t)B * (mode == HIPGP_MV_RT ? pl->E : pl->M) * elem_size(pl);
+    pl->stage_in.ensure(nin, &pl->dev_bytes); pl->stage_out.ensure(nout, &pl->dev_bytes);
+    CK(cudaMemcpyAsync(pl->stage_in.p, in_host, nin, cudaMemcpyHostToDevice, s));
+    DISPATCH(pl, matvec<float>(pl, mode, pl->stage_in.p, pl->stage_out.p, (long)B, s), matvec<double>(pl, mode, pl->stage_in.p, pl->stage_out.p, (long)B, s));
+    CK(cudaMemcpyAsync(out_host, pl->stage_out.p, nout, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    API_END
+}
+
+int hipgp_pcg(hipgp_plan* pl, const void* b, void* x, int64_t B, int maxiter, double tol, int precond, int* iters_out,
+              int* callbacks_out, double* resid_out, hipgp_iter_cb cb, void* user, void* stream) {
+    API_BEGIN
+    set_device(pl);
+    cudaStream_t s = (cudaStream_t)stream;
+    DISPATCH(pl, pcg<float>(pl, b, x, (long)B, maxiter, tol, precond != 0, iters_out, callbacks_out, resid_out, cb, user, s),
+             pcg<double>(pl, b, x, (long)B, maxiter, tol, precond != 0, iters_out, callbacks_out, resid_out, cb, user, s));
+    API_END
+}
+
+int hipgp_pcg_host(hipgp_plan* pl, const void* b_host, void* x_host, int64_t B, int maxiter, double tol, int precond,
+                   int* iters_out, int* callbacks_out, double* resid_out, void* stream) {
+    API_BEGIN
+    set_device(pl);
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t n = (size_t)B * pl->M * elem_size(pl);
+    pl->stage_in.ensure(n, &pl->dev_bytes); pl->stage_out.ensure(n, &pl->dev_bytes);
+    CK(cudaMemcpyAsync(pl->stage_in.p, b_host, n, cudaMemcpyHostToDevice, s));
+    DISPATCH(pl, pcg<float>(pl, pl->stage_in.p, pl->stage_out.p, (long)B, maxiter, tol, precond != 0, iters_out, callbacks_out, resid_out, nullptr, nullptr, s),
+             pcg<double>(pl, pl->stage_in.p, pl->stage_out.p, (long)B, maxiter, tol, precond != 0, iters_out, callbacks_out, resid_out, nullptr, nullptr, s));
+    CK(cudaMemcpyAsync(x_host, pl->stage_out.p, n, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    API_END
+}
+
+int hipgp_compute_kn(hipgp_plan* pl, const void* Knm, void* kn, int64_t B, int maxiter, double tol, int* iters_out, void* stream) {
+    API_BEGIN
+    set_device(pl);
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t n = (size_t)B * pl->M * elem_size(pl);
+    pl->stage_out.ensure(n, &pl->dev_bytes);
+    void* d0 = pl->stage_out.p;
+    DISPATCH(pl, pcg<float>(pl, Knm, d0, (long)B, maxiter, tol, true, iters_out, nullptr, nullptr, nullptr, nullptr, s),
+             pcg<double>(pl, Knm, d0, (long)B, maxiter, tol, true, iters_out, nullptr, nullptr, nullptr, nullptr, s));
+    DISPATCH(pl, matvec<float>(pl, HIPGP_MV_RT, d0, kn, (long)B, s), matvec<double>(pl, HIPGP_MV_RT, d0, kn, (long)B, s));
+    API_END
+}
+
+int hipgp_plan_device_bytes(const hipgp_plan* pl, size_t* bytes) { API_BEGIN if (bytes) *bytes = pl->dev_bytes; API_END }
+int hipgp_plan_launch_count(const hipgp_plan* pl, int64_t* launches) { API_BEGIN if (launches) *launches = pl->launches; API_END }
+
+}  // extern "C"
+
+#include "vec_api.inl"
+#include "kxu_api.inl"
+
+#ifdef HIPGP_EMU
+namespace emu {
+thread_local dim3 t_threadIdx, t_blockIdx;
+dim3 g_blockDim, g_gridDim;
+Barrier g_block_barrier;
+Barrier g_warp_barrier[64];
+unsigned char* g_dyn_smem = nullptr;
+double g_shfl_scratch[64][32][2];
+}
+#endif

@@ -1,0 +1,128 @@
+// setup_kernels.cuh -- spectrum set-up (runs once per plan / per kernel-hyperparameter change).
+//
+// The reference builds D = max(Re FFT_N(embed(column)), 1e-6) with N_d = 2 m_d - 2
+// (ziggy/misc/toeplitz_tensor.py:19-33).  The embedded first row is the even extension of the column, so
+// Re FFT_N is exactly the separable DCT-I of the (m_1..m_D) column and D is even per axis.  Hence every
+// operator the reference applies -- C' = F^-1 D F, C'^-1, C'^(1/2) -- is a block-circulant whose first
+// column is again a DCT-I of an (m_1..m_D) array.  Set-up therefore is:  DCT-I -> clamp -> {id, 1/x, sqrt}
+// -> DCT-I (first columns c', g, s), all in fp64, followed by a forward FFT of the re-embedded columns at a
+// smooth length L_d (done with the matvec's own forward passes, so the spectra come out in the pipeline's
+// digit-reversed layout).
+#pragma once
+#include "fft_engine.cuh"
+
+namespace hipgp {
+
+// out[o][k][i] = sum_j w_j in[o][j][i] cos(pi j k / (m-1)),  w_0 = w_{m-1} = 1, else 2.   (DCT-I, unnormalised;
+// applying it twice multiplies by N = 2(m-1)).  costab[t] = cos(pi t / (m-1)), t in [0, 2(m-1)).
+// grid: (ceil(inner/64), ceil(m/4), outer); block (64, 4)
+__global__ void __launch_bounds__(256) dct1_axis_kernel(const double* __restrict__ in, double* __restrict__ out,
+                                                        const double* __restrict__ costab, int m, long inner, double scale) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int k = blockIdx.y * blockDim.y + threadIdx.y;
+    if (i >= inner || k >= m) return;
+    const size_t o = (size_t)blockIdx.z * m * inner;
+    const int N = 2 * (m - 1);
+    double acc = 0.0;
+    if (m == 1) {
+        acc = in[o + i];
+    } else {
+        int t = 0;   // (j*k) mod N, updated incrementally
+        for (int j = 0; j < m; ++j) {
+            const double w = (j == 0 || j == m - 1) ? 1.0 : 2.0;
+            acc += w * in[o + (size_t)j * inner + i] * costab[t];
+            t += k; if (t >= N) t -= N;
+        }
+    }
+    out[o + (size_t)k * inner + i] = acc * scale;
+}
+
+template <class T>
+__global__ void to_double_kernel(const T* __restrict__ in, double* __restrict__ out, long n) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (double)in[i];
+}
+
+// D (fp64 DCT output) -> rounded to the plan dtype, clamped (toeplitz_tensor.py:26), then the three
+// derived spectra in fp64.  counts[0] += number of clamped entries.
+template <class T>
+__global__ void clamp_derive_kernel(const double* __restrict__ Draw, double* __restrict__ D, double* __restrict__ Dinv,
+                                    double* __restrict__ Dsqrt, long n, double clampv, unsigned* counts) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    T d = (T)Draw[i];
+    if (d < (T)clampv) { d = (T)clampv; atomicAdd(counts, 1u); }
+    const double dd = (double)d;
+    D[i] = dd; Dinv[i] = 1.0 / dd; Dsqrt[i] = sqrt(dd);
+}
+
+struct EmbedDims {
+    int D;
+    int m[3];      // column extents
+    int N[3];      // 2m-2 (1 if m == 1)
+    int L[3];      // embedding length
+    int wide[3];   // 0: Toeplitz-block embedding (K, Cinv)  1: full-circulant-output embedding (RT / R)
+};
+
+__host__ __device__ __forceinline__ int embed_index(int i, int m, int N, int L, int wide) {
+    // returns the column index in [0,m) feeding embedded position i, or -1 for the zero gap
+    if (!wide) {
+        if (i < m) return i;
+        if (i > L - m) return L - i;
+        return -1;
+    }
+    if (i < N) return i < m ? i : N - i;
+    if (i > L - m) return L - i;
+    return -1;
+}
+
+// h[i1][i2][i3] (real, extents L) from col[(m1,m2,m3)]
+__global__ void embed_kernel(const double* __restrict__ col, double* __restrict__ h, EmbedDims e) {
+    const long total = (long)e.L[0] * e.L[1] * e.L[2];
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        const int i3 = (int)(idx % e.L[2]);
+        const int i2 = (int)((idx / e.L[2]) % e.L[1]);
+        const int i1 = (int)(idx / ((long)e.L[2] * e.L[1]));
+        const int j1 = embed_index(i1, e.m[0], e.N[0], e.L[0], e.wide[0]);
+        const int j2 = embed_index(i2, e.m[1], e.N[1], e.L[1], e.wide[1]);
+        const int j3 = embed_index(i3, e.m[2], e.N[2], e.L[2], e.wide[2]);
+        double v = 0.0;
+        if (j1 >= 0 && j2 >= 0 && j3 >= 0) v = col[((size_t)j1 * e.m[1] + j2) * e.m[2] + j3];
+        h[idx] = v;
+    }
+}
+
+// raw forward-pipeline output (fp64 complex) -> stored spectrum in the plan dtype, scaled.
+template <class T>
+__global__ void store_spec_real_kernel(const cplx<double>* __restrict__ raw, T* __restrict__ out, long n, double scale) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (T)(raw[i].x * scale);
+}
+template <class T>
+__global__ void store_spec_cplx_kernel(const cplx<double>* __restrict__ raw, cplx<T>* __restrict__ out, long n, double scale) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = mk<T>((T)(raw[i].x * scale), (T)(raw[i].y * scale));
+}
+
+// D-shaped (m_1..m_D) fp64 -> reference layout (N_1..N_D) in the plan dtype (even extension), for the
+// `D`, `D_sqrt`, `Di` attributes of the drop-in ToeplitzTensor.
+template <class T>
+__global__ void expand_even_kernel(const double* __restrict__ Dm, T* __restrict__ out, EmbedDims e, int op) {
+    const long total = (long)e.N[0] * e.N[1] * e.N[2];
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        const int i3 = (int)(idx % e.N[2]);
+        const int i2 = (int)((idx / e.N[2]) % e.N[1]);
+        const int i1 = (int)(idx / ((long)e.N[2] * e.N[1]));
+        const int j1 = i1 < e.m[0] ? i1 : e.N[0] - i1;
+        const int j2 = i2 < e.m[1] ? i2 : e.N[1] - i2;
+        const int j3 = i3 < e.m[2] ? i3 : e.N[2] - i3;
+        const double d = Dm[((size_t)j1 * e.m[1] + j2) * e.m[2] + j3];
+        T v = (T)d;
+        if (op == 1) v = (T)sqrt((double)v);            // D_sqrt = sqrt(D)      (toeplitz_tensor.py:29)
+        else if (op == 2) v = (T)1 / v;                 // Di = 1 / D            (toeplitz_tensor.py:30)
+        else if (op == 3) v = (T)sqrt((double)((T)1 / v));   // Di_sqrt = sqrt(Di)    (toeplitz_tensor.py:33)
+        out[idx] = v;
+    }
+}
+
+}  // namespace hipgp

@@ -1,0 +1,159 @@
+"""`Plan`: torch-tensor front end of the C-ABI plan object (include/hipgp_b200.h).
+
+PyTorch is used for device memory and streams only; all arithmetic happens inside libhipgp_b200.so.
+Tensors must live on a CUDA device -- there is no CPU path.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib as L
+
+_DT = {torch.float32: L.F32, torch.float64: L.F64}
+
+
+def _stream_ptr(device):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _require_cuda(t, what):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError("hipgp_b200: %s must be a CUDA tensor (the structured path has no CPU fallback)" % what)
+
+
+class Plan:
+    """One structured K_uu on a D-dimensional inducing grid (replaces the state of the reference's
+    ToeplitzTensor / ToeplitzMatmul, ziggy/misc/toeplitz_tensor.py:9-45)."""
+
+    def __init__(self, dims, dtype, device):
+        self.lib = L.load()
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise RuntimeError("hipgp_b200: plans live on CUDA devices only (got %s); there is no CPU fallback" % device)
+        if dtype not in _DT:
+            raise TypeError("dtype must be torch.float32 or torch.float64")
+        self.device = device if device.index is not None else torch.device("cuda", torch.cuda.current_device())
+        self.dtype = dtype
+        self.dims = tuple(int(d) for d in dims)
+        m = (C.c_int64 * len(self.dims))(*self.dims)
+        h = C.c_void_p()
+        L.check(self.lib, self.lib.hipgp_plan_create(len(self.dims), m, _DT[dtype], self.device.index, C.byref(h)))
+        self._h = h
+        M, E = C.c_int64(), C.c_int64()
+        L.check(self.lib, self.lib.hipgp_plan_sizes(h, C.byref(M), C.byref(E)))
+        self.M, self.Mprime = M.value, E.value
+        self.embedded_dims = tuple(2 * d - 2 if d > 1 else 1 for d in self.dims)
+        self.num_clamped = None
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h is not None and h.value:
+            try:
+                self.lib.hipgp_plan_destroy(h)
+            except Exception:
+                pass
+            self._h = None
+
+    # ------------------------------------------------------------------
+    def _vec(self, t, ncols, what):
+        _require_cuda(t, what)
+        if t.dim() != 2 or t.shape[1] != ncols:
+            raise ValueError("%s must have shape (bsz, %d), got %s" % (what, ncols, tuple(t.shape)))
+        if t.device != self.device:
+            raise RuntimeError("%s is on %s but the plan is on %s" % (what, t.device, self.device))
+        return t.to(self.dtype).contiguous()
+
+    def embedding(self):
+        n = len(self.dims)
+        a, b = (C.c_int64 * n)(), (C.c_int64 * n)()
+        L.check(self.lib, self.lib.hipgp_plan_embedding(self._h, a, b))
+        return tuple(a), tuple(b)
+
+    def set_first_row(self, column, clamp=1e-6):
+        _require_cuda(column, "column")
+        col = column.detach().reshape(-1).to(self.dtype).contiguous()
+        if col.numel() != self.M:
+            raise ValueError("column must have %d entries" % self.M)
+        n = C.c_int64()
+        with torch.cuda.device(self.device):
+            L.check(self.lib, self.lib.hipgp_plan_set_first_row(self._h, C.c_void_p(col.data_ptr()), float(clamp),
+                                                                 C.byref(n), _stream_ptr(self.device)))
+        self.num_clamped = n.value
+        return self
+
+    def spectrum(self, which=L.SPEC_D):
+        out = torch.empty(self.embedded_dims, dtype=self.dtype, device=self.device)
+        with torch.cuda.device(self.device):
+            L.check(self.lib, self.lib.hipgp_plan_spectrum(self._h, which, C.c_void_p(out.data_ptr()), _stream_ptr(self.device)))
+        return out
+
+    def matvec(self, mode, vec):
+        nin = self.Mprime if mode == L.MV_R else self.M
+        nout = self.Mprime if mode == L.MV_RT else self.M
+        v = self._vec(vec, nin, "vec")
+        out = torch.empty((v.shape[0], nout), dtype=self.dtype, device=self.device)
+        with torch.cuda.device(self.device):
+            L.check(self.lib, self.lib.hipgp_matvec(self._h, mode, C.c_void_p(v.data_ptr()), C.c_void_p(out.data_ptr()),
+                                                     v.shape[0], _stream_ptr(self.device)))
+        return out
+
+    def pcg(self, b, maxiter=20, tol=1e-10, precond=True, callback=None, return_info=False):
+        """Fused device-resident PCG (replaces conj_grad/conj_grad2, ziggy/misc/cg.py).  `callback(n, x)` fires
+        after every iteration that did not satisfy the stopping test, as in the reference (cg.py:70-78)."""
+        v = self._vec(b, self.M, "b")
+        x = torch.empty_like(v)
+        iters, ncb = C.c_int(), C.c_int()
+        resid = (C.c_double * v.shape[0])()
+        if callback is not None:
+            def _cb(n, xptr, user):
+                callback(n, x.clone())
+            cfn = L.ITER_CB(_cb)
+        else:
+            cfn = L.ITER_CB(0)
+        with torch.cuda.device(self.device):
+            L.check(self.lib, self.lib.hipgp_pcg(self._h, C.c_void_p(v.data_ptr()), C.c_void_p(x.data_ptr()), v.shape[0],
+                                                  int(maxiter), float(tol), 1 if precond else 0, C.byref(iters), C.byref(ncb),
+                                                  resid, cfn, None, _stream_ptr(self.device)))
+        if return_info:
+            return x, {"iters": iters.value, "callbacks": ncb.value, "resid": np.array(resid[:])}
+        return x
+
+    def compute_kn(self, Knm, maxiter=10, tol=1e-8):
+        """k_n = R^T K_uu^-1 K_un  (ziggy/hipgp.py:139-146)"""
+        v = self._vec(Knm, self.M, "Knm")
+        out = torch.empty((v.shape[0], self.Mprime), dtype=self.dtype, device=self.device)
+        iters = C.c_int()
+        with torch.cuda.device(self.device):
+            L.check(self.lib, self.lib.hipgp_compute_kn(self._h, C.c_void_p(v.data_ptr()), C.c_void_p(out.data_ptr()),
+                                                         v.shape[0], int(maxiter), float(tol), C.byref(iters),
+                                                         _stream_ptr(self.device)))
+        return out
+
+    # host-buffer entry points (H2D / D2H inside the call) -- used for the end-to-end benchmark figure
+    def matvec_host(self, mode, vec_host, out_host):
+        assert not vec_host.is_cuda and not out_host.is_cuda and vec_host.is_contiguous() and out_host.is_contiguous()
+        with torch.cuda.device(self.device):
+            L.check(self.lib, self.lib.hipgp_matvec_host(self._h, mode, C.c_void_p(vec_host.data_ptr()),
+                                                          C.c_void_p(out_host.data_ptr()), vec_host.shape[0],
+                                                          _stream_ptr(self.device)))
+        return out_host
+
+    def pcg_host(self, b_host, x_host, maxiter=20, tol=1e-10, precond=True):
+        assert not b_host.is_cuda and not x_host.is_cuda and b_host.is_contiguous() and x_host.is_contiguous()
+        iters, ncb = C.c_int(), C.c_int()
+        with torch.cuda.device(self.device):
+            L.check(self.lib, self.lib.hipgp_pcg_host(self._h, C.c_void_p(b_host.data_ptr()), C.c_void_p(x_host.data_ptr()),
+                                                       b_host.shape[0], int(maxiter), float(tol), 1 if precond else 0,
+                                                       C.byref(iters), C.byref(ncb), None, _stream_ptr(self.device)))
+        return x_host, iters.value
+
+    def device_bytes(self):
+        n = C.c_size_t()
+        L.check(self.lib, self.lib.hipgp_plan_device_bytes(self._h, C.byref(n)))
+        return n.value
+
+    def launch_count(self):
+        n = C.c_int64()
+        L.check(self.lib, self.lib.hipgp_plan_launch_count(self._h, C.byref(n)))
+        return n.value

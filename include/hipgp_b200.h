@@ -1,0 +1,113 @@
+/* hipgp_b200.h -- C ABI of libhipgp_b200.so: the B200 (sm_100a) implementation of HIP-GP's
+ * structured-kernel hot path.  Plain pointers and sizes only; every function returns 0 on success and a
+ * negative status otherwise (the message is available from hipgp_last_error(), thread-local).
+ * All device pointers must be contiguous, of the plan's dtype, on the plan's device.  Work is enqueued on
+ * `stream` (a cudaStream_t passed as void*; NULL = default stream); calls that report scalars to the host
+ * (hipgp_pcg, *_host) synchronise that stream before returning.
+ *
+ * Each entry point names the reference interface (suyashk12/hipgp, package `ziggy`) it replaces.
+ */
+#ifndef HIPGP_B200_H
+#define HIPGP_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct hipgp_plan hipgp_plan;
+
+enum { HIPGP_F32 = 0, HIPGP_F64 = 1 };
+
+/* matvec modes                     reference (ziggy/misc/toeplitz_tensor.py : toeplitz_expanded.py "multiply_type") */
+enum {
+    HIPGP_MV_K = 0,    /* K v            _matmul_by_K    :70-83   : "gram"     (B,M)  -> (B,M)  */
+    HIPGP_MV_CINV = 1, /* C^-1 block v   _matmul_by_Cinv :114-125 : "circ_inv" (B,M)  -> (B,M)  */
+    HIPGP_MV_RT = 2,   /* R^T v          _matmul_by_RT   :85-97   : "RTv"      (B,M)  -> (B,M') */
+    HIPGP_MV_R = 3     /* R w            _matmul_by_R    :99-112  : "Rv"       (B,M') -> (B,M)  */
+};
+
+/* which spectrum hipgp_plan_spectrum exports (attributes D, D_sqrt, Di, Di_sqrt; toeplitz_tensor.py:26-33) */
+enum { HIPGP_SPEC_D = 0, HIPGP_SPEC_D_SQRT = 1, HIPGP_SPEC_DI = 2, HIPGP_SPEC_DI_SQRT = 3 };
+
+/* kernel families (ziggy/kernels.py) and cross-covariance modes (ziggy/svi_gp.py:48-76) */
+enum { HIPGP_K_SQEXP = 0, HIPGP_K_MATERN12 = 1, HIPGP_K_MATERN32 = 2, HIPGP_K_MATERN52 = 3, HIPGP_K_GNEITING = 4 };
+enum {
+    HIPGP_KXU_POINT = 0,         /* kernel(xbatch, xinduce)            kernels.py:73-79,108-117,145-158 */
+    HIPGP_KXU_SEMI_ANALYTIC = 1, /* SqExp.k_semi (ray from the origin) kernels.py:85-90,223-237         */
+    HIPGP_KXU_SEMI_MC = 2,       /* Kernel.k_semi_mc                   kernels.py:19-39                 */
+    HIPGP_KXU_DERIV = 3          /* kprime (1-D SqExp d/dx)            exact_gp_1d_derivatives.py:19-23 */
+};
+
+const char* hipgp_last_error(void);
+int hipgp_version(void);
+
+/* ---- plan: replaces ToeplitzTensor.__init__ / ToeplitzMatmul.__init__ (toeplitz_tensor.py:9-45,
+ *      toeplitz_expanded.py:82-127).  m[ndim] are the grid extents (C order, last fastest). */
+int hipgp_plan_create(int ndim, const int64_t* m, int dtype, int device, hipgp_plan** out);
+int hipgp_plan_destroy(hipgp_plan* plan);
+/* sizes: M = prod m_d, Mprime = prod (2 m_d - 2)  (1 for m_d == 1; ziggy/hipgp.py:72) */
+int hipgp_plan_sizes(const hipgp_plan* plan, int64_t* M, int64_t* Mprime);
+/* embedding lengths actually used: narrow (K, C^-1) and wide (R^T, R), ndim entries each */
+int hipgp_plan_embedding(const hipgp_plan* plan, int64_t* L_narrow, int64_t* L_wide);
+
+/* first row of K_uu (M values of the plan dtype, device; jitter already added -- toeplitz_tensor.py:127-133)
+ * -> D = max(Re FFT(embed(column)), clamp) and the spectra of K, C^-1 (and lazily C^1/2).
+ * `clamped_out` (host, optional) receives the number of clamped eigenvalues. */
+int hipgp_plan_set_first_row(hipgp_plan* plan, const void* column_dev, double clamp, int64_t* clamped_out, void* stream);
+/* writes Mprime reals in the reference's (N_1..N_D) layout */
+int hipgp_plan_spectrum(hipgp_plan* plan, int which, void* out_dev, void* stream);
+
+/* ---- structured matvecs; `in`/`out` are (B, M) or (B, M') row-major device arrays */
+int hipgp_matvec(hipgp_plan* plan, int mode, const void* in_dev, void* out_dev, int64_t B, void* stream);
+/* same, host buffers in and out (H2D + D2H inside the call) */
+int hipgp_matvec_host(hipgp_plan* plan, int mode, const void* in_host, void* out_host, int64_t B, void* stream);
+
+/* ---- PCG: replaces conj_grad2/conj_grad driven by ToeplitzTensor._solve / gram_solve
+ *      (ziggy/misc/cg.py:5-80, toeplitz_tensor.py:54-68, toeplitz_expanded.py:17-58).
+ * b, x: (B, M).  precond != 0 uses the HIP-GP preconditioner (upper-left block of C^-1).
+ * Stops when all_b sqrt(r_b.r_b) < tol (checked after the x/r update, as the reference does) or after
+ * maxiter iterations.  iters_out: iterations executed; callbacks_out: iterations that did not break
+ * (= number of reference callback invocations).  resid_out (host, optional): B values of sqrt(r.r).
+ * cb (optional) is called on the host after every non-breaking iteration with x valid on the device. */
+typedef void (*hipgp_iter_cb)(int n, const void* x_dev, void* user);
+int hipgp_pcg(hipgp_plan* plan, const void* b_dev, void* x_dev, int64_t B, int maxiter, double tol, int precond,
+              int* iters_out, int* callbacks_out, double* resid_out, hipgp_iter_cb cb, void* user, void* stream);
+int hipgp_pcg_host(hipgp_plan* plan, const void* b_host, void* x_host, int64_t B, int maxiter, double tol, int precond,
+                   int* iters_out, int* callbacks_out, double* resid_out, void* stream);
+/* k_n = R^T K^-1 K_un  (ziggy/hipgp.py:139-146): PCG(precond) followed by R^T.  Knm (B,M) -> kn (B,M') */
+int hipgp_compute_kn(hipgp_plan* plan, const void* Knm_dev, void* kn_dev, int64_t B, int maxiter, double tol,
+                     int* iters_out, void* stream);
+
+/* ---- fused CG vector updates for callers that bring their own A_mul / precond closures
+ *      (cg.py:25-36 / :64-75).  All vectors (B, M) in the plan dtype; scalars (B) fp64 on the device. */
+int hipgp_vec_dot(int dtype, const void* a_dev, const void* b_dev, double* out_dev, int64_t B, int64_t M, void* stream);
+/* x += alpha p ; r -= alpha Ap with alpha = rs / pAp ; rr_out = r.r */
+int hipgp_vec_xr_update(int dtype, void* x_dev, void* r_dev, const void* p_dev, const void* Ap_dev, const double* rs_dev,
+                        const double* pAp_dev, double* rr_out_dev, int64_t B, int64_t M, void* stream);
+/* p = z + (zr_new / zr_old) p */
+int hipgp_vec_p_update(int dtype, void* p_dev, const void* z_dev, const double* zr_new_dev, const double* zr_old_dev,
+                       int64_t B, int64_t M, void* stream);
+
+/* ---- cross-covariances evaluated on the fly from the grid (ziggy/svi_gp.py:48-76 `_make_grams`).
+ * x: (B, ndim) device; grids: the concatenated 1-D grid coordinates (sum m_d values, plan dtype, device);
+ * ell: 1 or ndim host doubles (n_ell); out: (B, M) row-major.  mc_alphas: npts values (device, plan dtype)
+ * for SEMI_MC -- the stratified offsets arange(npts)/npts + U/npts drawn by the caller (kernels.py:25-27). */
+int hipgp_kxu(int dtype, int kernel_id, int mode, double sig2, const double* ell, int n_ell, double gneiting_alpha,
+              const void* x_dev, int64_t B, int ndim, const int64_t* m, const void* grids_dev,
+              const void* mc_alphas_dev, int npts, void* out_dev, void* stream);
+/* KernelDoublyDiagInterpolator.forward (kernels.py:199-218); table = distance_grid, slopes, knn (ntab each, device) */
+int hipgp_doubly_diag(int dtype, const void* x_dev, int64_t B, int ndim, double sig2, const double* ell, int n_ell,
+                      const void* distance_grid_dev, const void* slopes_dev, const void* knn_dev, int ntab,
+                      void* out_dev, void* stream);
+
+/* bytes of device memory the plan currently owns (spectra, twiddles, workspace) */
+int hipgp_plan_device_bytes(const hipgp_plan* plan, size_t* bytes);
+/* number of kernel launches issued through this plan since creation (for bench accounting) */
+int hipgp_plan_launch_count(const hipgp_plan* plan, int64_t* launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
