@@ -39,9 +39,12 @@ SIGNATURES = {
     "hipgp_vec_xr_update": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp]),
     "hipgp_vec_p_update": (_i, [_i, _vp, _vp, _vp, _vp, _i64, _i64, _vp]),
     "hipgp_kxu": (_i, [_i, _i, _i, _d, _pd, _i, _d, _vp, _i64, _i, _pi64, _vp, _vp, _i, _vp, _vp]),
+    "hipgp_kernel_pairwise": (_i, [_i, _i, _i, _d, _pd, _i, _d, _vp, _i64, _vp, _i64, _i, _vp, _i, _vp, _vp]),
     "hipgp_doubly_diag": (_i, [_i, _vp, _i64, _i, _d, _pd, _i, _vp, _vp, _vp, _i, _vp, _vp]),
     "hipgp_plan_device_bytes": (_i, [_vp, C.POINTER(_sz)]),
     "hipgp_plan_launch_count": (_i, [_vp, _pi64]),
+    "hipgp_plan_profile": (_i, [_vp, _i]),
+    "hipgp_plan_profile_read": (_i, [_vp, _i, _pd, _pi64, _i]),
 }
 
 

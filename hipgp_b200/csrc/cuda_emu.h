@@ -43,6 +43,7 @@ static inline float2 make_float2(float a, float b) { return float2{a, b}; }
 static inline double2 make_double2(double a, double b) { return double2{a, b}; }
 
 typedef void* cudaStream_t;
+typedef void* cudaEvent_t;
 typedef int cudaError_t;
 enum { cudaSuccess = 0 };
 enum cudaMemcpyKind { cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice, cudaMemcpyDefault };

@@ -1,12 +1,29 @@
 // kxu_api.inl -- C ABI for the on-the-fly cross-covariance kernels.
 namespace hipgp {
 template <class T>
-static void kxu_launch(const KxuParams& P, const void* x, const void* grids, const void* alphas, void* out, cudaStream_t s) {
+static void kxu_launch(const KxuParams& P, const void* x, const void* grids, const void* ypts, const void* alphas, void* out,
+                       cudaStream_t s) {
     if (P.B <= 0 || P.M <= 0) return;
     auto k = kxu_kernel<T>;
-    dim3 grid((unsigned)((P.M + 1023) / 1024), (unsigned)P.B);
-    HIPGP_LAUNCH(k, grid, dim3(256), 0, s, P, (const T*)x, (const T*)grids, (const T*)alphas, (T*)out);
-    CK_LAUNCH();
+    // grid.y is limited to 65535: walk the observation axis in slabs
+    for (long b0 = 0; b0 < P.B; b0 += 65535) {
+        const long nb = std::min<long>(65535, P.B - b0);
+        dim3 grid((unsigned)((P.M + 1023) / 1024), (unsigned)nb);
+        HIPGP_LAUNCH(k, grid, dim3(256), 0, s, P, (const T*)x + b0 * P.ndim, (const T*)grids, (const T*)ypts, (const T*)alphas,
+                     (T*)out + b0 * P.M);
+        CK_LAUNCH();
+    }
+}
+static void kxu_check(int dtype, int kernel_id, int mode, int ndim, int n_ell, const void* mc_alphas, int npts) {
+    if (ndim < 1 || ndim > 3) throw Error("hipgp_kxu: ndim must be 1..3");
+    if (kernel_id < 0 || kernel_id > 4) throw Error("hipgp_kxu: unknown kernel id");
+    if (n_ell != 1 && n_ell != ndim) throw Error("hipgp_kxu: ell must have 1 or ndim entries");
+    if (mode < 0 || mode > 4) throw Error("hipgp_kxu: unknown mode");
+    if (mode == HIPGP_KXU_SEMI_ANALYTIC && kernel_id != HIPGP_K_SQEXP) throw Error("hipgp_kxu: analytic line integral exists for SqExp only");
+    if ((mode == HIPGP_KXU_DERIV || mode == 4) && ndim != 1) throw Error("hipgp_kxu: derivative kernels are 1-D");
+    if (mode == HIPGP_KXU_SEMI_MC && (npts < 1 || !mc_alphas)) throw Error("hipgp_kxu: SEMI_MC needs npts >= 1 and mc_alphas");
+    if ((kernel_id >= 1 && kernel_id <= 3) && n_ell != 1) throw Error("hipgp_kxu: Matern takes a scalar ell");
+    if (dtype != HIPGP_F32 && dtype != HIPGP_F64) throw Error("bad dtype");
 }
 }  // namespace hipgp
 
@@ -15,13 +32,7 @@ int hipgp_kxu(int dtype, int kernel_id, int mode, double sig2, const double* ell
               const void* x, int64_t B, int ndim, const int64_t* m, const void* grids, const void* mc_alphas, int npts,
               void* out, void* stream) {
     API_BEGIN
-    if (ndim < 1 || ndim > 3) throw Error("hipgp_kxu: ndim must be 1..3");
-    if (kernel_id < 0 || kernel_id > 4) throw Error("hipgp_kxu: unknown kernel id");
-    if (n_ell != 1 && n_ell != ndim) throw Error("hipgp_kxu: ell must have 1 or ndim entries");
-    if (mode == HIPGP_KXU_SEMI_ANALYTIC && kernel_id != HIPGP_K_SQEXP) throw Error("hipgp_kxu: analytic line integral exists for SqExp only");
-    if ((mode == HIPGP_KXU_DERIV || mode == 4) && ndim != 1) throw Error("hipgp_kxu: derivative kernels are 1-D");
-    if (mode == HIPGP_KXU_SEMI_MC && (npts < 1 || !mc_alphas)) throw Error("hipgp_kxu: SEMI_MC needs npts >= 1 and mc_alphas");
-    if ((kernel_id >= 1 && kernel_id <= 3) && n_ell != 1) throw Error("hipgp_kxu: Matern takes a scalar ell");
+    kxu_check(dtype, kernel_id, mode, ndim, n_ell, mc_alphas, npts);
     KxuParams P{};
     P.kernel_id = kernel_id; P.mode = mode; P.ndim = ndim; P.npts = npts; P.sig2 = sig2; P.alpha = gneiting_alpha;
     P.B = (long)B; P.M = 1;
@@ -32,9 +43,24 @@ int hipgp_kxu(int dtype, int kernel_id, int mode, double sig2, const double* ell
         P.ell[d] = n_ell == 1 ? ell[0] : ell[d];
     }
     P.ell0 = ell[0];
-    if (dtype == HIPGP_F32) kxu_launch<float>(P, x, grids, mc_alphas, out, (cudaStream_t)stream);
-    else if (dtype == HIPGP_F64) kxu_launch<double>(P, x, grids, mc_alphas, out, (cudaStream_t)stream);
-    else throw Error("bad dtype");
+    if (dtype == HIPGP_F32) kxu_launch<float>(P, x, grids, nullptr, mc_alphas, out, (cudaStream_t)stream);
+    else kxu_launch<double>(P, x, grids, nullptr, mc_alphas, out, (cudaStream_t)stream);
+    API_END
+}
+
+int hipgp_kernel_pairwise(int dtype, int kernel_id, int mode, double sig2, const double* ell, int n_ell, double gneiting_alpha,
+                          const void* x, int64_t n, const void* y, int64_t m, int ndim, const void* mc_alphas, int npts,
+                          void* out, void* stream) {
+    API_BEGIN
+    kxu_check(dtype, kernel_id, mode, ndim, n_ell, mc_alphas, npts);
+    KxuParams P{};
+    P.kernel_id = kernel_id; P.mode = mode; P.ndim = ndim; P.npts = npts; P.sig2 = sig2; P.alpha = gneiting_alpha;
+    P.B = (long)n; P.M = (long)m;
+    for (int d = 0; d < 3; ++d) { P.m[d] = 1; P.goff[d] = 0; P.ell[d] = 1.0; }
+    for (int d = 0; d < ndim; ++d) P.ell[d] = n_ell == 1 ? ell[0] : ell[d];
+    P.ell0 = ell[0];
+    if (dtype == HIPGP_F32) kxu_launch<float>(P, x, nullptr, y, mc_alphas, out, (cudaStream_t)stream);
+    else kxu_launch<double>(P, x, nullptr, y, mc_alphas, out, (cudaStream_t)stream);
     API_END
 }
 

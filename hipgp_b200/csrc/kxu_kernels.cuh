@@ -76,7 +76,7 @@ __device__ __forceinline__ T eval_point(const KxuParams& P, const T* x, const T*
 // grid (ceil(M / (256*4)), B); block 256.  out[b][j]
 template <class T>
 __global__ void __launch_bounds__(256) kxu_kernel(KxuParams P, const T* __restrict__ xb, const T* __restrict__ grids,
-                                                  const T* __restrict__ alphas, T* __restrict__ out) {
+                                                  const T* __restrict__ ypts, const T* __restrict__ alphas, T* __restrict__ out) {
     const long b = blockIdx.y;
     T x[3] = {0, 0, 0};
     for (int d = 0; d < P.ndim; ++d) x[d] = xb[b * P.ndim + d];
@@ -90,7 +90,11 @@ __global__ void __launch_bounds__(256) kxu_kernel(KxuParams P, const T* __restri
         if (j >= P.M) break;
         long rem = j;
         T u[3] = {0, 0, 0};
-        for (int d = P.ndim - 1; d >= 0; --d) { const int jd = (int)(rem % P.m[d]); rem /= P.m[d]; u[d] = grids[P.goff[d] + jd]; }
+        if (ypts) {   // explicit second point set (generic Kernel.forward); otherwise the C-order grid
+            for (int d = 0; d < P.ndim; ++d) u[d] = ypts[j * P.ndim + d];
+        } else {
+            for (int d = P.ndim - 1; d >= 0; --d) { const int jd = (int)(rem % P.m[d]); rem /= P.m[d]; u[d] = grids[P.goff[d] + jd]; }
+        }
         T val;
         if (P.mode == 0) {
             val = eval_point<T>(P, x, u);

@@ -174,7 +174,26 @@ struct hipgp_plan {
     DevBuf stage_in, stage_out;            // device staging for the *_host entry points
     void* pinned = nullptr;                // host flags mirror
     long pcg_B = 0;
+    // optional per-kernel-class timing (bench.py roofline): CUDA events around every launch
+    bool profiling = false;
+    struct ProfRec { int cls; cudaEvent_t e0, e1; };
+    std::vector<ProfRec> prof;
+    double prof_ms[4] = {0, 0, 0, 0};
+    long prof_n[4] = {0, 0, 0, 0};
 };
+
+#ifdef HIPGP_EMU
+#define PROF_BEGIN(pl, cls, st) ((void)0)
+#define PROF_END(pl, st) ((void)0)
+#else
+#define PROF_BEGIN(pl, cls_, st)                                                   \
+    if ((pl)->profiling) {                                                         \
+        hipgp_plan::ProfRec r__; r__.cls = (cls_);                                 \
+        cudaEventCreate(&r__.e0); cudaEventCreate(&r__.e1);                        \
+        cudaEventRecord(r__.e0, (st)); (pl)->prof.push_back(r__);                  \
+    }
+#define PROF_END(pl, st) if ((pl)->profiling) cudaEventRecord((pl)->prof.back().e1, (st));
+#endif
 
 namespace hipgp {
 
@@ -200,6 +219,7 @@ static void launch_rows(hipgp_plan* pl, bool inverse, RowsParams<T>& P, cudaStre
     pick_rows_tiling<T>(P.total_rows, P.H, &P.RB, &P.RBP, &nth);
     const size_t smem = rows_smem<T>(P.H, P.RBP);
     dim3 grid((unsigned)((P.total_rows + P.RB - 1) / P.RB));
+    PROF_BEGIN(pl, inverse ? 2 : 0, st);
     if (inverse) {
         auto k = rows_inv_kernel<T>;
         if (smem > 48 * 1024) HIPGP_SET_MAX_SMEM(k, smem);
@@ -209,6 +229,7 @@ static void launch_rows(hipgp_plan* pl, bool inverse, RowsParams<T>& P, cudaStre
         if (smem > 48 * 1024) HIPGP_SET_MAX_SMEM(k, smem);
         HIPGP_LAUNCH(k, grid, dim3(nth), smem, st, P);
     }
+    PROF_END(pl, st);
     CK_LAUNCH();
     pl->launches++;
 }
@@ -228,7 +249,9 @@ static void launch_cols(hipgp_plan* pl, ColsParams<T>& P, long n_outer, long B, 
     dim3 grid((unsigned)((P.inner + tb - 1) / tb), (unsigned)n_outer, (unsigned)B);
     auto k = cols_pass_kernel<T>;
     if (smem > 48 * 1024) HIPGP_SET_MAX_SMEM(k, smem);
+    PROF_BEGIN(pl, 1, st);
     HIPGP_LAUNCH(k, grid, dim3(nth), smem, st, P);
+    PROF_END(pl, st);
     CK_LAUNCH();
     pl->launches++;
 }
@@ -523,7 +546,9 @@ static void launch_vec(hipgp_plan* pl, int mode, const PcgDev& st, long B, const
     R.RB = 8; R.RBP = 9;
     dim3 grid((unsigned)((R.total_rows + R.RB - 1) / R.RB));
     auto k = rows_fwd_kernel<T>;
+    PROF_BEGIN(pl, 3, s);
     HIPGP_LAUNCH(k, grid, dim3(256), 0, s, R);
+    PROF_END(pl, s);
     CK_LAUNCH(); pl->launches++;
 }
 
@@ -756,6 +781,30 @@ int hipgp_compute_kn(hipgp_plan* pl, const void* Knm, void* kn, int64_t B, int m
     API_END
 }
 
+int hipgp_plan_profile(hipgp_plan* pl, int enable) {
+    API_BEGIN
+    pl->profiling = enable != 0;
+    API_END
+}
+int hipgp_plan_profile_read(hipgp_plan* pl, int kernel_class, double* ms_total, int64_t* launches, int reset) {
+    API_BEGIN
+    if (kernel_class < 0 || kernel_class > 3) throw Error("kernel_class must be 0..3");
+#ifndef HIPGP_EMU
+    set_device(pl);
+    CK(cudaDeviceSynchronize());
+    for (auto& r : pl->prof) {
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, r.e0, r.e1));
+        pl->prof_ms[r.cls] += ms; pl->prof_n[r.cls] += 1;
+        cudaEventDestroy(r.e0); cudaEventDestroy(r.e1);
+    }
+    pl->prof.clear();
+#endif
+    if (ms_total) *ms_total = pl->prof_ms[kernel_class];
+    if (launches) *launches = pl->prof_n[kernel_class];
+    if (reset) for (int i = 0; i < 4; ++i) { pl->prof_ms[i] = 0; pl->prof_n[i] = 0; }
+    API_END
+}
 int hipgp_plan_device_bytes(const hipgp_plan* pl, size_t* bytes) { API_BEGIN if (bytes) *bytes = pl->dev_bytes; API_END }
 int hipgp_plan_launch_count(const hipgp_plan* pl, int64_t* launches) { API_BEGIN if (launches) *launches = pl->launches; API_END }
 

@@ -1,0 +1,112 @@
+"""Host-side mirror of the two callers on the hot path:
+
+  * `ToeplitzInducingGP.compute_kn`  (ziggy/hipgp.py:117-146, ziggy branch)  k_n = R^T K_uu^-1 K_un
+  * `SviGP._make_grams`              (ziggy/svi_gp.py:48-76)                  K_xu and the prior diagonal
+
+with the reference's names, arguments and error behaviour, so the unmodified variational families of the reference
+(`MeanFieldToeplitzGP` ...) can sit on top of it.  The dense Cholesky branch (hipgp.py:132-137) is the reference's
+O(M^3) baseline and is not part of this library.
+"""
+import numpy as np
+import torch
+from torch import nn
+
+from .toeplitz_tensor import ToeplitzTensor
+from . import kernels as hk
+
+
+class _GridKernelFn:
+    """`kfun = lambda x, y: kernel(x, y, params=cov_params)` (hipgp.py:139) that also knows how to produce the first
+    row of K_uu straight from the 1-D grids."""
+
+    def __init__(self, kernel, params):
+        self.kernel, self.params = kernel, params
+
+    def __call__(self, x, y):
+        return self.kernel(x, y, params=self.params)
+
+    def grid_row(self, xgrids):
+        return hk.first_row(xgrids, self.kernel, self.params)
+
+
+class ToeplitzInducingGP(nn.Module):
+    def __init__(self, kernel, xgrids, num_obs, sig2_init=1., ell_init=.05, noise2_init=1., learn_kernel=True,
+                 learn_noise=True, dtype=torch.float, whitened_type='ziggy', parameterization='expectation-family',
+                 jitter_val=1e-3):
+        super(ToeplitzInducingGP, self).__init__()
+        self.learn_kernel = learn_kernel
+        self.learn_noise = learn_noise
+        self.jitter_val = jitter_val
+        self.ell = torch.tensor(ell_init, dtype=dtype)
+        self.log_ell = nn.Parameter(torch.log(torch.tensor(ell_init, dtype=dtype)), requires_grad=self.learn_kernel)
+        self.sig2 = torch.tensor(sig2_init, dtype=dtype)
+        self.log_sig2 = nn.Parameter(torch.log(torch.tensor(sig2_init, dtype=dtype)), requires_grad=self.learn_kernel)
+        self.noise2 = torch.tensor(noise2_init, dtype=dtype)
+        self.log_noise2 = nn.Parameter(torch.log(torch.tensor(noise2_init, dtype=dtype)), requires_grad=self.learn_noise)
+        self.kernel = kernel
+        self.dtype = dtype
+        self.N = num_obs
+        assert len(xgrids) > 1, len(xgrids)
+        self.xgrids = xgrids
+        self.M = int(np.prod([len(xg) for xg in xgrids]))
+        if whitened_type != 'ziggy':
+            raise NotImplementedError("hipgp_b200 implements whitened_type='ziggy' (the structured path) only")
+        self.whitened_type = whitened_type
+        self.Mprime = int(np.prod([2 * len(xg) - 2 if len(xg) > 1 else len(xg) for xg in self.xgrids]))
+        self.parameterization = parameterization
+        self._Kmm_cache = None
+
+    @property
+    def xinduce(self):
+        """(M, D) meshgrid of the inducing points (hipgp.py:63-65) -- built on demand; the hot path never reads it."""
+        xxs = torch.meshgrid(*self.xgrids, indexing="ij")
+        return torch.stack([x.reshape(-1) for x in xxs], dim=-1)
+
+    def cuda_params(self, cuda_num=0):
+        device = torch.device('cuda:{}'.format(cuda_num))
+        self.to(device)
+        self.kernel = self.kernel.to(device)
+        self.xgrids = [x.to(device) for x in self.xgrids]
+        return self
+
+    def get_kernel_params(self):
+        if not self.learn_kernel:
+            return self.sig2, self.ell
+        return torch.exp(self.log_sig2), torch.exp(self.log_ell)
+
+    def make_Kmm(self):
+        """the structured K_uu for the current kernel parameters; cached while (sig2, ell, jitter) stay unchanged
+        (the reference rebuilds it every minibatch, hipgp.py:143)."""
+        sig2, ell = self.get_kernel_params()
+        key = (float(sig2), tuple(np.atleast_1d(ell.detach().cpu().numpy()).tolist()) if isinstance(ell, torch.Tensor)
+               else float(ell), float(self.jitter_val), str(self.xgrids[0].device))
+        if self._Kmm_cache is None or self._Kmm_cache[0] != key:
+            kfun = _GridKernelFn(self.kernel, (sig2, ell))
+            Kmm = ToeplitzTensor(xgrids=self.xgrids, kernel=kfun, batch_shape=None, jitter_val=self.jitter_val)
+            self._Kmm_cache = (key, Kmm)
+        return self._Kmm_cache[1]
+
+    def compute_kn(self, Knm, maxiter_cg=10, tol=1e-8, Kmm=None):
+        """kn = R^T Kmm^{-1} Kmn : (bsz, M) -> (bsz, M')  (hipgp.py:117-146)"""
+        if Kmm is None:
+            Kmm = self.make_Kmm()
+        if Knm.requires_grad:
+            d0 = Kmm.inv_matmul(Knm, do_precond=True, maxiter=maxiter_cg, tol=tol)
+            return Kmm._matmul_by_RT(d0)
+        return Kmm._plan.compute_kn(Knm, maxiter=maxiter_cg, tol=tol)
+
+    def _make_grams(self, xbatch, integrated_obs=False, semi_integrated_estimator="analytic", semi_integrated_samps=10):
+        """gram matrices needed for elbo, predict, etc (svi_gp.py:48-76), evaluated on the fly from the grid."""
+        kern_params = self.get_kernel_params()
+        if integrated_obs:
+            if semi_integrated_estimator == "analytic":
+                Knm = self.kernel.k_semi_grid(self.xgrids, xbatch, kern_params)
+            elif semi_integrated_estimator == "mc-biased":
+                Knm = self.kernel.k_semi_mc_grid(self.xgrids, xbatch, kern_params, npts=semi_integrated_samps)
+            else:
+                raise NotImplementedError
+            Knn_diag = self.kernel.k_doubly_diag(xbatch, kern_params)
+        else:
+            Knm = self.kernel.forward_grid(xbatch, self.xgrids, kern_params)
+            Knn_diag = self.kernel.diag(xbatch, kern_params)
+        return Knm, Knn_diag

@@ -157,3 +157,17 @@ class Plan:
         n = C.c_int64()
         L.check(self.lib, self.lib.hipgp_plan_launch_count(self._h, C.byref(n)))
         return n.value
+
+    def profile(self, enable):
+        L.check(self.lib, self.lib.hipgp_plan_profile(self._h, 1 if enable else 0))
+
+    def profile_read(self, reset=True):
+        """{class: (total_ms, launches)} for rows_fwd / cols_pass / rows_inv / vec kernels."""
+        out = {}
+        names = ("rows_fwd", "cols_pass", "rows_inv", "vec")
+        for i, nm in enumerate(names):
+            ms, n = C.c_double(), C.c_int64()
+            L.check(self.lib, self.lib.hipgp_plan_profile_read(self._h, i, C.byref(ms), C.byref(n),
+                                                                1 if (reset and i == len(names) - 1) else 0))
+            out[nm] = (ms.value, n.value)
+        return out

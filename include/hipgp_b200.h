@@ -37,7 +37,8 @@ enum {
     HIPGP_KXU_POINT = 0,         /* kernel(xbatch, xinduce)            kernels.py:73-79,108-117,145-158 */
     HIPGP_KXU_SEMI_ANALYTIC = 1, /* SqExp.k_semi (ray from the origin) kernels.py:85-90,223-237         */
     HIPGP_KXU_SEMI_MC = 2,       /* Kernel.k_semi_mc                   kernels.py:19-39                 */
-    HIPGP_KXU_DERIV = 3          /* kprime (1-D SqExp d/dx)            exact_gp_1d_derivatives.py:19-23 */
+    HIPGP_KXU_DERIV = 3,         /* kprime (1-D SqExp d/dx)            exact_gp_1d_derivatives.py:19-23 */
+    HIPGP_KXU_DERIV2 = 4         /* kprime_double_full (1-D SqExp)     exact_gp_1d_derivatives.py:32-38 */
 };
 
 const char* hipgp_last_error(void);
@@ -97,6 +98,11 @@ int hipgp_vec_p_update(int dtype, void* p_dev, const void* z_dev, const double* 
 int hipgp_kxu(int dtype, int kernel_id, int mode, double sig2, const double* ell, int n_ell, double gneiting_alpha,
               const void* x_dev, int64_t B, int ndim, const int64_t* m, const void* grids_dev,
               const void* mc_alphas_dev, int npts, void* out_dev, void* stream);
+/* the same kernels between two explicit point sets x (n, ndim) and y (m, ndim) -> out (n, m): the generic
+ * Kernel.forward(x, y) (kernels.py:73-79,108-117,145-158) and k_semi / k_semi_mc / kprime with y the point set */
+int hipgp_kernel_pairwise(int dtype, int kernel_id, int mode, double sig2, const double* ell, int n_ell, double gneiting_alpha,
+                          const void* x_dev, int64_t n, const void* y_dev, int64_t m, int ndim,
+                          const void* mc_alphas_dev, int npts, void* out_dev, void* stream);
 /* KernelDoublyDiagInterpolator.forward (kernels.py:199-218); table = distance_grid, slopes, knn (ntab each, device) */
 int hipgp_doubly_diag(int dtype, const void* x_dev, int64_t B, int ndim, double sig2, const double* ell, int n_ell,
                       const void* distance_grid_dev, const void* slopes_dev, const void* knn_dev, int ntab,
@@ -106,6 +112,12 @@ int hipgp_doubly_diag(int dtype, const void* x_dev, int64_t B, int ndim, double 
 int hipgp_plan_device_bytes(const hipgp_plan* plan, size_t* bytes);
 /* number of kernel launches issued through this plan since creation (for bench accounting) */
 int hipgp_plan_launch_count(const hipgp_plan* plan, int64_t* launches);
+
+/* per-kernel-class device timing (CUDA events around every launch while enabled); classes:
+ * 0 rows_fwd (last-axis r2c pass), 1 cols_pass (strided axes, spectrum multiply), 2 rows_inv (c2r pass),
+ * 3 stand-alone vector kernel.  Used by bench.py for the roofline figure; off by default. */
+int hipgp_plan_profile(hipgp_plan* plan, int enable);
+int hipgp_plan_profile_read(hipgp_plan* plan, int kernel_class, double* ms_total, int64_t* launches, int reset);
 
 #ifdef __cplusplus
 }

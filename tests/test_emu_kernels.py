@@ -1,0 +1,133 @@
+"""CPU execution of the CUDA kernel sources (g++ -DHIPGP_EMU build, tests/emu_build.py) against the golden vectors.
+This checks index arithmetic, barriers, digit-reversed layouts, mixed-radix stages and the fused PCG bookkeeping
+without a GPU.  Sizes are tiny because every CUDA thread is an OS thread here.  It is a checker for the kernel
+sources; the product never loads this library."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from hipgp_b200 import _lib as L
+import emu_build
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def rel(a, b):
+    a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+
+
+@pytest.fixture(scope="module")
+def lib():
+    return emu_build.load()
+
+
+def make_plan(lib, g, dt):
+    m = np.array([int(x[2]) for x in g["grids"]], dtype=np.int64)
+    plan = C.c_void_p()
+    assert lib.hipgp_plan_create(len(m), m.ctypes.data_as(L._pi64), L.F32 if dt == np.float32 else L.F64, 0, C.byref(plan)) == 0
+    col = np.ascontiguousarray(g["column"].astype(dt).reshape(-1))
+    ncl = C.c_int64()
+    assert lib.hipgp_plan_set_first_row(plan, ptr(col), 1e-6, C.byref(ncl), None) == 0, lib.hipgp_last_error()
+    return plan
+
+
+@pytest.mark.parametrize("case,dname", [("1d_m100_sqexp", "f64"), ("1d_m2", "f64"), ("2d_17x40_matern32", "f32"),
+                                        ("2d_33x20_gneiting", "f64"), ("3d_6x9x12_matern12", "f64")])
+def test_matvecs(lib, case, dname):
+    g = np.load(os.path.join(GOLD, "toeplitz_%s_%s.npz" % (case, dname)), allow_pickle=True)
+    dt = np.float32 if dname == "f32" else np.float64
+    tol = 1e-5 if dname == "f32" else 1e-10
+    plan = make_plan(lib, g, dt)
+    E = g["D"].size
+    D = np.zeros(E, dtype=dt)
+    assert lib.hipgp_plan_spectrum(plan, 0, ptr(D), None) == 0
+    assert np.abs(D - g["D"].reshape(-1)).max() / np.abs(g["D"]).max() < tol
+    v = np.ascontiguousarray(g["v"][:2]); w = np.ascontiguousarray(g["w"][:2])
+    B, M = v.shape
+    for mode, name, inp, osz in ((0, "Kv", v, M), (1, "Cinv_v", v, M), (2, "RT_v", v, E), (3, "R_w", w, M)):
+        out = np.zeros((B, osz), dtype=dt)
+        assert lib.hipgp_matvec(plan, mode, ptr(inp), ptr(out), B, None) == 0, lib.hipgp_last_error()
+        lim = 3e-3 if (name == "Cinv_v" and dname == "f32") else tol   # fp32 reference spectrum noise, see DESIGN.md
+        assert rel(out, g[name][:2]) < lim, (name, rel(out, g[name][:2]))
+    lib.hipgp_plan_destroy(plan)
+
+
+def test_pcg_iteration_bookkeeping(lib):
+    """PCG / CG callback counts and iterates against the reference on the 1-D case (7 / 20 iterations)."""
+    g = np.load(os.path.join(GOLD, "toeplitz_1d_m100_sqexp_f64.npz"), allow_pickle=True)
+    plan = make_plan(lib, g, np.float64)
+    v = np.ascontiguousarray(g["v"]); B, M = v.shape
+    for tag, prec in (("pcg", 1), ("cg", 0)):
+        maxiter, tol = g["solve_%s_args" % tag]
+        x = np.zeros((B, M)); it = C.c_int(); ncb = C.c_int(); res = np.zeros(B)
+        seen = []
+        cb = L.ITER_CB(lambda n, xp, user: seen.append(n))
+        assert lib.hipgp_pcg(plan, ptr(v), ptr(x), B, int(maxiter), float(tol), prec, C.byref(it), C.byref(ncb),
+                             res.ctypes.data_as(L._pd), cb, None, None) == 0, lib.hipgp_last_error()
+        assert ncb.value == int(g["solve_%s_ncb" % tag]) == len(seen)
+        assert seen == list(range(len(seen)))
+        assert rel(x, g["solve_%s" % tag]) < 1e-9
+    lib.hipgp_plan_destroy(plan)
+
+
+def test_kxu_kernels(lib):
+    g = np.load(os.path.join(GOLD, "kernels_f64.npz"))
+    sig2, ell = [float(t) for t in g["sig2_ell"]]
+    ids = {"sqexp": 0, "matern12": 1, "matern32": 2, "matern52": 3, "gneiting": 4}
+    for D in (2, 3):
+        grid = g["grid_d%d" % D]
+        m = np.array([int(r[2]) for r in grid], dtype=np.int64)
+        axes = np.concatenate([np.linspace(lo, hi, int(n)) for lo, hi, n in grid])
+        x = np.ascontiguousarray(g["x_d%d" % D])
+        B, M = x.shape[0], int(np.prod(m))
+        ellv = (C.c_double * 1)(ell)
+        for kname, kid in ids.items():
+            out = np.zeros((B, M))
+            assert lib.hipgp_kxu(L.F64, kid, L.KXU_POINT, sig2, ellv, 1, 1.0, ptr(x), B, D, m.ctypes.data_as(L._pi64),
+                                 ptr(axes), None, 0, ptr(out), None) == 0, lib.hipgp_last_error()
+            assert rel(out, g["fwd_%s_d%d" % (kname, D)]) < 1e-12, kname
+        al = np.ascontiguousarray(g["semimc_alphas"])
+        out = np.zeros((B, M))
+        assert lib.hipgp_kxu(L.F64, 3, L.KXU_SEMI_MC, sig2, ellv, 1, 1.0, ptr(x), B, D, m.ctypes.data_as(L._pi64), ptr(axes),
+                             ptr(al), al.size, ptr(out), None) == 0
+        assert rel(out, g["semimc_matern52_d%d" % D]) < 1e-12
+        out = np.zeros((B, M))
+        assert lib.hipgp_kxu(L.F64, 0, L.KXU_SEMI_ANALYTIC, sig2, ellv, 1, 1.0, ptr(x), B, D, m.ctypes.data_as(L._pi64),
+                             ptr(axes), None, 0, ptr(out), None) == 0
+        assert rel(out, g["semi_sqexp_d%d" % D]) < 1e-10
+        tab = g["table_sqexp"]
+        out = np.zeros(B)
+        xz = x.copy(); xz[1] = 0.
+        assert lib.hipgp_doubly_diag(L.F64, ptr(xz), B, D, sig2, ellv, 1, ptr(np.ascontiguousarray(tab[0])),
+                                     ptr(np.ascontiguousarray(tab[1])), ptr(np.ascontiguousarray(tab[2])), tab.shape[1],
+                                     ptr(out), None) == 0
+        assert rel(out, g["ddiag0_sqexp_d%d" % D]) < 1e-12
+    # errors come back as status + message, never as exceptions across the ABI
+    assert lib.hipgp_kxu(L.F64, 2, L.KXU_SEMI_ANALYTIC, sig2, ellv, 1, 1.0, ptr(x), B, 3, m.ctypes.data_as(L._pi64),
+                         ptr(axes), None, 0, ptr(out), None) != 0
+    assert b"SqExp only" in lib.hipgp_last_error()
+
+
+def test_vec_kernels(lib):
+    rng = np.random.default_rng(0)
+    B, M = 3, 5000
+    a = rng.standard_normal((B, M)); b = rng.standard_normal((B, M))
+    out = np.zeros(B)
+    assert lib.hipgp_vec_dot(L.F64, ptr(a), ptr(b), ptr(out), B, M, None) == 0
+    assert np.allclose(out, (a * b).sum(1), rtol=1e-12)
+    x = rng.standard_normal((B, M)); r = rng.standard_normal((B, M)); p = rng.standard_normal((B, M)); Ap = rng.standard_normal((B, M))
+    rs = rng.random(B) + 1; pAp = rng.random(B) + 1; rr = np.zeros(B)
+    x0, r0 = x.copy(), r.copy()
+    assert lib.hipgp_vec_xr_update(L.F64, ptr(x), ptr(r), ptr(p), ptr(Ap), ptr(rs), ptr(pAp), ptr(rr), B, M, None) == 0
+    al = (rs / pAp)[:, None]
+    assert np.allclose(x, x0 + al * p) and np.allclose(r, r0 - al * Ap) and np.allclose(rr, (r * r).sum(1))
+    p0 = p.copy()
+    assert lib.hipgp_vec_p_update(L.F64, ptr(p), ptr(x), ptr(rs), ptr(pAp), B, M, None) == 0
+    assert np.allclose(p, x + al * p0)
