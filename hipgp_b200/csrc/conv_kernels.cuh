@@ -114,8 +114,11 @@ struct RowsParams {
     int W_rows;           // rows per rhs in W (>= nrows): W row of global row g is (g/nrows)*W_rows + g%nrows
     LineFft<T> f;         // H-point complex FFT
     const cplx<T>* twL;   // exp(-2 pi i k / L), k < H
+    const cplx<T>* twLp;  // twL in position order: twLp[q] = twL[rev[q]]
+    const int* part;      // partner position of q in the r2c split: pos[H - rev[q]] (q > 0)
     int RB, RBP;          // rows per CTA, padded smem line count
     int mode, dot_kind, do_fft;
+    int vec_ok;           // all row pointers are aligned for 2-element vector access
     const void* spec; int spec_kind;   // rows_inv only (1-D grids)
     PcgDev st;
 };

@@ -141,6 +141,7 @@ static inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetc
 static inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 static inline unsigned atomicInc_emu(unsigned* p) { return __atomic_fetch_add(p, 1u, __ATOMIC_SEQ_CST); }
 template <class T> static inline T __ldg(const T* p) { return *p; }
+static inline int __popc(int x) { return __builtin_popcount((unsigned)x); }
 static inline void sincospi(double x, double* s, double* c) { *s = std::sin(M_PI * x); *c = std::cos(M_PI * x); }
 static inline double cospi(double x) { return std::cos(M_PI * x); }
 static inline double rsqrt(double x) { return 1.0 / std::sqrt(x); }

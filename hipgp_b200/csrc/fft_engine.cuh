@@ -28,6 +28,22 @@ template <class T> __host__ __device__ __forceinline__ cplx<T> mulc(cplx<T> a, c
 // multiply by -i (forward) or +i (inverse)
 template <bool INV, class T> __host__ __device__ __forceinline__ cplx<T> mul_mi(cplx<T> a) { return INV ? mk<T>(-a.y, a.x) : mk<T>(a.y, -a.x); }
 
+#ifndef HIPGP_EMU
+// Blackwell packed fp32 pairs (FADD2 / FMUL2 / FFMA2, sm_100+): one instruction per complex add, two per complex
+// multiply.  (re, im) of a cplx<float> is exactly one f32x2 operand.
+__device__ __forceinline__ float2 f2(cplx<float> a) { return make_float2(a.x, a.y); }
+__device__ __forceinline__ cplx<float> c2(float2 a) { return mk<float>(a.x, a.y); }
+__device__ __forceinline__ cplx<float> operator+(cplx<float> a, cplx<float> b) { return c2(__fadd2_rn(f2(a), f2(b))); }
+__device__ __forceinline__ cplx<float> operator-(cplx<float> a, cplx<float> b) { return c2(__fadd2_rn(f2(a), make_float2(-b.x, -b.y))); }
+__device__ __forceinline__ cplx<float> operator*(cplx<float> a, cplx<float> b) {
+    return c2(__ffma2_rn(make_float2(a.x, a.x), f2(b), __fmul2_rn(make_float2(a.y, a.y), make_float2(-b.y, b.x))));
+}
+__device__ __forceinline__ cplx<float> operator*(cplx<float> a, float s) { return c2(__fmul2_rn(f2(a), make_float2(s, s))); }
+__device__ __forceinline__ cplx<float> mulc(cplx<float> a, cplx<float> b) {
+    return c2(__ffma2_rn(make_float2(a.x, a.x), make_float2(b.x, -b.y), __fmul2_rn(make_float2(a.y, a.y), make_float2(b.y, b.x))));
+}
+#endif
+
 // read-only (non-coherent) load of a complex table entry
 #ifdef HIPGP_EMU
 template <class T> __device__ __forceinline__ cplx<T> ldg_c(const cplx<T>* p) { return *p; }
@@ -51,6 +67,8 @@ struct LineFft {
     const cplx<T>* tw;      // Ln entries, exp(-2 pi i k / Ln)
     const int* rev;         // Ln entries: rev[p] = frequency index k stored at position p after DIF
     const int* pos;         // Ln entries: pos[k] = position p (inverse permutation)
+    const cplx<T>* twst;    // per-stage twiddles, stage s at twst + twoff[s], layout [(r-1) * S + j] = w_Nt^{j r}
+    int twoff[kMaxStages];
 };
 
 // ---- radix butterflies: v[q] = sum_r v[r] w_R^{qr}  (w_R = exp(-+2 pi i / R)) ----------------------
@@ -97,12 +115,37 @@ template <bool INV, class T> __device__ __forceinline__ void bfly5(cplx<T>* v) {
     v[0] = v[0] + a1 + a2;
     v[1] = m1 + j1; v[4] = m1 - j1; v[2] = m2 + j2; v[3] = m2 - j2;
 }
+// radix-16 as 4 x 4:  r = b + 4a, q = c + 4d:  X[c+4d] = sum_b w4^{db} ( w16^{cb} sum_a v[b+4a] w4^{ca} )
+template <bool INV, class T> __device__ __forceinline__ void bfly16(cplx<T>* v) {
+    const T c1 = (T)0.92387953251128675613, s1 = (T)0.38268343236508977173, h = (T)0.70710678118654752440;
+    cplx<T> t[4][4];
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+        cplx<T> u[4] = {v[b], v[b + 4], v[b + 8], v[b + 12]};
+        bfly4<INV>(u);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) t[b][c] = u[c];
+    }
+    const cplx<T> w1 = mk<T>(c1, INV ? s1 : -s1), w2 = mk<T>(h, INV ? h : -h), w3 = mk<T>(s1, INV ? c1 : -c1);
+    const cplx<T> w6 = mk<T>(-h, INV ? h : -h), w9 = mk<T>(-c1, INV ? -s1 : s1);
+    t[1][1] = t[1][1] * w1; t[1][2] = t[1][2] * w2; t[1][3] = t[1][3] * w3;
+    t[2][1] = t[2][1] * w2; t[2][2] = mul_mi<INV>(t[2][2]); t[2][3] = t[2][3] * w6;
+    t[3][1] = t[3][1] * w3; t[3][2] = t[3][2] * w6; t[3][3] = t[3][3] * w9;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        cplx<T> u[4] = {t[0][c], t[1][c], t[2][c], t[3][c]};
+        bfly4<INV>(u);
+#pragma unroll
+        for (int d = 0; d < 4; ++d) v[c + 4 * d] = u[d];
+    }
+}
 template <int R, bool INV, class T> __device__ __forceinline__ void bfly(cplx<T>* v) {
     if (R == 2) bfly2<INV>(v);
     else if (R == 3) bfly3<INV>(v);
     else if (R == 4) bfly4<INV>(v);
     else if (R == 5) bfly5<INV>(v);
-    else bfly8<INV>(v);
+    else if (R == 8) bfly8<INV>(v);
+    else bfly16<INV>(v);
 }
 
 // One stage over `nlines` lines.  Nt = current sub-transform length, S = Nt / R, twmul = Ln / Nt.
@@ -144,6 +187,7 @@ template <bool INV, class T>
 __device__ __forceinline__ void fft_stage_dyn(int R, cplx<T>* s, int pos_stride, int nlines, int Ln, int Nt,
                                               const cplx<T>* __restrict__ tw, int tid, int nthreads) {
     switch (R) {
+        case 16: fft_stage<16, INV>(s, pos_stride, nlines, Ln, Nt, tw, tid, nthreads); break;
         case 8: fft_stage<8, INV>(s, pos_stride, nlines, Ln, Nt, tw, tid, nthreads); break;
         case 4: fft_stage<4, INV>(s, pos_stride, nlines, Ln, Nt, tw, tid, nthreads); break;
         case 2: fft_stage<2, INV>(s, pos_stride, nlines, Ln, Nt, tw, tid, nthreads); break;

@@ -2,6 +2,7 @@
 // driver and the C ABI (include/hipgp_b200.h).
 #include "../../include/hipgp_b200.h"
 #include "conv_kernels.cuh"
+#include "fast_kernels.cuh"
 #include "setup_kernels.cuh"
 #include "kxu_kernels.cuh"
 
@@ -37,18 +38,41 @@ struct DevBuf {
 
 // ---------------------------------------------------------------------------------------------
 // line FFT descriptors
+// Lengths with a compile-time specialised kernel family (fast_kernels.cuh) and their DIF radix lists.
+// X(length, radices...)
+#ifdef HIPGP_DEV_SMALL   /* quick developer builds: a handful of lengths, everything else takes the generic kernels */
+#define HIPGP_FAST_LIST(X) X(16, 16) X(32, 8, 4) X(64, 8, 8) X(128, 16, 8) X(1024, 16, 8, 8) X(2048, 16, 16, 8)
+#else
+#define HIPGP_FAST_LIST(X)                                                                              \
+    X(4, 4) X(8, 8) X(16, 16) X(32, 8, 4) X(64, 8, 8) X(128, 16, 8) X(256, 16, 16) X(512, 8, 8, 8)      \
+    X(1024, 16, 8, 8) X(2048, 16, 16, 8) X(4096, 16, 16, 16) X(8192, 16, 8, 8, 8)                       \
+    X(96, 3, 8, 4) X(192, 3, 8, 8) X(384, 3, 16, 8) X(768, 3, 16, 16) X(1536, 3, 8, 8, 8)               \
+    X(3072, 3, 16, 8, 8) X(320, 5, 8, 8) X(640, 5, 16, 8)
+#endif
+
+static bool g_no_fast = false;
+
+static std::vector<int> fast_radices(int Ln) {
+    switch (Ln) {
+#define X(LEN, ...) case LEN: return std::vector<int>{__VA_ARGS__};
+        HIPGP_FAST_LIST(X)
+#undef X
+        default: return {};
+    }
+}
+
 static std::vector<int> choose_radices(int Ln) {
-    std::vector<int> r;
+    std::vector<int> r = fast_radices(Ln);
+    if (!r.empty()) return r;
     int n = Ln;
     while (n % 5 == 0) { r.push_back(5); n /= 5; }
     while (n % 3 == 0) { r.push_back(3); n /= 3; }
     int e = 0;
     while (n % 2 == 0) { ++e; n /= 2; }
     if (n != 1) throw Error("FFT length " + std::to_string(Ln) + " is not 2^a 3^b 5^c");
-    // as many radix-8 stages as possible; a remainder of 2 with at least one 8 becomes 4*4
-    int n8 = e / 3, rem = e % 3;
-    if (rem == 1 && n8 >= 1) { n8 -= 1; for (int i = 0; i < n8; ++i) r.push_back(8); r.push_back(4); r.push_back(4); }
-    else { for (int i = 0; i < n8; ++i) r.push_back(8); if (rem == 2) r.push_back(4); else if (rem == 1) r.push_back(2); }
+    // radix-16 stages first, then one stage for the remainder
+    while (e >= 4) { r.push_back(16); e -= 4; }
+    if (e == 3) r.push_back(8); else if (e == 2) r.push_back(4); else if (e == 1) r.push_back(2);
     return r;
 }
 
@@ -56,7 +80,8 @@ static double fft_cost(int Ln) {
     std::vector<int> r = choose_radices(Ln);
     double c = 0;
     for (int x : r) c += (x == 3 || x == 5) ? 1.3 : 1.0;
-    return (double)Ln * (c + 0.5);
+    const bool fast = !fast_radices(Ln).empty();
+    return (double)Ln * (c + 0.5) * (fast ? 1.0 : 2.5);    // the generic runtime-radix kernels are ~2.5x slower
 }
 
 static bool is_smooth(long n) {
@@ -81,7 +106,8 @@ static int choose_length(long n, bool even, bool pow2_only) {
 template <class T>
 struct LineFftHost {
     LineFft<T> dev{};
-    DevBuf tw, rev, pos;
+    DevBuf tw, rev, pos, twst;
+    std::vector<int> hrev_, hpos_;
     void build(int Ln, size_t* total) {
         std::vector<int> r = Ln > 1 ? choose_radices(Ln) : std::vector<int>();
         if ((int)r.size() > kMaxStages) throw Error("too many FFT stages");
@@ -106,8 +132,28 @@ struct LineFftHost {
         CK(cudaMemcpy(rev.p, hrev.data(), sizeof(int) * Ln, cudaMemcpyHostToDevice));
         CK(cudaMemcpy(pos.p, hpos.data(), sizeof(int) * Ln, cudaMemcpyHostToDevice));
         dev.tw = tw.as<cplx<T>>(); dev.rev = rev.as<int>(); dev.pos = pos.as<int>();
+        hrev_ = hrev; hpos_ = hpos;
+        // per-stage twiddle tables [(r-1) * S + j] = exp(-2 pi i j r / Nt)
+        std::vector<cplx<T>> st;
+        int Nt = Ln;
+        for (size_t i = 0; i < r.size(); ++i) {
+            const int R = r[i], S = Nt / R;
+            dev.twoff[i] = (int)st.size();
+            for (int rr = 1; rr < R; ++rr)
+                for (int j = 0; j < S; ++j) {
+                    const long num = ((long)j * rr) % Nt;
+                    const double a = -2.0 * M_PI * (double)num / (double)Nt;
+                    cplx<T> wv; wv.x = (T)std::cos(a); wv.y = (T)std::sin(a);
+                    st.push_back(wv);
+                }
+            Nt = S;
+        }
+        if (st.empty()) st.resize(1);
+        twst.ensure(sizeof(cplx<T>) * st.size(), total);
+        CK(cudaMemcpy(twst.p, st.data(), sizeof(cplx<T>) * st.size(), cudaMemcpyHostToDevice));
+        dev.twst = twst.as<cplx<T>>();
     }
-    void release(size_t* total) { tw.release(total); rev.release(total); pos.release(total); }
+    void release(size_t* total) { tw.release(total); rev.release(total); pos.release(total); twst.release(total); }
 };
 
 // geometry of one embedding: D active axes with lengths L[d]; the last axis is the real (row) axis
@@ -119,7 +165,7 @@ struct Geom {
     long P = 0;         // row pitch in complex elements (>= H + 1)
     LineFftHost<T> fcol[2];
     LineFftHost<T> frow;
-    DevBuf twL;
+    DevBuf twL, twLp, part;
     bool built = false;
     void build(int D_, const int* L_, size_t* total) {
         D = D_;
@@ -135,10 +181,19 @@ struct Geom {
         }
         twL.ensure(sizeof(cplx<T>) * H, total);
         CK(cudaMemcpy(twL.p, w.data(), sizeof(cplx<T>) * H, cudaMemcpyHostToDevice));
+        std::vector<cplx<T>> wp(H); std::vector<int> pt(H);
+        for (int q = 0; q < H; ++q) {
+            const int k = frow.hrev_[q];
+            wp[q] = w[k];
+            pt[q] = k == 0 ? 0 : frow.hpos_[H - k];
+        }
+        twLp.ensure(sizeof(cplx<T>) * H, total); part.ensure(sizeof(int) * H, total);
+        CK(cudaMemcpy(twLp.p, wp.data(), sizeof(cplx<T>) * H, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(part.p, pt.data(), sizeof(int) * H, cudaMemcpyHostToDevice));
         built = true;
     }
     long spec_elems() const { long n = P; for (int d = 0; d + 1 < D; ++d) n *= L[d]; return n; }
-    void release(size_t* total) { for (auto& f : fcol) f.release(total); frow.release(total); twL.release(total); built = false; }
+    void release(size_t* total) { for (auto& f : fcol) f.release(total); frow.release(total); twL.release(total); twLp.release(total); part.release(total); built = false; }
 };
 
 struct RowsFusion {
@@ -213,8 +268,54 @@ static void pick_rows_tiling(long total_rows, int H, int* RB, int* RBP, int* nth
     *nthreads = work >= 256 ? 256 : (work >= 128 ? 128 : (work >= 64 ? 64 : 32));
 }
 
+template <class T> static bool aligned2(const void* p) { return ((uintptr_t)p % (2 * sizeof(T))) == 0; }
+
+template <class T> constexpr int rows_pad(int pos) { return sizeof(T) == 4 ? pos + (pos >> 4) : pos + (pos >> 3) + (pos >> 6); }
+
+template <class T, int R0, int... Rs>
+static void launch_rows_fast_t(hipgp_plan* pl, bool inverse, RowsParams<T>& P, cudaStream_t st) {
+    constexpr int H = RLInfo<RL<R0, Rs...>>::N;
+    constexpr int S0 = H / R0;
+    const int RS = line_stride<T>(H);
+    auto smem_for = [&](int rb) { return sizeof(cplx<T>) * (size_t)RS * rb + sizeof(double) * (size_t)S0 * rb; };
+    int rb = 16;
+    while (rb > 1 && (smem_for(rb) > 72 * 1024 || P.total_rows < (long)rb * 148 * 2)) rb >>= 1;
+    if (smem_for(rb) > 220 * 1024) throw Error("row axis too long for the shared-memory FFT");
+    P.RB = rb; P.RBP = rb;
+    const size_t smem = smem_for(rb);
+    const long items = (long)S0 * rb;
+    int nth = items >= 256 ? 256 : (items >= 128 ? 128 : (items >= 64 ? 64 : 32));
+    dim3 grid((unsigned)((P.total_rows + rb - 1) / rb));
+    PROF_BEGIN(pl, inverse ? 2 : 0, st);
+    if (inverse) {
+        auto k = rows_inv_fast_kernel<T, R0, Rs...>;
+        if (smem > 48 * 1024) HIPGP_SET_MAX_SMEM(k, smem);
+        HIPGP_LAUNCH(k, grid, dim3(nth), smem, st, P);
+    } else {
+        auto k = rows_fwd_fast_kernel<T, R0, Rs...>;
+        if (smem > 48 * 1024) HIPGP_SET_MAX_SMEM(k, smem);
+        HIPGP_LAUNCH(k, grid, dim3(nth), smem, st, P);
+    }
+    PROF_END(pl, st);
+    CK_LAUNCH();
+    pl->launches++;
+}
+
+template <class T>
+static bool launch_rows_fast(hipgp_plan* pl, bool inverse, RowsParams<T>& P, cudaStream_t st) {
+    if (g_no_fast) return false;
+    switch (P.H) {
+#define X(LEN, ...) case LEN: launch_rows_fast_t<T, __VA_ARGS__>(pl, inverse, P, st); return true;
+        HIPGP_FAST_LIST(X)
+#undef X
+        default: return false;
+    }
+}
+
 template <class T>
 static void launch_rows(hipgp_plan* pl, bool inverse, RowsParams<T>& P, cudaStream_t st) {
+    P.vec_ok = (aligned2<T>(P.in) && aligned2<T>(P.out) && aligned2<T>(P.v0) && aligned2<T>(P.v1) && aligned2<T>(P.v2)) ? 1 : 0;
+    if (P.do_fft && launch_rows_fast<T>(pl, inverse, P, st)) return;
     int nth;
     pick_rows_tiling<T>(P.total_rows, P.H, &P.RB, &P.RBP, &nth);
     const size_t smem = rows_smem<T>(P.H, P.RBP);
@@ -234,8 +335,51 @@ static void launch_rows(hipgp_plan* pl, bool inverse, RowsParams<T>& P, cudaStre
     pl->launches++;
 }
 
+#ifndef HIPGP_TB_SHIFT
+#define HIPGP_TB_SHIFT 0
+#endif
+template <class T> constexpr int cols_tb_base(int L);
+template <class T> constexpr int cols_tb(int L) { return cols_tb_base<T>(L) >> HIPGP_TB_SHIFT > 0 ? cols_tb_base<T>(L) >> HIPGP_TB_SHIFT : 1; }
+template <class T> constexpr int cols_tb_base(int L) {
+    // lines per CTA: keep the tile <= 128 KB and, where it fits, >= 64 B of contiguous lines per position
+    return sizeof(T) == 4 ? (L <= 256 ? 32 : (L <= 512 ? 16 : (L <= 2048 ? 8 : (L <= 4096 ? 4 : 2))))
+                          : (L <= 256 ? 16 : (L <= 512 ? 8 : (L <= 2048 ? 4 : (L <= 4096 ? 2 : 1))));
+}
+
+template <class T, int LEN, int R0, int... Rs>
+static void launch_cols_fast_t(hipgp_plan* pl, ColsParams<T>& P, long n_outer, long B, cudaStream_t st) {
+    constexpr int TB = cols_tb<T>(LEN);
+    static_assert(RLInfo<RL<R0, Rs...>>::N == LEN, "radix list does not multiply to the length");
+    P.TB = TB; P.TBP = TB;
+    const size_t smem = sizeof(cplx<T>) * (size_t)line_stride<T>(LEN) * TB;
+    const long items = (long)LEN * TB / 16;
+    int nth = items >= 512 ? 512 : (items >= 256 ? 256 : (items >= 128 ? 128 : (items >= 64 ? 64 : 32)));
+    static const char* env_nth = getenv("HIPGP_COLS_NTH");
+    if (env_nth) nth = atoi(env_nth);
+    dim3 grid((unsigned)((P.inner + TB - 1) / TB), (unsigned)n_outer, (unsigned)B);
+    auto k = cols_fast_kernel<T, TB, R0, Rs...>;
+    if (smem > 48 * 1024) HIPGP_SET_MAX_SMEM(k, smem);
+    PROF_BEGIN(pl, 1, st);
+    HIPGP_LAUNCH(k, grid, dim3(nth), smem, st, P);
+    PROF_END(pl, st);
+    CK_LAUNCH();
+    pl->launches++;
+}
+
+template <class T>
+static bool launch_cols_fast(hipgp_plan* pl, ColsParams<T>& P, long n_outer, long B, cudaStream_t st) {
+    if (g_no_fast) return false;
+    switch (P.f.Ln) {
+#define X(LEN, ...) case LEN: launch_cols_fast_t<T, LEN, __VA_ARGS__>(pl, P, n_outer, B, st); return true;
+        HIPGP_FAST_LIST(X)
+#undef X
+        default: return false;
+    }
+}
+
 template <class T>
 static void launch_cols(hipgp_plan* pl, ColsParams<T>& P, long n_outer, long B, cudaStream_t st) {
+    if (launch_cols_fast<T>(pl, P, n_outer, B, st)) return;
     const int L = P.f.Ln;
     int tb = sizeof(T) == 4 ? 16 : 8;
     while (tb > 1 && sizeof(cplx<T>) * (size_t)L * (tb + 1) > 100 * 1024) tb >>= 1;
@@ -285,7 +429,7 @@ static void run_pipeline(hipgp_plan* pl, Geom<T>& g, const int* n_in, const int*
 
     RowsParams<T> R{};
     R.W = W1; R.L = g.L[D - 1]; R.H = g.H; R.W_pitch = P; R.W_rows = (int)Wrows;
-    R.f = g.frow.dev; R.twL = g.twL.template as<cplx<T>>(); R.st = st;
+    R.f = g.frow.dev; R.twL = g.twL.template as<cplx<T>>(); R.twLp = g.twLp.template as<cplx<T>>(); R.part = g.part.template as<int>(); R.st = st;
     // forward rows
     R.in = (const T*)ff.in; R.v0 = (T*)ff.v0; R.v1 = (T*)ff.v1; R.v2 = (const T*)ff.v2;
     R.mode = ff.mode; R.do_fft = 1; R.total_rows = B * rows_in; R.nrows = (int)rows_in; R.n_real = n_in[D - 1];
@@ -336,7 +480,7 @@ static void forward_full(hipgp_plan* pl, Geom<double>& g, const double* h, cudaS
     cplx<double>* W = pl->W1.as<cplx<double>>();
     RowsParams<double> R{};
     R.in = h; R.W = W; R.L = g.L[D - 1]; R.H = g.H; R.W_pitch = g.P; R.W_rows = (int)rows;
-    R.f = g.frow.dev; R.twL = g.twL.as<cplx<double>>(); R.mode = RF_PLAIN; R.do_fft = 1;
+    R.f = g.frow.dev; R.twL = g.twL.as<cplx<double>>(); R.twLp = g.twLp.as<cplx<double>>(); R.part = g.part.as<int>(); R.mode = RF_PLAIN; R.do_fft = 1;
     R.total_rows = rows; R.nrows = (int)rows; R.n_real = g.L[D - 1];
     launch_rows<double>(pl, false, R, s);
     if (D >= 2) {
@@ -415,14 +559,18 @@ static void build_spectrum(hipgp_plan* pl, bool wide, const double* col, DevBuf&
     const long n = g.spec_elems();
     double scale = 0.25;
     for (int d = 0; d < g.D; ++d) scale /= (double)g.L[d];
+    // the specialised column pass reads the spectrum transposed ([line][position of axis 0])
+    const bool transposed = g.D >= 2 && !g_no_fast && !fast_radices(g.L[0]).empty();
+    const long L0 = g.L[0], inner = n / L0;
+    const unsigned nblk = (unsigned)((n + 255) / 256);
     if (complex_spec) {
         dst.ensure(sizeof(cplx<T>) * (size_t)n, &pl->dev_bytes);
-        auto k = store_spec_cplx_kernel<T>;
-        HIPGP_LAUNCH(k, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, s, pl->W1.as<cplx<double>>(), dst.as<cplx<T>>(), n, scale);
+        if (transposed) { auto k = store_spec_cplx_T_kernel<T>; HIPGP_LAUNCH(k, dim3(nblk), dim3(256), 0, s, pl->W1.as<cplx<double>>(), dst.as<cplx<T>>(), L0, inner, scale); }
+        else { auto k = store_spec_cplx_kernel<T>; HIPGP_LAUNCH(k, dim3(nblk), dim3(256), 0, s, pl->W1.as<cplx<double>>(), dst.as<cplx<T>>(), n, scale); }
     } else {
         dst.ensure(sizeof(T) * (size_t)n, &pl->dev_bytes);
-        auto k = store_spec_real_kernel<T>;
-        HIPGP_LAUNCH(k, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, s, pl->W1.as<cplx<double>>(), dst.as<T>(), n, scale);
+        if (transposed) { auto k = store_spec_real_T_kernel<T>; HIPGP_LAUNCH(k, dim3(nblk), dim3(256), 0, s, pl->W1.as<cplx<double>>(), dst.as<T>(), L0, inner, scale); }
+        else { auto k = store_spec_real_kernel<T>; HIPGP_LAUNCH(k, dim3(nblk), dim3(256), 0, s, pl->W1.as<cplx<double>>(), dst.as<T>(), n, scale); }
     }
     CK_LAUNCH(); pl->launches++;
 }
@@ -652,6 +800,8 @@ int hipgp_plan_create(int ndim, const int64_t* m, int dtype, int device, hipgp_p
     }
     if (D == 0) { D = 1; pl->m[0] = 1; pl->N[0] = 1; }
     pl->D = D;
+    const char* nf = getenv("HIPGP_NO_FAST");
+    g_no_fast = nf && nf[0] == '1';
     const char* env = getenv("HIPGP_POW2_ONLY");
     const bool pow2 = env && env[0] == '1';
     for (int d = 0; d < D; ++d) {
