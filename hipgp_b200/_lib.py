@@ -33,6 +33,8 @@ SIGNATURES = {
     "hipgp_matvec": (_i, [_vp, _i, _vp, _vp, _i64, _vp]),
     "hipgp_matvec_host": (_i, [_vp, _i, _vp, _vp, _i64, _vp]),
     "hipgp_pcg": (_i, [_vp, _vp, _vp, _i64, _i, _d, _i, _pi, _pi, _pd, ITER_CB, _vp, _vp]),
+    "hipgp_pcg_begin": (_i, [_vp, _vp, _vp, _i64, _d, _i, _vp]),
+    "hipgp_pcg_step": (_i, [_vp, _i, _pi, _pi, _pd, _vp]),
     "hipgp_pcg_host": (_i, [_vp, _vp, _vp, _i64, _i, _d, _i, _pi, _pi, _pd, _vp]),
     "hipgp_compute_kn": (_i, [_vp, _vp, _vp, _i64, _i, _d, _pi, _vp]),
     "hipgp_vec_dot": (_i, [_i, _vp, _vp, _vp, _i64, _i64, _vp]),
@@ -41,6 +43,8 @@ SIGNATURES = {
     "hipgp_kxu": (_i, [_i, _i, _i, _d, _pd, _i, _d, _vp, _i64, _i, _pi64, _vp, _vp, _i, _vp, _vp]),
     "hipgp_kernel_pairwise": (_i, [_i, _i, _i, _d, _pd, _i, _d, _vp, _i64, _vp, _i64, _i, _vp, _i, _vp, _vp]),
     "hipgp_doubly_diag": (_i, [_i, _vp, _i64, _i, _d, _pd, _i, _vp, _vp, _vp, _i, _vp, _vp]),
+    "hipgp_meanfield_rowstats": (_i, [_i, _vp, _vp, _vp, _i64, _i64, _vp, _vp]),
+    "hipgp_meanfield_colstats": (_i, [_i, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp]),
     "hipgp_plan_device_bytes": (_i, [_vp, C.POINTER(_sz)]),
     "hipgp_plan_launch_count": (_i, [_vp, _pi64]),
     "hipgp_plan_profile": (_i, [_vp, _i]),

@@ -197,6 +197,50 @@ __global__ void __launch_bounds__(256) vec_kernel(int op, T* x, T* r, const T* a
         if (threadIdx.x == 0) partial[bb * nchunk + blockIdx.x] = t;
     }
 }
+// ---- mean-field natural-gradient reductions over k_n (B x E) ------------------------------------------
+// grid (nchunk, B), block 256: partial[(b*3 + t)*nchunk + chunk]
+template <class T>
+__global__ void __launch_bounds__(256) mf_rowstats_kernel(const T* __restrict__ kn, const T* __restrict__ qm, const T* __restrict__ qS,
+                                                          double* partial, long E, int nchunk) {
+    const long bb = blockIdx.y;
+    const long per = (E + nchunk - 1) / nchunk;
+    const long lo = (long)blockIdx.x * per, hi = lo + per < E ? lo + per : E;
+    const T* row = kn + (size_t)bb * E;
+    double a0 = 0, a1 = 0, a2 = 0;
+    for (long j = lo + threadIdx.x; j < hi; j += 256) {
+        const T k = row[j];
+        a0 += (double)(k * qm[j]); a1 += (double)(k * k); a2 += (double)(k * k * qS[j]);
+    }
+    a0 = block_sum_256<T>(a0); a1 = block_sum_256<T>(a1); a2 = block_sum_256<T>(a2);
+    if (threadIdx.x == 0) {
+        partial[(bb * 3 + 0) * nchunk + blockIdx.x] = a0;
+        partial[(bb * 3 + 1) * nchunk + blockIdx.x] = a1;
+        partial[(bb * 3 + 2) * nchunk + blockIdx.x] = a2;
+    }
+}
+template <class T>
+__global__ void mf_rowstats_reduce_kernel(const double* partial, T* out, int nchunk, long B) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;   // over 3*B
+    if (i >= 3 * B) return;
+    const long bb = i / 3, t = i - bb * 3;
+    double s = 0;
+    for (int c = 0; c < nchunk; ++c) s += partial[i * nchunk + c];
+    out[t * B + bb] = (T)s;
+}
+// thread per column j, coalesced across j; loops over the B rows
+template <class T>
+__global__ void __launch_bounds__(256) mf_colstats_kernel(const T* __restrict__ kn, const T* __restrict__ w1, const T* __restrict__ w2,
+                                                          T* __restrict__ dm, T* __restrict__ lam, long B, long E) {
+    const long j = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= E) return;
+    T a = 0, l = 0;
+    for (long b = 0; b < B; ++b) {
+        const T k = kn[(size_t)b * E + j];
+        a += w1[b] * k; l += w2[b] * k * k;
+    }
+    dm[j] = a; lam[j] = l;
+}
+
 __global__ void vec_reduce_kernel(const double* partial, double* out, int nchunk, long B) {
     const long bb = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (bb >= B) return;

@@ -229,6 +229,7 @@ struct hipgp_plan {
     DevBuf stage_in, stage_out;            // device staging for the *_host entry points
     void* pinned = nullptr;                // host flags mirror
     long pcg_B = 0;
+    void* run_x = nullptr; long run_B = 0; bool run_precond = true; double run_tol = 0; bool run_active = false;   // begin/step state
     // optional per-kernel-class timing (bench.py roofline): CUDA events around every launch
     bool profiling = false;
     struct ProfRec { int cls; cudaEvent_t e0, e1; };
@@ -700,22 +701,18 @@ static void launch_vec(hipgp_plan* pl, int mode, const PcgDev& st, long B, const
     CK_LAUNCH(); pl->launches++;
 }
 
+// x = 0 ; r = b ; z = P r (or r) ; r.z  -- everything before the first iteration of cg.py:58-62
 template <class T>
-static void pcg(hipgp_plan* pl, const void* b, void* x, long B, int maxiter, double tol, bool precond, int* iters_out,
-                int* callbacks_out, double* resid_out, hipgp_iter_cb cb, void* user, cudaStream_t s) {
+static void pcg_begin(hipgp_plan* pl, const void* b, void* x, long B, double tol, bool precond, cudaStream_t s) {
     if (!pl->have_spec) throw Error("plan has no spectrum: call hipgp_plan_set_first_row first");
-    if (iters_out) *iters_out = 0;
-    if (callbacks_out) *callbacks_out = 0;
-    if (B <= 0) return;
+    if (B <= 0) throw Error("pcg needs at least one right-hand side");
     const long M = pl->M;
     PcgDev st = pcg_state<T>(pl, B, tol, !precond);
     if (!pl->pinned) CK(cudaMallocHost(&pl->pinned, 64));
-    int* hflags = reinterpret_cast<int*>(pl->pinned);
     Geom<T>& g = geom(pl, false, Tag<T>());
     int nn[3];
     for (int d = 0; d < pl->D; ++d) nn[d] = pl->m[d];
-    T* r = pl->vr.as<T>(); T* p = pl->vp.as<T>(); T* z = precond ? pl->vz.as<T>() : r; T* Ap = pl->vAp.as<T>();
-
+    T* r = pl->vr.as<T>(); T* z = precond ? pl->vz.as<T>() : r;
     // x = 0 ; r = b - A(0) = b   (cg.py:58-59; the reference spends a matvec on the zero vector)
     CK(cudaMemsetAsync(x, 0, sizeof(T) * (size_t)(B * M), s));
     CK(cudaMemcpyAsync(r, b, sizeof(T) * (size_t)(B * M), cudaMemcpyDeviceToDevice, s));
@@ -728,39 +725,79 @@ static void pcg(hipgp_plan* pl, const void* b, void* x, long B, int maxiter, dou
     } else {         // z = r ; zr = r.r
         launch_vec<T>(pl, RF_SELFDOT, st, B, r, nullptr, nullptr, nullptr, s);
     }
+    pl->run_x = x; pl->run_B = B; pl->run_precond = precond; pl->run_tol = tol; pl->run_active = true;
+}
+
+// `niter` more iterations of the loop body cg.py:64-78 (kernels of a locally converged solve are no-ops)
+template <class T>
+static void pcg_iterate(hipgp_plan* pl, int niter, cudaStream_t s) {
+    if (!pl->run_active) throw Error("hipgp_pcg_step without hipgp_pcg_begin");
+    const long B = pl->run_B;
+    const bool precond = pl->run_precond;
+    PcgDev st = pcg_state<T>(pl, B, pl->run_tol, !precond);
+    Geom<T>& g = geom(pl, false, Tag<T>());
+    int nn[3];
+    for (int d = 0; d < pl->D; ++d) nn[d] = pl->m[d];
+    T* r = pl->vr.as<T>(); T* p = pl->vp.as<T>(); T* z = precond ? pl->vz.as<T>() : r; T* Ap = pl->vAp.as<T>();
+    void* x = pl->run_x;
+    RowsFusion ff, fi;
+    for (int c = 0; c < niter; ++c) {
+        // p = z + beta p ; Ap = K p ; pAp
+        ff = RowsFusion(); fi = RowsFusion();
+        ff.mode = RF_PUPDATE; ff.in = z; ff.v0 = p;
+        fi.mode = RI_DOT; fi.dot_kind = DOT_PAP; fi.out = Ap; fi.v0 = p;
+        run_pipeline<T>(pl, g, nn, nn, pl->specK.p, SPEC_REAL, B, ff, fi, st, true, s);
+        if (precond) {   // x += a p ; r -= a Ap ; rr ; stop test ; z = P r ; zr
+            ff = RowsFusion(); fi = RowsFusion();
+            ff.mode = RF_XRUPDATE; ff.in = Ap; ff.v0 = r; ff.v1 = x; ff.v2 = p;
+            fi.mode = RI_DOT; fi.dot_kind = DOT_ZR; fi.out = z; fi.v0 = r;
+            run_pipeline<T>(pl, g, nn, nn, pl->specCinv.p, SPEC_REAL, B, ff, fi, st, true, s);
+        } else {
+            launch_vec<T>(pl, RF_XRUPDATE, st, B, Ap, r, x, p, s);
+        }
+    }
+}
+
+// flags + residuals to the host (synchronises the stream)
+static void pcg_poll(hipgp_plan* pl, int* done, int* iters, double* max_resid, double* resid_out, cudaStream_t s) {
+    int* hflags = reinterpret_cast<int*>(pl->pinned);
+    CK(cudaMemcpyAsync(hflags, pl->flags.p, sizeof(int) * 4, cudaMemcpyDeviceToHost, s));
+    std::vector<double> rr;
+    if (max_resid || resid_out) {
+        rr.resize(pl->run_B);
+        CK(cudaMemcpyAsync(rr.data(), pl->scal.as<double>() + 3 * pl->run_B, sizeof(double) * pl->run_B, cudaMemcpyDeviceToHost, s));
+    }
+    CK(cudaStreamSynchronize(s));
+    if (done) *done = hflags[0];
+    if (iters) *iters = hflags[1];
+    if (max_resid) {
+        double mx = 0.0; bool nan = false;
+        for (double v : rr) { const double q = std::sqrt(v); if (q != q) nan = true; else if (q > mx) mx = q; }
+        *max_resid = nan ? NAN : mx;
+    }
+    if (resid_out) for (long i = 0; i < pl->run_B; ++i) resid_out[i] = std::sqrt(rr[i]);
+}
+
+template <class T>
+static void pcg(hipgp_plan* pl, const void* b, void* x, long B, int maxiter, double tol, bool precond, int* iters_out,
+                int* callbacks_out, double* resid_out, hipgp_iter_cb cb, void* user, cudaStream_t s) {
+    if (iters_out) *iters_out = 0;
+    if (callbacks_out) *callbacks_out = 0;
+    if (B <= 0) return;
+    pcg_begin<T>(pl, b, x, B, tol, precond, s);
     const int check_every = cb ? 1 : 8;
     int done = 0, iters = 0, n = 0;
     while (n < maxiter && !done) {
         const int chunk = std::min(check_every, maxiter - n);
-        for (int c = 0; c < chunk; ++c) {
-            // p = z + beta p ; Ap = K p ; pAp
-            ff = RowsFusion(); fi = RowsFusion();
-            ff.mode = RF_PUPDATE; ff.in = z; ff.v0 = p;
-            fi.mode = RI_DOT; fi.dot_kind = DOT_PAP; fi.out = Ap; fi.v0 = p;
-            run_pipeline<T>(pl, g, nn, nn, pl->specK.p, SPEC_REAL, B, ff, fi, st, true, s);
-            if (precond) {   // x += a p ; r -= a Ap ; rr ; stop test ; z = P r ; zr
-                ff = RowsFusion(); fi = RowsFusion();
-                ff.mode = RF_XRUPDATE; ff.in = Ap; ff.v0 = r; ff.v1 = x; ff.v2 = p;
-                fi.mode = RI_DOT; fi.dot_kind = DOT_ZR; fi.out = z; fi.v0 = r;
-                run_pipeline<T>(pl, g, nn, nn, pl->specCinv.p, SPEC_REAL, B, ff, fi, st, true, s);
-            } else {
-                launch_vec<T>(pl, RF_XRUPDATE, st, B, Ap, r, x, p, s);
-            }
-        }
-        CK(cudaMemcpyAsync(hflags, st.flags, sizeof(int) * 4, cudaMemcpyDeviceToHost, s));
-        CK(cudaStreamSynchronize(s));
-        done = hflags[0]; iters = hflags[1];
+        pcg_iterate<T>(pl, chunk, s);
+        pcg_poll(pl, &done, &iters, nullptr, nullptr, s);
         n += chunk;
         if (cb && !done) cb(n - 1, x, user);
     }
     if (iters_out) *iters_out = iters;
     if (callbacks_out) *callbacks_out = done ? iters - 1 : iters;
-    if (resid_out) {
-        std::vector<double> rr(B);
-        CK(cudaMemcpyAsync(rr.data(), st.rr, sizeof(double) * B, cudaMemcpyDeviceToHost, s));
-        CK(cudaStreamSynchronize(s));
-        for (long i = 0; i < B; ++i) resid_out[i] = std::sqrt(rr[i]);
-    }
+    if (resid_out) pcg_poll(pl, nullptr, nullptr, nullptr, resid_out, s);
+    pl->run_active = false;
 }
 
 }  // namespace hipgp
@@ -900,6 +937,23 @@ int hipgp_pcg(hipgp_plan* pl, const void* b, void* x, int64_t B, int maxiter, do
     cudaStream_t s = (cudaStream_t)stream;
     DISPATCH(pl, pcg<float>(pl, b, x, (long)B, maxiter, tol, precond != 0, iters_out, callbacks_out, resid_out, cb, user, s),
              pcg<double>(pl, b, x, (long)B, maxiter, tol, precond != 0, iters_out, callbacks_out, resid_out, cb, user, s));
+    API_END
+}
+
+int hipgp_pcg_begin(hipgp_plan* pl, const void* b, void* x, int64_t B, double tol, int precond, void* stream) {
+    API_BEGIN
+    set_device(pl);
+    cudaStream_t s = (cudaStream_t)stream;
+    DISPATCH(pl, pcg_begin<float>(pl, b, x, (long)B, tol, precond != 0, s), pcg_begin<double>(pl, b, x, (long)B, tol, precond != 0, s));
+    API_END
+}
+
+int hipgp_pcg_step(hipgp_plan* pl, int niter, int* done_out, int* iters_out, double* max_resid_out, void* stream) {
+    API_BEGIN
+    set_device(pl);
+    cudaStream_t s = (cudaStream_t)stream;
+    DISPATCH(pl, pcg_iterate<float>(pl, niter, s), pcg_iterate<double>(pl, niter, s));
+    if (done_out || iters_out || max_resid_out) pcg_poll(pl, done_out, iters_out, max_resid_out, nullptr, s);
     API_END
 }
 

@@ -13,6 +13,8 @@ from torch import nn
 
 from .toeplitz_tensor import ToeplitzTensor
 from . import kernels as hk
+from . import dist as hdist
+from .plan import meanfield_rowstats, meanfield_colstats
 
 
 class _GridKernelFn:
@@ -110,3 +112,108 @@ class ToeplitzInducingGP(nn.Module):
             Knm = self.kernel.forward_grid(xbatch, self.xgrids, kern_params)
             Knn_diag = self.kernel.diag(xbatch, kern_params)
         return Knm, Knn_diag
+
+
+class MeanFieldToeplitzGP(ToeplitzInducingGP):
+    """Mean-field variational family (ziggy/hipgp.py:449-524) with the natural-gradient step of
+    `elbo_and_grad` (hipgp.py:194-276).  When torch.distributed is initialised the minibatch is sharded over the ranks
+    and the statistics are combined with one packed all-reduce, so every rank ends the step with identical gradients."""
+
+    def __init__(self, kernel, xgrids, num_obs, sig2_init=1., ell_init=.05, noise2_init=1., init_Svar=.1, learn_kernel=False,
+                 learn_noise=False, dtype=torch.float, whitened_type='ziggy', parameterization='expectation-family',
+                 jitter_val=1e-3):
+        super(MeanFieldToeplitzGP, self).__init__(kernel, xgrids, num_obs, sig2_init=sig2_init, ell_init=ell_init,
+                                                  noise2_init=noise2_init, learn_kernel=learn_kernel, learn_noise=learn_noise,
+                                                  dtype=dtype, whitened_type=whitened_type, parameterization=parameterization,
+                                                  jitter_val=jitter_val)
+        if self.parameterization == 'standard':
+            self.global_m = nn.Parameter(torch.nn.init.xavier_normal_(torch.zeros(self.Mprime, 1, dtype=self.dtype)))
+            self.global_S = nn.Parameter(init_Svar * torch.ones(self.Mprime, 1, dtype=self.dtype))
+        else:
+            self.global_theta1 = nn.Parameter(torch.nn.init.xavier_normal_(torch.zeros(self.Mprime, 1, dtype=self.dtype)))
+            self.global_theta2 = nn.Parameter((-.5 / init_Svar) * torch.ones(self.Mprime, 1, dtype=self.dtype))
+
+    @property
+    def name(self):
+        return 'mean-field'
+
+    def standard_variational_params(self):
+        if self.parameterization == 'standard':
+            return self.global_m, self.global_S
+        S = -0.5 * 1 / self.global_theta2
+        m = S * self.global_theta1
+        return m, S
+
+    def get_kl_to_prior(self, qm=None, qS=None):
+        if qm is None or qS is None:
+            qm, qS = self.standard_variational_params()
+        return .5 * (torch.sum(qS) + torch.sum(qm * qm) - torch.sum(torch.log(qS)) - len(qm))   # stats.py:4-8
+
+    def compute_knSkn(self, kn, qS):
+        return meanfield_rowstats(kn, torch.zeros_like(qS), qS)[2]
+
+    def _row_stats(self, kn, qm, qS):
+        return meanfield_rowstats(kn, qm, qS)      # knt_m, knt_kn, knSkn
+
+    def elbo_and_grad(self, xbatch, ybatch, noise_std_batch=None, maxiter_cg=10, integrated_obs=False,
+                      semi_integrated_estimator="analytic", semi_integrated_samps=10, print_debug_info=False, Kmm=None,
+                      shard=True):
+        """ELBO estimate and natural gradient for the global parameters (hipgp.py:194-276, mean-field branch).
+        xbatch (bsz, D), ybatch (bsz, 1), noise_std_batch None or (bsz, 1): the GLOBAL minibatch on every rank; with
+        `shard` and an initialised process group each rank works on its contiguous slice."""
+        assert self.parameterization == 'expectation-family', \
+            "need parameterization=expectation-family when performing natural gradient descent"
+        bsz = xbatch.shape[0]
+        sl = hdist.shard_slice(bsz) if (shard and hdist.is_dist()) else slice(0, bsz)
+        xb, yb = xbatch[sl], ybatch[sl]
+        nb = noise_std_batch[sl] if noise_std_batch is not None else None
+        with torch.no_grad():
+            Knm, Knn_diag = self._make_grams(xb, integrated_obs=integrated_obs,
+                                             semi_integrated_estimator=semi_integrated_estimator,
+                                             semi_integrated_samps=semi_integrated_samps)
+            kn = self.compute_kn(Knm, maxiter_cg=maxiter_cg, Kmm=Kmm)
+            qm, qS = self.standard_variational_params()
+            knt_m, knt_kn, knSkn = self._row_stats(kn, qm, qS)
+            y = yb.reshape(-1)
+            if nb is not None:
+                ivar_noise = (1 / (nb ** 2)).reshape(-1)
+                log_noise_std = torch.log(nb).reshape(-1)
+            else:
+                ivar_noise = torch.exp(-self.log_noise2) * torch.ones_like(y)
+                log_noise_std = 0.5 * self.log_noise2
+            # compute_batch_an, hipgp.py:370-414
+            mse = (knt_m - y) ** 2
+            variance = Knn_diag.reshape(-1) - knt_kn + knSkn
+            batch_an = -0.5 * ivar_noise * (mse + variance) - log_noise_std - 0.5 * np.log(2 * np.pi)
+            # natural-gradient statistics, hipgp.py:241-250
+            bdiff = ivar_noise * (knt_m - y)
+            dm_sum, lam_sum = meanfield_colstats(kn, bdiff, ivar_noise)
+            an_sum = batch_an.sum().reshape(1)
+            hdist.allreduce_packed([dm_sum, lam_sum, an_sum])          # the one data-path collective of the step
+            bscale = self.N / bsz
+            data_dm = -dm_sum[:, None]
+            dm = bscale * data_dm - qm
+            lam_diag = bscale * lam_sum + 1
+            dS = -.5 * lam_diag[:, None] - self.global_theta2.data
+            deta1 = dm + dS * (-2 * qm)
+            deta2 = dS
+            self.global_theta1.grad = -deta1
+            self.global_theta2.grad = -deta2
+            kl_to_prior = self.get_kl_to_prior(qm, qS)
+            elbo_estimate = an_sum[0] / bsz - (kl_to_prior / self.N)
+        return elbo_estimate
+
+    def predict(self, x, integrated_obs=False, semi_integrated_estimator="analytic", semi_integrated_samps=10,
+                maxiter_cg=50, Kmm=None):
+        """E[f(x)] and sd[f(x)] (hipgp.py:416-446)"""
+        x = x.to(self.xgrids[0].device)
+        with torch.no_grad():
+            Knm, Knn_diag = self._make_grams(x, integrated_obs=integrated_obs,
+                                             semi_integrated_estimator=semi_integrated_estimator,
+                                             semi_integrated_samps=semi_integrated_samps)
+            kn = self.compute_kn(Knm, maxiter_cg=maxiter_cg, Kmm=Kmm)
+            qm, qS = self.standard_variational_params()
+            knt_m, knt_kn, knSkn = self._row_stats(kn, qm, qS)
+            ktilde_star = (Knn_diag.reshape(-1) - knt_kn).clamp_min(1e-5)
+            sig_star = torch.sqrt(ktilde_star + knSkn)[:, None]
+        return knt_m[:, None].cpu().detach(), sig_star.cpu().detach()

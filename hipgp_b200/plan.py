@@ -171,3 +171,52 @@ class Plan:
                                                                 1 if (reset and i == len(names) - 1) else 0))
             out[nm] = (ms.value, n.value)
         return out
+
+    # ---- PCG split in two for callers that own the stopping rule (multi-GPU sharded minibatches) ----
+    def pcg_begin(self, b, tol=-1.0, precond=True):
+        v = self._vec(b, self.M, "b")
+        x = torch.empty_like(v)
+        self._run = (v, x)                      # keep both alive while the solve is in flight
+        with torch.cuda.device(self.device):
+            L.check(self.lib, self.lib.hipgp_pcg_begin(self._h, C.c_void_p(v.data_ptr()), C.c_void_p(x.data_ptr()), v.shape[0],
+                                                        float(tol), 1 if precond else 0, _stream_ptr(self.device)))
+        return x
+
+    def pcg_step(self, niter=1, poll=True):
+        """`niter` more iterations; returns (done, iters, max_b sqrt(r.r)) of this rank when `poll`."""
+        done, iters, mx = C.c_int(), C.c_int(), C.c_double()
+        with torch.cuda.device(self.device):
+            if poll:
+                L.check(self.lib, self.lib.hipgp_pcg_step(self._h, int(niter), C.byref(done), C.byref(iters), C.byref(mx),
+                                                           _stream_ptr(self.device)))
+                return bool(done.value), iters.value, mx.value
+            L.check(self.lib, self.lib.hipgp_pcg_step(self._h, int(niter), None, None, None, _stream_ptr(self.device)))
+        return None
+
+
+def meanfield_rowstats(kn, qm, qS):
+    """(kn.qm, kn.kn, kn^2.qS) per row of kn (B, M'): hipgp.py:395-397,524.  Returns a (3, B) tensor."""
+    _require_cuda(kn, "kn")
+    lib = L.load()
+    kn = kn.contiguous(); qm = qm.reshape(-1).to(kn.dtype).contiguous(); qS = qS.reshape(-1).to(kn.dtype).contiguous()
+    B, E = kn.shape
+    out = torch.empty((3, B), dtype=kn.dtype, device=kn.device)
+    with torch.cuda.device(kn.device):
+        L.check(lib, lib.hipgp_meanfield_rowstats(_DT[kn.dtype], C.c_void_p(kn.data_ptr()), C.c_void_p(qm.data_ptr()),
+                                                  C.c_void_p(qS.data_ptr()), B, E, C.c_void_p(out.data_ptr()),
+                                                  _stream_ptr(kn.device)))
+    return out
+
+
+def meanfield_colstats(kn, w1, w2):
+    """(sum_b w1_b kn[b,:], sum_b w2_b kn[b,:]^2): hipgp.py:241-250.  Returns two (M',) tensors."""
+    _require_cuda(kn, "kn")
+    lib = L.load()
+    kn = kn.contiguous(); w1 = w1.reshape(-1).to(kn.dtype).contiguous(); w2 = w2.reshape(-1).to(kn.dtype).contiguous()
+    B, E = kn.shape
+    dm = torch.empty(E, dtype=kn.dtype, device=kn.device); lam = torch.empty_like(dm)
+    with torch.cuda.device(kn.device):
+        L.check(lib, lib.hipgp_meanfield_colstats(_DT[kn.dtype], C.c_void_p(kn.data_ptr()), C.c_void_p(w1.data_ptr()),
+                                                  C.c_void_p(w2.data_ptr()), B, E, C.c_void_p(dm.data_ptr()),
+                                                  C.c_void_p(lam.data_ptr()), _stream_ptr(kn.device)))
+    return dm, lam

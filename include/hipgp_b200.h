@@ -75,6 +75,12 @@ int hipgp_matvec_host(hipgp_plan* plan, int mode, const void* in_host, void* out
 typedef void (*hipgp_iter_cb)(int n, const void* x_dev, void* user);
 int hipgp_pcg(hipgp_plan* plan, const void* b_dev, void* x_dev, int64_t B, int maxiter, double tol, int precond,
               int* iters_out, int* callbacks_out, double* resid_out, hipgp_iter_cb cb, void* user, void* stream);
+/* the same solve split in two, for callers that own the stopping rule (a minibatch sharded over several GPUs must
+ * stop on all_b over ALL ranks, cg.py:70): begin = everything before the loop; step = `niter` more iterations, then
+ * (if any out pointer is given) a stream sync and done flag / iteration count / max_b sqrt(r_b.r_b) of this rank.
+ * Pass tol < 0 to begin to disable the local stopping test. */
+int hipgp_pcg_begin(hipgp_plan* plan, const void* b_dev, void* x_dev, int64_t B, double tol, int precond, void* stream);
+int hipgp_pcg_step(hipgp_plan* plan, int niter, int* done_out, int* iters_out, double* max_resid_out, void* stream);
 int hipgp_pcg_host(hipgp_plan* plan, const void* b_host, void* x_host, int64_t B, int maxiter, double tol, int precond,
                    int* iters_out, int* callbacks_out, double* resid_out, void* stream);
 /* k_n = R^T K^-1 K_un  (ziggy/hipgp.py:139-146): PCG(precond) followed by R^T.  Knm (B,M) -> kn (B,M') */
@@ -107,6 +113,14 @@ int hipgp_kernel_pairwise(int dtype, int kernel_id, int mode, double sig2, const
 int hipgp_doubly_diag(int dtype, const void* x_dev, int64_t B, int ndim, double sig2, const double* ell, int n_ell,
                       const void* distance_grid_dev, const void* slopes_dev, const void* knn_dev, int ntab,
                       void* out_dev, void* stream);
+
+/* ---- mean-field natural-gradient reductions over k_n (B, M') (ziggy/hipgp.py:241-250,395-397,439,524).
+ * rowstats: out[0][b] = k_n[b].qm, out[1][b] = k_n[b].k_n[b], out[2][b] = sum_j k_n[b,j]^2 qS[j]   (3 x B, plan dtype)
+ * colstats: dm[j] = sum_b w1[b] k_n[b,j], lam[j] = sum_b w2[b] k_n[b,j]^2                       (M' each) */
+int hipgp_meanfield_rowstats(int dtype, const void* kn_dev, const void* qm_dev, const void* qS_dev, int64_t B, int64_t E,
+                             void* out_dev, void* stream);
+int hipgp_meanfield_colstats(int dtype, const void* kn_dev, const void* w1_dev, const void* w2_dev, int64_t B, int64_t E,
+                             void* dm_dev, void* lam_dev, void* stream);
 
 /* bytes of device memory the plan currently owns (spectra, twiddles, workspace) */
 int hipgp_plan_device_bytes(const hipgp_plan* plan, size_t* bytes);

@@ -344,3 +344,34 @@ def meshgrid_points(xgrids):
     """hipgp.py:63-65"""
     xxs = torch.meshgrid(*xgrids, indexing="ij")
     return torch.stack([x.reshape(-1) for x in xxs], dim=-1)
+
+
+def meanfield_elbo_and_grad(xgrids, kfun, Knm, Knn_diag, ybatch, noise_std_batch, theta1, theta2, num_obs, maxiter_cg=10,
+                            jitter_val=1e-3):
+    """hipgp.py:194-276 (mean-field branch) + compute_batch_an (hipgp.py:370-414) + stats.diag_kl_to_standard.
+    Returns (elbo_estimate, theta1.grad, theta2.grad)."""
+    kn = compute_kn(xgrids, kfun, Knm, maxiter_cg=maxiter_cg, jitter_val=jitter_val)
+    qS = -0.5 * 1 / theta2                      # hipgp.py:499-503
+    qm = qS * theta1
+    y = ybatch.squeeze()
+    Knn = Knn_diag.squeeze()
+    knt_kn = torch.sum(kn * kn, dim=-1).squeeze()
+    knt_m = kn.matmul(qm).squeeze()
+    knSkn = torch.sum((kn * qS.t()) * kn, dim=-1).squeeze()
+    ivar = (1 / (noise_std_batch ** 2)).squeeze()
+    log_noise_std = torch.log(noise_std_batch)
+    mse = (knt_m - y) ** 2
+    variance = Knn - knt_kn + knSkn
+    batch_an = -0.5 * ivar * (mse + variance) - log_noise_std - 0.5 * np.log(2 * np.pi)
+    kl = .5 * (torch.sum(qS) + torch.sum(qm * qm) - torch.sum(torch.log(qS)) - len(qm))
+    elbo = torch.mean(batch_an) - (kl / num_obs)
+    bscale = num_obs / Knm.shape[0]
+    ivar_noise = (1 / (noise_std_batch ** 2))
+    knt_m2 = kn.matmul(qm)
+    bdiff = ivar_noise * (knt_m2 - ybatch)
+    data_dm = -torch.matmul(bdiff.t(), kn).t()
+    dm = bscale * data_dm - qm
+    lam_diag = bscale * torch.sum(ivar_noise * kn * kn, dim=0) + 1
+    dS = -.5 * lam_diag[:, None] - theta2
+    deta1 = dm + dS * (-2 * qm)
+    return elbo, -deta1, -dS

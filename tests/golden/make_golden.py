@@ -216,6 +216,28 @@ def make_compute_kn():
         np.savez_compressed(os.path.join(HERE, "compute_kn_%s.npz" % dname), **out)
 
 
+def make_svi_step():
+    """MeanFieldToeplitzGP.elbo_and_grad / predict (hipgp.py:194-276,416-446) on a small 2-D problem."""
+    for dname, dtype in DT.items():
+        torch.manual_seed(11)
+        grids = [(-5.7, 1.8, 14), (50., 55.5, 11)]
+        xgrids = [torch.linspace(lo, hi, m, dtype=dtype) for lo, hi, m in grids]
+        kern = get_kernel("matern32", dtype)
+        mod = zh.MeanFieldToeplitzGP(kern, xgrids, num_obs=500, sig2_init=0.9, ell_init=0.7, dtype=dtype, jitter_val=1e-3)
+        lo = torch.tensor([g[0] for g in grids], dtype=dtype); hi = torch.tensor([g[1] for g in grids], dtype=dtype)
+        xb = lo + (hi - lo) * torch.rand(8, 2, dtype=dtype)
+        yb = torch.randn(8, 1, dtype=dtype)
+        nb = 0.3 + 0.1 * torch.rand(8, 1, dtype=dtype)
+        th1 = mod.global_theta1.data.clone(); th2 = mod.global_theta2.data.clone()
+        elbo = mod.elbo_and_grad(xb, yb, nb, maxiter_cg=20)
+        mu, sig = mod.predict(xb, maxiter_cg=50)
+        np.savez_compressed(os.path.join(HERE, "svi_step_%s.npz" % dname), grids=np.array(grids), x=xb.numpy(), y=yb.numpy(),
+                            noise_std=nb.numpy(), theta1=th1.numpy(), theta2=th2.numpy(), elbo=float(elbo),
+                            g1=mod.global_theta1.grad.numpy(), g2=mod.global_theta2.grad.numpy(), mu=mu.numpy(), sig=sig.numpy(),
+                            params=np.array([0.9, 0.7, 1e-3, 500]))
+        print("svi_step", dname, float(elbo))
+
+
 def make_notebook_counts():
     """Saved cell outputs of experiments-hip-gp/preconditioner-analysis.ipynb -- the only numbers the
     reference repo pins (unseeded RNG there => reproducible to a few iterations only)."""
@@ -228,7 +250,11 @@ def make_notebook_counts():
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "svi":
+        make_svi_step()
+        sys.exit(0)
     make_notebook_counts()
+    make_svi_step()
     make_toeplitz()
     make_kernels()
     make_compute_kn()

@@ -1,0 +1,90 @@
+"""GPU parity of the mean-field natural-gradient step / predict (hipgp.py:194-276,416-446) against the golden vectors of
+the unmodified reference, the shard-additivity of its statistics, and the begin/step PCG with a caller-owned stop rule."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DT = {"f32": torch.float32, "f64": torch.float64}
+DEV = "cuda:0"
+
+
+def relerr(a, b):
+    if isinstance(a, torch.Tensor):
+        a = a.detach().cpu().numpy()
+    a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+
+
+def make_model(g, dtype):
+    from hipgp_b200 import hipgp as hh, kernels as hk
+    xgrids = [torch.linspace(lo, hi, int(m), dtype=dtype) for lo, hi, m in g["grids"]]
+    mod = hh.MeanFieldToeplitzGP(hk.Matern(nu=1.5, dtype=dtype), xgrids, num_obs=int(g["params"][3]),
+                                 sig2_init=float(g["params"][0]), ell_init=float(g["params"][1]), dtype=dtype,
+                                 jitter_val=float(g["params"][2])).cuda_params(0)
+    mod.global_theta1.data.copy_(torch.from_numpy(g["theta1"])); mod.global_theta2.data.copy_(torch.from_numpy(g["theta2"]))
+    return mod
+
+
+@pytest.mark.parametrize("dname", ["f32", "f64"])
+def test_meanfield_step_vs_reference(dname, golden_dir):
+    g = np.load(os.path.join(golden_dir, "svi_step_%s.npz" % dname))
+    dtype = DT[dname]
+    tol = 1e-6 if dname == "f64" else 2e-3
+    mod = make_model(g, dtype)
+    x = torch.from_numpy(g["x"]).to(DEV); y = torch.from_numpy(g["y"]).to(DEV); nb = torch.from_numpy(g["noise_std"]).to(DEV)
+    elbo = mod.elbo_and_grad(x, y, nb, maxiter_cg=20)
+    assert abs(float(elbo) - float(g["elbo"])) <= tol * abs(float(g["elbo"]))
+    assert relerr(mod.global_theta1.grad, g["g1"]) < tol
+    assert relerr(mod.global_theta2.grad, g["g2"]) < tol
+    mu, sig = mod.predict(x, maxiter_cg=50)
+    assert not mu.is_cuda and relerr(mu, g["mu"]) < tol and relerr(sig, g["sig"]) < tol
+    # one optimiser step exactly as svigp_fit does (SGD on theta with grad = -natural gradient, svi_gp.py:248,329)
+    opt = torch.optim.SGD([mod.global_theta1, mod.global_theta2], lr=1e-2)
+    opt.step()
+    want1 = g["theta1"] - 1e-2 * g["g1"]
+    assert relerr(mod.global_theta1.data, want1) < tol
+
+
+def test_shard_additivity_of_statistics(golden_dir):
+    """The packed all-reduce is exact because the statistics are sums over observations: two half-batches add up to
+    the full batch (what N ranks compute, emulated on one GPU)."""
+    from hipgp_b200.plan import meanfield_colstats, meanfield_rowstats
+    torch.manual_seed(0)
+    B, E = 10, 5000
+    kn = torch.randn(B, E, dtype=torch.float64, device=DEV)
+    w1 = torch.randn(B, dtype=torch.float64, device=DEV); w2 = torch.rand(B, dtype=torch.float64, device=DEV)
+    qm = torch.randn(E, dtype=torch.float64, device=DEV); qS = torch.rand(E, dtype=torch.float64, device=DEV)
+    dm, lam = meanfield_colstats(kn, w1, w2)
+    dm2 = sum(meanfield_colstats(kn[s], w1[s], w2[s])[0] for s in (slice(0, 4), slice(4, 10)))
+    lam2 = sum(meanfield_colstats(kn[s], w1[s], w2[s])[1] for s in (slice(0, 4), slice(4, 10)))
+    assert relerr(dm2, dm.cpu().numpy()) < 1e-13 and relerr(lam2, lam.cpu().numpy()) < 1e-13
+    assert relerr(dm, (w1[:, None] * kn).sum(0).cpu().numpy()) < 1e-13
+    rs = meanfield_rowstats(kn, qm, qS)
+    assert relerr(rs[0], (kn @ qm).cpu().numpy()) < 1e-12
+    assert relerr(rs[1], (kn * kn).sum(1).cpu().numpy()) < 1e-12
+    assert relerr(rs[2], (kn * kn * qS).sum(1).cpu().numpy()) < 1e-12
+
+
+def test_begin_step_pcg_matches_fused_solve(golden_dir):
+    """hipgp_pcg_begin/step with the stop rule evaluated by the caller reproduces hipgp_pcg (same iterates, same count);
+    a minibatch split in two shards with the GLOBAL rule stops both shards at the unsharded iteration."""
+    from hipgp_b200.plan import Plan
+    from hipgp_b200 import dist as hdist
+    g = np.load(os.path.join(golden_dir, "toeplitz_2d_25x25_matern52_f64.npz"), allow_pickle=True)
+    plan = Plan([25, 25], torch.float64, DEV).set_first_row(torch.from_numpy(g["column"]).to(DEV))
+    v = torch.from_numpy(g["v"]).to(DEV)
+    x_ref, info = plan.pcg(v, maxiter=500, tol=1e-10, return_info=True)
+    x, it = hdist.sharded_pcg(plan, v, maxiter=500, tol=1e-10)
+    assert it == info["iters"] and relerr(x, x_ref.cpu().numpy()) < 1e-14
+    # two shards, global rule: iterate both until max over shards < tol
+    plans = [Plan([25, 25], torch.float64, DEV).set_first_row(torch.from_numpy(g["column"]).to(DEV)) for _ in range(2)]
+    xs = [plans[0].pcg_begin(v[:1]), plans[1].pcg_begin(v[1:])]
+    for it2 in range(1, 501):
+        mx = max(plans[0].pcg_step(1)[2], plans[1].pcg_step(1)[2])
+        if mx < 1e-10:
+            break
+    assert it2 == info["iters"]
+    assert relerr(torch.cat(xs), x_ref.cpu().numpy()) < 1e-12

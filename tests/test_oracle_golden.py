@@ -160,3 +160,22 @@ def test_notebook_iteration_counts(golden_dir):
                 cnt[0] += 1
             zo.gram_solve([x1], kfun, vec, do_precond=True, tol=1e-10, maxiter=2000, callback=cb, mult_RT=False)
             assert abs(cnt[0] - int(want)) <= max(3, int(0.35 * want)), (kname, M, cnt[0], want)
+
+
+@pytest.mark.parametrize("dname", ["f32", "f64"])
+def test_meanfield_step(dname, golden_dir):
+    """hipgp.py:194-276 natural-gradient step of MeanFieldToeplitzGP, reference vs oracle restatement."""
+    g = np.load(os.path.join(golden_dir, "svi_step_%s.npz" % dname))
+    dtype = DT[dname]
+    xgrids = [torch.linspace(lo, hi, int(m), dtype=dtype) for lo, hi, m in g["grids"]]
+    sig2 = torch.tensor(float(g["params"][0]), dtype=dtype); ell = torch.tensor(float(g["params"][1]), dtype=dtype)
+    kfun = kernel_fn("matern32", sig2, ell)
+    x = torch.from_numpy(g["x"])
+    Knm = kfun(x, zo.meshgrid_points(xgrids))
+    Knn = sig2 * x.new_ones(x.shape[0])
+    elbo, g1, g2 = zo.meanfield_elbo_and_grad(xgrids, kfun, Knm, Knn, torch.from_numpy(g["y"]), torch.from_numpy(g["noise_std"]),
+                                              torch.from_numpy(g["theta1"]), torch.from_numpy(g["theta2"]),
+                                              num_obs=int(g["params"][3]), maxiter_cg=20, jitter_val=float(g["params"][2]))
+    tol = TIGHT[dname] * 50
+    assert abs(float(elbo) - float(g["elbo"])) <= tol * abs(float(g["elbo"]))
+    assert relerr(g1.numpy(), g["g1"]) < tol and relerr(g2.numpy(), g["g2"]) < tol
