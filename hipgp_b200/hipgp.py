@@ -164,7 +164,8 @@ class MeanFieldToeplitzGP(ToeplitzInducingGP):
         assert self.parameterization == 'expectation-family', \
             "need parameterization=expectation-family when performing natural gradient descent"
         bsz = xbatch.shape[0]
-        sl = hdist.shard_slice(bsz) if (shard and hdist.is_dist()) else slice(0, bsz)
+        sharded = bool(shard and hdist.is_dist())
+        sl = hdist.shard_slice(bsz) if sharded else slice(0, bsz)
         xb, yb = xbatch[sl], ybatch[sl]
         nb = noise_std_batch[sl] if noise_std_batch is not None else None
         with torch.no_grad():
@@ -189,7 +190,8 @@ class MeanFieldToeplitzGP(ToeplitzInducingGP):
             bdiff = ivar_noise * (knt_m - y)
             dm_sum, lam_sum = meanfield_colstats(kn, bdiff, ivar_noise)
             an_sum = batch_an.sum().reshape(1)
-            hdist.allreduce_packed([dm_sum, lam_sum, an_sum])          # the one data-path collective of the step
+            if sharded:
+                hdist.allreduce_packed([dm_sum, lam_sum, an_sum])      # the one data-path collective of the step
             bscale = self.N / bsz
             data_dm = -dm_sum[:, None]
             dm = bscale * data_dm - qm
