@@ -27,7 +27,7 @@ def _structured_owner(A_mul, precond):
     return None
 
 
-def _generic_cg(A_mul, b, precond, maxiter, tol, callback, to_rows, from_rows):
+def _generic_cg(A_mul, b, precond, maxiter, tol, callback, to_rows, from_rows, reduce=None):
     """b in the caller's layout; internally vectors are (bsz, M) contiguous rows."""
     if not b.is_cuda:
         raise RuntimeError("hipgp_b200.cg: tensors must be CUDA tensors (no CPU fallback)")
@@ -46,16 +46,21 @@ def _generic_cg(A_mul, b, precond, maxiter, tol, callback, to_rows, from_rows):
     p = z.clone()
     rs = torch.empty(B, dtype=torch.float64, device=dev); pAp = torch.empty_like(rs)
     rr = torch.empty_like(rs); zr = torch.empty_like(rs)
+    red = reduce if reduce is not None else (lambda t: t)      # sums the per-rank partial dot products (grid-sharded vectors)
     with torch.cuda.device(dev):
         L.check(lib, lib.hipgp_vec_dot(dt, p_(r), p_(z), p_(rs), B, M, st()))
+        red(rs)
         for n in range(maxiter):
             Ap = apply_A(p)
             L.check(lib, lib.hipgp_vec_dot(dt, p_(p), p_(Ap), p_(pAp), B, M, st()))
+            red(pAp)
             L.check(lib, lib.hipgp_vec_xr_update(dt, p_(x), p_(r), p_(p), p_(Ap), p_(rs), p_(pAp), p_(rr), B, M, st()))
+            red(rr)
             if bool(torch.all(torch.sqrt(rr) < tol)):
                 break
             z = apply_P(r)
             L.check(lib, lib.hipgp_vec_dot(dt, p_(z), p_(r), p_(zr), B, M, st()))
+            red(zr)
             L.check(lib, lib.hipgp_vec_p_update(dt, p_(p), p_(z), p_(zr), p_(rs), B, M, st()))
             rs, zr = zr, rs
             if callback is not None:
@@ -73,10 +78,11 @@ def conj_grad(A_mul, b, precond=None, maxiter=20, tol=1e-10, callback=None):
     return _generic_cg(A_mul, b, precond, maxiter, tol, callback, lambda t: t.t(), lambda t: t.t())
 
 
-def conj_grad2(A_mul, b, precond=None, maxiter=20, tol=1e-10, callback=None):
-    """A^{-1} b by (P)CG; b is (bsz, M) (cg.py:44-80)."""
-    s = _structured_owner(A_mul, precond)
+def conj_grad2(A_mul, b, precond=None, maxiter=20, tol=1e-10, callback=None, reduce=None):
+    """A^{-1} b by (P)CG; b is (bsz, M) (cg.py:44-80).  `reduce` (not in the reference) sums device scalars over ranks when
+    the vectors are sharded along the grid (slab decomposition)."""
+    s = _structured_owner(A_mul, precond) if reduce is None else None
     if s is not None:
         plan, use_p = s
         return plan.pcg(b, maxiter=maxiter, tol=tol, precond=use_p, callback=callback)
-    return _generic_cg(A_mul, b, precond, maxiter, tol, callback, lambda t: t, lambda t: t)
+    return _generic_cg(A_mul, b, precond, maxiter, tol, callback, lambda t: t, lambda t: t, reduce=reduce)

@@ -315,7 +315,14 @@ struct ColsParams {
     int mode;
     const void* spec; int spec_kind;   // FUSED: spectrum indexed [pos * pitch + line]
     const int* done_flag;         // optional PCG early-exit flag
+    // slab-decomposed grids: rows of the output (FWD) / input (INV) are scattered / gathered in blocks of `split_len`
+    // positions, `split_stride` elements apart, so that the pass writes (reads) the all-to-all buffer directly
+    int out_split_len; long out_split_stride;
+    int in_split_len; long in_split_stride;
 };
+template <class T> __device__ __forceinline__ size_t cols_rowoff(int i, long pitch, int split_len, long split_stride) {
+    return split_len ? (size_t)(i / split_len) * split_stride + (size_t)(i % split_len) * pitch : (size_t)i * pitch;
+}
 
 template <class T>
 __global__ void __launch_bounds__(512) cols_pass_kernel(ColsParams<T> P) {
@@ -333,7 +340,7 @@ __global__ void __launch_bounds__(512) cols_pass_kernel(ColsParams<T> P) {
     for (int w = tid; w < L * TB; w += nthreads) {
         const int c = w % TB, i = w / TB;
         cplx<T> v = mk<T>(0, 0);
-        if (i < rows_in && c < nc) v = in[(size_t)i * P.pitch + c];
+        if (i < rows_in && c < nc) v = in[cols_rowoff<T>(i, P.pitch, P.in_split_len, P.in_split_stride) + c];
         s[(size_t)i * TBP + c] = v;
     }
     __syncthreads();
@@ -351,7 +358,7 @@ __global__ void __launch_bounds__(512) cols_pass_kernel(ColsParams<T> P) {
     const int rows_out = P.mode == CM_FWD ? L : P.n_out;
     for (int w = tid; w < rows_out * TB; w += nthreads) {
         const int c = w % TB, i = w / TB;
-        if (c < nc) out[(size_t)i * P.pitch + c] = s[(size_t)i * TBP + c];
+        if (c < nc) out[cols_rowoff<T>(i, P.pitch, P.out_split_len, P.out_split_stride) + c] = s[(size_t)i * TBP + c];
     }
 }
 

@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(512) cols_fast_kernel(ColsParams<T> P) {
         for (int w = tid; w < Ln * TB; w += nthreads) {
             const int c = w % TB, i = w / TB;
             cplx<T>* d = s + (c * RS + rpad<T>(i));
-            if (i < rows_in && c < nc) cp_async<(int)sizeof(cplx<T>)>(d, in + ((size_t)i * pitch + c));
+            if (i < rows_in && c < nc) cp_async<(int)sizeof(cplx<T>)>(d, in + (cols_rowoff<T>(i, pitch, P.in_split_len, P.in_split_stride) + c));
             else *d = mk<T>(0, 0);
         }
         cp_async_wait_all();
@@ -234,7 +234,7 @@ __global__ void __launch_bounds__(512) cols_fast_kernel(ColsParams<T> P) {
         const int rows_out = mode == CM_FWD ? Ln : P.n_out;
         for (int w = tid; w < rows_out * TB; w += nthreads) {
             const int c = w % TB, i = w / TB;
-            if (c < nc) out[(size_t)i * pitch + c] = s[(size_t)c * RS + rpad<T>(i)];
+            if (c < nc) out[cols_rowoff<T>(i, pitch, P.out_split_len, P.out_split_stride) + c] = s[(size_t)c * RS + rpad<T>(i)];
         }
     }
 }

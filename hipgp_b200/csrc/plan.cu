@@ -229,6 +229,7 @@ struct hipgp_plan {
     DevBuf stage_in, stage_out;            // device staging for the *_host entry points
     void* pinned = nullptr;                // host flags mirror
     long pcg_B = 0;
+    int slab_rank = 0, slab_nranks = 1;      // slab-decomposed grid (axis 0 split over ranks); 1 = not decomposed
     void* run_x = nullptr; long run_B = 0; bool run_precond = true; double run_tol = 0; bool run_active = false;   // begin/step state
     // optional per-kernel-class timing (bench.py roofline): CUDA events around every launch
     bool profiling = false;
@@ -635,6 +636,79 @@ static void ensure_wide(hipgp_plan* pl, cudaStream_t s) {
 
 static PcgDev null_state() { PcgDev st{}; return st; }
 
+// ---- slab-decomposed 3-D matvec (K / C^-1), axis 0 split over `nranks` ranks -------------------------------
+// stage 1 (local)  : rows r2c + axis-1 forward on this rank's slab of n0/P planes, written straight into the all-to-all
+//                    send buffer [dest q][i0_loc][L1/P positions of axis 1][P3]
+// (all-to-all)     : every rank now holds ALL i0 for its chunk of (axis-1 position, bin) lines
+// stage 2 (local)  : axis-0 forward, spectrum multiply, axis-0 inverse on that chunk, in place; the result is already in
+//                    [dest q][i0_loc][chunk] order
+// (all-to-all back)
+// stage 3 (local)  : axis-1 inverse reading the receive buffer in place, rows c2r, crop
+struct SlabGeo { long n0_loc, Lq, chunk, P3, exch_elems; };
+template <class T>
+static SlabGeo slab_geo(hipgp_plan* pl, Geom<T>& g) {
+    SlabGeo q;
+    q.n0_loc = pl->m[0] / pl->slab_nranks;
+    q.Lq = g.L[1] / pl->slab_nranks;
+    q.P3 = g.P;
+    q.chunk = q.Lq * q.P3;
+    q.exch_elems = (long)pl->slab_nranks * q.n0_loc * q.chunk;
+    return q;
+}
+
+template <class T>
+static void slab_stage1(hipgp_plan* pl, const void* in_slab, void* send_buf, cudaStream_t s) {
+    Geom<T>& g = geom(pl, false, Tag<T>());
+    const SlabGeo q = slab_geo<T>(pl, g);
+    const long rows = q.n0_loc * pl->m[1];
+    pl->W1.ensure(sizeof(cplx<T>) * (size_t)rows * g.P, &pl->dev_bytes);
+    cplx<T>* W1 = pl->W1.as<cplx<T>>();
+    RowsParams<T> R{};
+    R.in = (const T*)in_slab; R.W = W1; R.L = g.L[2]; R.H = g.H; R.W_pitch = g.P; R.W_rows = (int)rows;
+    R.f = g.frow.dev; R.twL = g.twL.template as<cplx<T>>(); R.twLp = g.twLp.template as<cplx<T>>(); R.part = g.part.template as<int>();
+    R.mode = RF_PLAIN; R.do_fft = 1; R.total_rows = rows; R.nrows = (int)rows; R.n_real = pl->m[2]; R.st = null_state();
+    launch_rows<T>(pl, false, R, s);
+    ColsParams<T> C{};
+    C.in = W1; C.out = (cplx<T>*)send_buf; C.n_in = pl->m[1]; C.n_out = pl->m[1]; C.inner = g.H + 1; C.pitch = g.P;
+    C.in_ostride = (long)pl->m[1] * g.P; C.in_bstride = 0; C.out_ostride = q.chunk; C.out_bstride = 0;
+    C.out_split_len = (int)q.Lq; C.out_split_stride = q.n0_loc * q.chunk;
+    C.f = g.fcol[1].dev; C.mode = CM_FWD;
+    launch_cols<T>(pl, C, q.n0_loc, 1, s);
+}
+
+template <class T>
+static void slab_stage2(hipgp_plan* pl, int mode, void* buf, cudaStream_t s) {
+    Geom<T>& g = geom(pl, false, Tag<T>());
+    const SlabGeo q = slab_geo<T>(pl, g);
+    const bool transposed = !g_no_fast && !fast_radices(g.L[0]).empty();
+    if (!transposed) throw Error("slab mode needs a specialised column kernel for the axis-0 length");
+    const T* spec = (mode == HIPGP_MV_K ? pl->specK.as<T>() : pl->specCinv.as<T>()) + (size_t)pl->slab_rank * q.chunk * g.L[0];
+    ColsParams<T> C{};
+    C.in = (cplx<T>*)buf; C.out = (cplx<T>*)buf; C.n_in = pl->m[0]; C.n_out = pl->m[0]; C.inner = q.chunk; C.pitch = q.chunk;
+    C.f = g.fcol[0].dev; C.mode = CM_FUSED; C.spec = spec; C.spec_kind = SPEC_REAL;
+    launch_cols<T>(pl, C, 1, 1, s);
+}
+
+template <class T>
+static void slab_stage3(hipgp_plan* pl, const void* recv_buf, void* out_slab, cudaStream_t s) {
+    Geom<T>& g = geom(pl, false, Tag<T>());
+    const SlabGeo q = slab_geo<T>(pl, g);
+    const long rows = q.n0_loc * pl->m[1];
+    cplx<T>* W1 = pl->W1.as<cplx<T>>();
+    ColsParams<T> C{};
+    C.in = (const cplx<T>*)recv_buf; C.out = W1; C.n_in = pl->m[1]; C.n_out = pl->m[1]; C.inner = g.H + 1; C.pitch = g.P;
+    C.in_ostride = q.chunk; C.in_bstride = 0; C.out_ostride = (long)pl->m[1] * g.P; C.out_bstride = 0;
+    C.in_split_len = (int)q.Lq; C.in_split_stride = q.n0_loc * q.chunk;
+    C.f = g.fcol[1].dev; C.mode = CM_INV;
+    launch_cols<T>(pl, C, q.n0_loc, 1, s);
+    RowsParams<T> R{};
+    R.out = (T*)out_slab; R.W = W1; R.L = g.L[2]; R.H = g.H; R.W_pitch = g.P; R.W_rows = (int)rows;
+    R.f = g.frow.dev; R.twL = g.twL.template as<cplx<T>>(); R.twLp = g.twLp.template as<cplx<T>>(); R.part = g.part.template as<int>();
+    R.mode = RI_PLAIN; R.total_rows = rows; R.nrows = (int)rows; R.n_real = pl->m[2]; R.st = null_state();
+    R.spec = nullptr; R.spec_kind = SPEC_NONE;
+    launch_rows<T>(pl, true, R, s);
+}
+
 template <class T>
 static void matvec(hipgp_plan* pl, int mode, const void* in, void* out, long B, cudaStream_t s) {
     if (!pl->have_spec) throw Error("plan has no spectrum: call hipgp_plan_set_first_row first");
@@ -985,6 +1059,43 @@ int hipgp_compute_kn(hipgp_plan* pl, const void* Knm, void* kn, int64_t B, int m
     API_END
 }
 
+int hipgp_plan_set_slab(hipgp_plan* pl, int rank, int nranks) {
+    API_BEGIN
+    if (pl->D != 3) throw Error("slab decomposition needs a 3-D grid");
+    if (nranks < 1 || rank < 0 || rank >= nranks) throw Error("bad rank / nranks");
+    if (pl->m[0] % nranks) throw Error("grid extent of axis 0 must be divisible by the number of ranks");
+    if (pl->Ln[1] % nranks) throw Error("embedding length of axis 1 must be divisible by the number of ranks");
+    pl->slab_rank = rank; pl->slab_nranks = nranks;
+    API_END
+}
+int hipgp_slab_sizes(const hipgp_plan* pl, int64_t* slab_reals, int64_t* exchange_complex) {
+    API_BEGIN
+    const long n0 = pl->m[0] / pl->slab_nranks;
+    if (slab_reals) *slab_reals = n0 * pl->m[1] * pl->m[2];
+    const long P3 = ((long)pl->Ln[2] / 2 + 1 + 7) / 8 * 8;
+    if (exchange_complex) *exchange_complex = (long)pl->slab_nranks * n0 * (pl->Ln[1] / pl->slab_nranks) * P3;
+    API_END
+}
+int hipgp_slab_stage1(hipgp_plan* pl, const void* in_slab, void* send_buf, void* stream) {
+    API_BEGIN
+    set_device(pl);
+    if (!pl->have_spec) throw Error("plan has no spectrum");
+    DISPATCH(pl, slab_stage1<float>(pl, in_slab, send_buf, (cudaStream_t)stream), slab_stage1<double>(pl, in_slab, send_buf, (cudaStream_t)stream));
+    API_END
+}
+int hipgp_slab_stage2(hipgp_plan* pl, int mode, void* buf, void* stream) {
+    API_BEGIN
+    set_device(pl);
+    if (mode != HIPGP_MV_K && mode != HIPGP_MV_CINV) throw Error("slab mode supports K and C^-1");
+    DISPATCH(pl, slab_stage2<float>(pl, mode, buf, (cudaStream_t)stream), slab_stage2<double>(pl, mode, buf, (cudaStream_t)stream));
+    API_END
+}
+int hipgp_slab_stage3(hipgp_plan* pl, const void* recv_buf, void* out_slab, void* stream) {
+    API_BEGIN
+    set_device(pl);
+    DISPATCH(pl, slab_stage3<float>(pl, recv_buf, out_slab, (cudaStream_t)stream), slab_stage3<double>(pl, recv_buf, out_slab, (cudaStream_t)stream));
+    API_END
+}
 int hipgp_plan_profile(hipgp_plan* pl, int enable) {
     API_BEGIN
     pl->profiling = enable != 0;

@@ -122,6 +122,19 @@ int hipgp_meanfield_rowstats(int dtype, const void* kn_dev, const void* qm_dev, 
 int hipgp_meanfield_colstats(int dtype, const void* kn_dev, const void* w1_dev, const void* w2_dev, int64_t B, int64_t E,
                              void* dm_dev, void* lam_dev, void* stream);
 
+/* ---- slab-decomposed 3-D grids (axis 0 split over `nranks` GPUs; K and C^-1 matvecs; one right-hand side).
+ * The reference has no multi-GPU path; this is the grid-sharded route of SURVEY.md 8e.  A matvec is
+ *   stage1(in_slab -> send) ; all-to-all(send -> buf) ; stage2(mode, buf in place) ; all-to-all(buf -> recv) ;
+ *   stage3(recv -> out_slab)
+ * with the two all-to-alls issued by the caller (NCCL through torch.distributed); the passes next to them read / write
+ * the exchange buffers in their packed layout directly, so there is no separate pack / unpack kernel.
+ * Buffers: slab = (n0/nranks, m1, m2) reals; exchange = `exchange_complex` complex numbers. */
+int hipgp_plan_set_slab(hipgp_plan* plan, int rank, int nranks);
+int hipgp_slab_sizes(const hipgp_plan* plan, int64_t* slab_reals, int64_t* exchange_complex);
+int hipgp_slab_stage1(hipgp_plan* plan, const void* in_slab_dev, void* send_buf_dev, void* stream);
+int hipgp_slab_stage2(hipgp_plan* plan, int mode, void* buf_dev, void* stream);
+int hipgp_slab_stage3(hipgp_plan* plan, const void* recv_buf_dev, void* out_slab_dev, void* stream);
+
 /* bytes of device memory the plan currently owns (spectra, twiddles, workspace) */
 int hipgp_plan_device_bytes(const hipgp_plan* plan, size_t* bytes);
 /* number of kernel launches issued through this plan since creation (for bench accounting) */
