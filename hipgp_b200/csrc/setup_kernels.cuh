@@ -15,13 +15,15 @@ namespace hipgp {
 
 // out[o][k][i] = sum_j w_j in[o][j][i] cos(pi j k / (m-1)),  w_0 = w_{m-1} = 1, else 2.   (DCT-I, unnormalised;
 // applying it twice multiplies by N = 2(m-1)).  costab[t] = cos(pi t / (m-1)), t in [0, 2(m-1)).
-// grid: (ceil(inner/64), ceil(m/4), outer); block (64, 4)
+// block (bx, 256/bx) with bx = min(64, inner); grid.x = ceil(inner/bx) * outer (outer folded into x: no 65535 limit),
+// grid.y = ceil(m / blockDim.y)
 __global__ void __launch_bounds__(256) dct1_axis_kernel(const double* __restrict__ in, double* __restrict__ out,
-                                                        const double* __restrict__ costab, int m, long inner, double scale) {
-    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+                                                        const double* __restrict__ costab, int m, long inner, double scale, int nx) {
+    const long ob = blockIdx.x / nx, xb = blockIdx.x - ob * nx;
+    const long i = xb * blockDim.x + threadIdx.x;
     const int k = blockIdx.y * blockDim.y + threadIdx.y;
     if (i >= inner || k >= m) return;
-    const size_t o = (size_t)blockIdx.z * m * inner;
+    const size_t o = (size_t)ob * m * inner;
     const int N = 2 * (m - 1);
     double acc = 0.0;
     if (m == 1) {
