@@ -38,9 +38,19 @@ struct DevBuf {
 // Lengths with a compile-time specialised kernel family (fast_kernels.cuh) and their DIF radix lists.
 // X(length, radices...)
 #ifdef HIPGP_DEV_SMALL   /* quick developer / emulation builds: a handful of lengths, the rest takes the generic kernels */
-#define HIPGP_FAST_LIST_G0(X) X(2048, 16, 16, 8)
+#if defined(HIPGP_EXP) && HIPGP_EXP == 1
+#define HIPGP_EXP_R2048 8, 8, 8, 4
+#define HIPGP_EXP_R1024 8, 8, 4, 4
+#elif defined(HIPGP_EXP) && HIPGP_EXP == 2
+#define HIPGP_EXP_R2048 8, 16, 16
+#define HIPGP_EXP_R1024 8, 8, 16
+#else
+#define HIPGP_EXP_R2048 16, 16, 8
+#define HIPGP_EXP_R1024 16, 8, 8
+#endif
+#define HIPGP_FAST_LIST_G0(X) X(2048, HIPGP_EXP_R2048)
 #define HIPGP_FAST_LIST_G1(X) X(16, 16)
-#define HIPGP_FAST_LIST_G2(X) X(1024, 16, 8, 8) X(128, 16, 8)
+#define HIPGP_FAST_LIST_G2(X) X(1024, HIPGP_EXP_R1024) X(128, 16, 8)
 #define HIPGP_FAST_LIST_G3(X) X(64, 8, 8) X(32, 8, 4)
 #define HIPGP_FAST_LIST_G4(X)
 #else
