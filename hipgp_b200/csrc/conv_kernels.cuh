@@ -116,6 +116,7 @@ struct RowsParams {
     const cplx<T>* twL;   // exp(-2 pi i k / L), k < H
     const cplx<T>* twLp;  // twL in position order: twLp[q] = twL[rev[q]]
     const int* part;      // partner position of q in the r2c split: pos[H - rev[q]] (q > 0)
+    const int* pairq;     // the H/2 + 1 positions q with q <= part[q] (one per (k, H-k) pair), ascending
     int RB, RBP;          // rows per CTA, padded smem line count
     int mode, dot_kind, do_fft;
     int vec_ok;           // all row pointers are aligned for 2-element vector access
@@ -313,7 +314,8 @@ struct ColsParams {
     LineFft<T> f;                 // L-point complex FFT along the axis
     int TB, TBP;                  // lines per CTA, padded
     int mode;
-    const void* spec; int spec_kind;   // FUSED: spectrum indexed [pos * pitch + line]
+    const void* spec; int spec_kind;   // FUSED: spectrum indexed [pos * spec_pitch + line]
+    long spec_pitch;              // 0 = same as pitch
     const int* done_flag;         // optional PCG early-exit flag
     // slab-decomposed grids: rows of the output (FWD) / input (INV) are scattered / gathered in blocks of `split_len`
     // positions, `split_stride` elements apart, so that the pass writes (reads) the all-to-all buffer directly

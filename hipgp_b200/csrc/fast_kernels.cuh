@@ -1,247 +1,22 @@
-// fast_kernels.cuh -- compile-time specialised versions of the three matvec passes.
+// fast_kernels.cuh -- compile-time specialised versions of the three matvec passes on the lane engine (lane_fft.cuh).
 //
 // Same math and the same digit-reversed layouts as conv_kernels.cuh (the generic, runtime-radix kernels stay as the
-// fallback for lengths without an instantiation), but:
-//   * the radix list is a template parameter pack, so all index arithmetic is shifts / constant divisions;
-//   * radix-16 butterflies (4x4) cut the number of shared-memory sweeps;
-//   * a thread owns a BUTTERFLY and walks the lines of the tile with it: positions and twiddles (read once from a
-//     per-stage table laid out [r][j], i.e. coalesced) are loop invariants, so per line only the 2R shared-memory
-//     accesses and the butterfly arithmetic remain;
-//   * fp32 complex arithmetic uses Blackwell's packed FADD2/FMUL2/FFMA2 (fft_engine.cuh);
-//   * row passes: the first forward stage reads its operands straight from global memory (zero padding = predicated
-//     loads, PCG vector updates fused into those loads) and the last inverse stage writes straight to global memory
-//     (crop = predicated stores, dot products fused into those stores);
-//   * column pass: last forward stage, spectrum multiply and first inverse stage run back to back in registers; the
-//     spectrum is stored transposed ([line][position]) so that those reads are contiguous per thread;
-//   * shared memory is line-major, s[line][pad(pos)], with a padding function that keeps the strided stage accesses
-//     spread over the banks.
+// fallback for lengths without an instantiation).  What is different:
+//   * a thread owns (butterfly, lane): 16-byte lanes (two fp32 lines / one fp64 line), LDS.128 / STS.128 only, packed
+//     f32x2 arithmetic across the two lines of a lane, all butterfly legs at [base + immediate];
+//   * the first forward stage reads its operands straight from global memory (zero padding = skipped loads and a
+//     pruned butterfly when the upper half of the inputs is padding; PCG vector updates fused into the row loads) and
+//     the last inverse stage writes straight to global memory (crop = skipped stores, dot products fused);
+//   * column pass: last forward stage, spectrum multiply and first inverse stage run back to back in registers;
+//   * row passes: the r2c split / c2r merge works on (k, H-k) PAIRS (one thread produces both members from one pair of
+//     shared-memory reads) straight to / from global memory;
+//   * tiles are small (64-72 KB) so that two or three CTAs are resident per SM and one CTA's global traffic overlaps
+//     another's butterflies.
 #pragma once
-#include "conv_kernels.cuh"
+#include "lane_fft.cuh"
 
 namespace hipgp {
 
-// ---- asynchronous global -> shared copies (LDGSTS): no register staging, all requests in flight at once ----
-template <int BYTES> __device__ __forceinline__ void cp_async(void* smem_dst, const void* gmem_src) {
-#ifdef HIPGP_EMU
-    std::memcpy(smem_dst, gmem_src, BYTES);
-#else
-    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
-    if (BYTES == 16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem_src));
-    else asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gmem_src));
-#endif
-}
-__device__ __forceinline__ void cp_async_wait_all() {
-#ifndef HIPGP_EMU
-    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
-#endif
-}
-
-template <int... Rs> struct RL {};
-template <class L> struct RLInfo;
-template <> struct RLInfo<RL<>> { static constexpr int N = 1; static constexpr int count = 0; };
-template <int R0, int... Rs> struct RLInfo<RL<R0, Rs...>> {
-    static constexpr int N = R0 * RLInfo<RL<Rs...>>::N;
-    static constexpr int count = 1 + RLInfo<RL<Rs...>>::count;
-};
-template <class L> struct RLLast;
-template <int R0> struct RLLast<RL<R0>> { static constexpr int value = R0; };
-template <int R0, int R1, int... Rs> struct RLLast<RL<R0, R1, Rs...>> { static constexpr int value = RLLast<RL<R1, Rs...>>::value; };
-
-// padding of a position inside a line: keeps stride-2^k butterflies of neighbouring threads on distinct banks
-template <class T> __host__ __device__ constexpr int rpad(int pos) {
-    return sizeof(T) == 4 ? pos + (pos >> 4) : pos + (pos >> 3) + (pos >> 6);
-}
-template <class T> __host__ __device__ constexpr int line_stride(int L) {
-    // == 2 (mod 16) complex slots: in the column pass the TB lines of one position (and the next position) fall on
-    // disjoint banks during the lines-fast copy in / copy out
-    return ((rpad<T>(L) + 15) / 16) * 16 + 2;
-}
-__host__ __device__ constexpr bool is_pow2(int x) { return (x & (x - 1)) == 0; }
-// padded offset of element r of a butterfly starting at p0 with stride S inside a sub-transform of length Nt.
-// For power-of-two Nt the padding is additive (no carries between p0's and r*S's low bits), so the offsets relative
-// to rpad(p0) are compile-time constants and every access is [register + immediate].
-template <class T, int Nt, int S> __device__ __forceinline__ int boff(int rp0, int p0, int r) {
-    return is_pow2(Nt) ? rp0 + rpad<T>(r * S) : rpad<T>(p0 + r * S);
-}
-
-// per-stage twiddles w^{j r}, r = 1..R-1 (conjugated for the inverse), from the [r][j] table
-template <int R, int S, bool INV, class T>
-__device__ __forceinline__ void load_twiddles(cplx<T>* w, const cplx<T>* __restrict__ tab, int j) {
-#pragma unroll
-    for (int r = 1; r < R; ++r) { w[r] = ldg_c(tab + (r - 1) * S + j); if (INV) w[r] = conj(w[r]); }
-}
-
-// ---- one in-place shared-memory stage over `nlines` lines, compile-time geometry -------------------------
-// thread -> (butterfly bf, line group g); the thread applies its butterfly to lines g, g+G, ...
-template <class T, int Ln, int Nt, int R, bool INV>
-__device__ __forceinline__ void smem_stage(cplx<T>* s, int RS, int nlines, const cplx<T>* __restrict__ twtab, int tid, int nthreads) {
-    constexpr int S = Nt / R, NB = Ln / R;
-    auto process = [&](int bf, int g, int G) {
-        const int blk = bf / S, j = bf - blk * S;
-        const int p0 = blk * Nt + j;
-        const int rp0 = rpad<T>(p0);
-        int o[R];
-#pragma unroll
-        for (int r = 0; r < R; ++r) o[r] = boff<T, Nt, S>(0, p0, r) - (is_pow2(Nt) ? 0 : rp0);
-        cplx<T> w[R];
-        const bool tw_on = (S > 1) && (j != 0);
-        if (S > 1) load_twiddles<R, S, INV>(w, twtab, j);
-        for (int line = g; line < nlines; line += G) {
-            cplx<T>* base = s + (line * RS + rp0);
-            cplx<T> v[R];
-#pragma unroll
-            for (int r = 0; r < R; ++r) v[r] = base[o[r]];
-            if (INV) {
-                if (tw_on) {
-#pragma unroll
-                    for (int r = 1; r < R; ++r) v[r] = v[r] * w[r];
-                }
-                bfly<R, true>(v);
-            } else {
-                bfly<R, false>(v);
-                if (tw_on) {
-#pragma unroll
-                    for (int r = 1; r < R; ++r) v[r] = v[r] * w[r];
-                }
-            }
-#pragma unroll
-            for (int r = 0; r < R; ++r) base[o[r]] = v[r];
-        }
-    };
-    if (nthreads >= NB) {
-        const int G = nthreads / NB, g = tid / NB;
-        if (g < G) process(tid % NB, g, G);
-    } else {
-        for (int bf = tid; bf < NB; bf += nthreads) process(bf, 0, 1);
-    }
-}
-
-// middle DIF stages (all but the first and the last of the list), each followed by a barrier.  STG = stage index.
-template <class T, int Ln, int Nt, int STG, int... Rs> struct MidFwd;
-template <class T, int Ln, int Nt, int STG, int R0> struct MidFwd<T, Ln, Nt, STG, R0> {
-    static __device__ __forceinline__ void run(cplx<T>*, int, int, const LineFft<T>&, int, int) {}
-};
-template <class T, int Ln, int Nt, int STG, int R0, int R1, int... Rs> struct MidFwd<T, Ln, Nt, STG, R0, R1, Rs...> {
-    static __device__ __forceinline__ void run(cplx<T>* s, int RS, int nl, const LineFft<T>& f, int tid, int nth) {
-        smem_stage<T, Ln, Nt, R0, false>(s, RS, nl, f.twst + f.twoff[STG], tid, nth);
-        __syncthreads();
-        MidFwd<T, Ln, Nt / R0, STG + 1, R1, Rs...>::run(s, RS, nl, f, tid, nth);
-    }
-};
-template <class T, int Ln, int Nt, int STG, int... Rs> struct MidInv;
-template <class T, int Ln, int Nt, int STG, int R0> struct MidInv<T, Ln, Nt, STG, R0> {
-    static __device__ __forceinline__ void run(cplx<T>*, int, int, const LineFft<T>&, int, int) {}
-};
-template <class T, int Ln, int Nt, int STG, int R0, int R1, int... Rs> struct MidInv<T, Ln, Nt, STG, R0, R1, Rs...> {
-    static __device__ __forceinline__ void run(cplx<T>* s, int RS, int nl, const LineFft<T>& f, int tid, int nth) {
-        MidInv<T, Ln, Nt / R0, STG + 1, R1, Rs...>::run(s, RS, nl, f, tid, nth);
-        smem_stage<T, Ln, Nt, R0, true>(s, RS, nl, f.twst + f.twoff[STG], tid, nth);
-        __syncthreads();
-    }
-};
-
-// =====================================================================================================
-// Column pass.  Radix list <R0, Rmid..., RLAST>; TB lines per CTA.
-// =====================================================================================================
-template <class T, int TB, int R0, int... Rs>
-__global__ void __launch_bounds__(512) cols_fast_kernel(ColsParams<T> P) {
-    using List = RL<R0, Rs...>;
-    constexpr int Ln = RLInfo<List>::N;
-    constexpr int NST = RLInfo<List>::count;
-    constexpr int RLAST = RLLast<List>::value;
-    constexpr int RS = line_stride<T>(Ln);
-    HIPGP_DYN_SMEM(smem_raw);
-    cplx<T>* s = reinterpret_cast<cplx<T>*>(smem_raw);
-    const int tid = threadIdx.x, nthreads = blockDim.x;
-    if (P.done_flag && *P.done_flag) return;
-    const long c0 = (long)blockIdx.x * TB;
-    const int nc = (int)(P.inner - c0 < TB ? P.inner - c0 : TB);
-    const cplx<T>* in = P.in + (size_t)blockIdx.y * P.in_ostride + (size_t)blockIdx.z * P.in_bstride + c0;
-    cplx<T>* out = P.out + (size_t)blockIdx.y * P.out_ostride + (size_t)blockIdx.z * P.out_bstride + c0;
-    const long pitch = P.pitch;
-    const int mode = P.mode;
-
-    // ---- copy in (lines fast => TB contiguous elements per row), zero padding ----
-    {
-        const int rows_in = mode == CM_INV ? Ln : P.n_in;
-        for (int w = tid; w < Ln * TB; w += nthreads) {
-            const int c = w % TB, i = w / TB;
-            cplx<T>* d = s + (c * RS + rpad<T>(i));
-            if (i < rows_in && c < nc) cp_async<(int)sizeof(cplx<T>)>(d, in + (cols_rowoff<T>(i, pitch, P.in_split_len, P.in_split_stride) + c));
-            else *d = mk<T>(0, 0);
-        }
-        cp_async_wait_all();
-        __syncthreads();
-    }
-
-    // ---- forward stages except the last ----
-    if (mode != CM_INV) {
-        if constexpr (NST > 1) MidFwd<T, Ln, Ln, 0, R0, Rs...>::run(s, RS, TB, P.f, tid, nthreads);
-    }
-
-    // ---- last forward stage + spectrum + first inverse stage: same RLAST contiguous positions ----
-    {
-        constexpr int NB = Ln / RLAST;
-        auto process = [&](int bf, int g, int G) {
-            const int p0 = bf * RLAST;
-            const int rp0 = rpad<T>(p0);
-            int o[RLAST];
-#pragma unroll
-            for (int r = 0; r < RLAST; ++r) o[r] = boff<T, RLAST, 1>(0, p0, r) - (is_pow2(RLAST) ? 0 : rp0);
-            for (int line = g; line < TB; line += G) {
-                cplx<T>* base = s + (line * RS + rp0);
-                cplx<T> v[RLAST];
-#pragma unroll
-                for (int r = 0; r < RLAST; ++r) v[r] = base[o[r]];
-                if (mode != CM_INV) bfly<RLAST, false>(v);
-                if (mode == CM_FUSED && line < nc) {
-                    // transposed spectrum: [line][position], RLAST contiguous values per thread
-                    const size_t sidx = (size_t)(c0 + line) * Ln + p0;
-                    if (P.spec_kind == SPEC_REAL) {
-                        const T* sp = reinterpret_cast<const T*>(P.spec) + sidx;
-#pragma unroll
-                        for (int r = 0; r < RLAST; ++r) v[r] = v[r] * __ldg(sp + r);
-                    } else {
-                        const cplx<T>* sp = reinterpret_cast<const cplx<T>*>(P.spec) + sidx;
-#pragma unroll
-                        for (int r = 0; r < RLAST; ++r) {
-                            const cplx<T> sv = ldg_c(sp + r);
-                            v[r] = P.spec_kind == SPEC_CPLX ? v[r] * sv : mulc(v[r], sv);
-                        }
-                    }
-                }
-                if (mode != CM_FWD) bfly<RLAST, true>(v);
-#pragma unroll
-                for (int r = 0; r < RLAST; ++r) base[o[r]] = v[r];
-            }
-        };
-        if (nthreads >= NB) {
-            const int G = nthreads / NB, g = tid / NB;
-            if (g < G) process(tid % NB, g, G);
-        } else {
-            for (int bf = tid; bf < NB; bf += nthreads) process(bf, 0, 1);
-        }
-        __syncthreads();
-    }
-
-    // ---- inverse stages except the first ----
-    if (mode != CM_FWD) {
-        if constexpr (NST > 1) MidInv<T, Ln, Ln, 0, R0, Rs...>::run(s, RS, TB, P.f, tid, nthreads);
-    }
-
-    // ---- copy out (crop) ----
-    {
-        const int rows_out = mode == CM_FWD ? Ln : P.n_out;
-        for (int w = tid; w < rows_out * TB; w += nthreads) {
-            const int c = w % TB, i = w / TB;
-            if (c < nc) out[cols_rowoff<T>(i, pitch, P.out_split_len, P.out_split_stride) + c] = s[(size_t)c * RS + rpad<T>(i)];
-        }
-    }
-}
-
-// =====================================================================================================
-// Row passes.  H = product of the radix list; a CTA owns RB rows.
-// =====================================================================================================
 template <class T> __device__ __forceinline__ void ld2(const T* p, bool vec, T& a, T& b, bool ok0, bool ok1) {
     if (vec && ok1) { const cplx<T> t = *reinterpret_cast<const cplx<T>*>(p); a = t.x; b = t.y; }
     else { a = ok0 ? p[0] : (T)0; b = ok1 ? p[1] : (T)0; }
@@ -262,22 +37,191 @@ __device__ __forceinline__ void rows_reduce_partials(const double* scratch, int 
     }
 }
 
-template <class T, int R0, int... Rs>
-__global__ void __launch_bounds__(256) rows_fwd_fast_kernel(RowsParams<T> P) {
-    using List = RL<R0, Rs...>;
-    constexpr int H = RLInfo<List>::N;
-    constexpr int NST = RLInfo<List>::count;
-    constexpr int RLAST = RLLast<List>::value;
-    constexpr int S0 = H / R0;
-    constexpr int RS = line_stride<T>(H);
+// spectrum factor(s) of one lane: `idx` = index of the lane's first line in the spectrum array
+__device__ __forceinline__ Lane<float> lane_spec(Lane<float> v, const void* spec, int kind, size_t idx) {
+    if (kind == SPEC_REAL) {
+        const cplx<float> sv = ldg_c(reinterpret_cast<const cplx<float>*>(reinterpret_cast<const float*>(spec) + idx));   // two reals
+        return lmul_real2(v, sv.x, sv.y);
+    }
+    const cplx<float>* sp = reinterpret_cast<const cplx<float>*>(spec) + idx;
+    const cplx<float> w0 = ldg_c(sp), w1 = ldg_c(sp + 1);
+    return kind == SPEC_CPLX ? lmul_cplx2<false>(v, w0, w1) : lmul_cplx2<true>(v, w0, w1);
+}
+__device__ __forceinline__ Lane<double> lane_spec(Lane<double> v, const void* spec, int kind, size_t idx) {
+    if (kind == SPEC_REAL) return lscale(v, __ldg(reinterpret_cast<const double*>(spec) + idx));
+    const cplx<double> w = ldg_c(reinterpret_cast<const cplx<double>*>(spec) + idx);
+    return kind == SPEC_CPLX ? lmul(v, w) : lmulc(v, w);
+}
+
+// =====================================================================================================
+// Column pass.  A CTA owns NL lanes (= NL * LPT neighbouring lines) of one (outer, batch) slice.
+// =====================================================================================================
+template <class T, int NL, int NT, int MINB, int R0, int... Rs>
+__global__ void __launch_bounds__(NT, MINB) cols_fast_kernel(ColsParams<T> P) {
+    using G = TileGeo<T, NL, R0, Rs...>;
+    constexpr int Ln = G::Ln, NST = G::NST, RLAST = G::RLAST, LPT = LaneInfo<T>::LPT, TBL = NL * LPT, S0 = Ln / R0;
     HIPGP_DYN_SMEM(smem_raw);
-    const int RB = P.RB;
-    cplx<T>* s = reinterpret_cast<cplx<T>*>(smem_raw);
-    double* scratch = reinterpret_cast<double*>(smem_raw + sizeof(cplx<T>) * (size_t)RS * RB);
-    const int tid = threadIdx.x, nthreads = blockDim.x;
+    Lane<T>* s = reinterpret_cast<Lane<T>*>(smem_raw);
+    const int tid = threadIdx.x;
+    if (P.done_flag && *P.done_flag) return;
+    const long c0 = (long)blockIdx.x * TBL;
+    const long nvalid = P.inner - c0;                       // lines of this tile that exist
+    const cplx<T>* in = P.in + (size_t)blockIdx.y * P.in_ostride + (size_t)blockIdx.z * P.in_bstride + c0;
+    cplx<T>* out = P.out + (size_t)blockIdx.y * P.out_ostride + (size_t)blockIdx.z * P.out_bstride + c0;
+    const int mode = P.mode;
+    const long pitch = P.pitch;
+    const size_t spitch = P.spec_pitch ? (size_t)P.spec_pitch : (size_t)P.pitch;
+    auto in_off = [&](int i) { return cols_rowoff<T>(i, pitch, P.in_split_len, P.in_split_stride); };
+    auto out_off = [&](int i) { return cols_rowoff<T>(i, pitch, P.out_split_len, P.out_split_stride); };
+
+    if constexpr (NST == 1) {
+        // the whole line lives in one thread's registers
+        for (int lane = tid; lane < NL; lane += NT) {
+            if ((long)lane * LPT >= nvalid) continue;
+            const int rows_in = mode == CM_INV ? Ln : P.n_in;
+            const int rows_out = mode == CM_FWD ? Ln : P.n_out;
+            Lane<T> v[R0];
+#pragma unroll
+            for (int r = 0; r < R0; ++r) v[r] = r < rows_in ? lane_from_global(in + in_off(r) + lane * LPT) : lzero<T>();
+            if (mode != CM_INV) lbfly<R0, false, T>(v);
+            if (mode == CM_FUSED) {
+#pragma unroll
+                for (int r = 0; r < R0; ++r) v[r] = lane_spec(v[r], P.spec, P.spec_kind, (size_t)r * spitch + c0 + lane * LPT);
+            }
+            if (mode != CM_FWD) lbfly<R0, true, T>(v);
+#pragma unroll
+            for (int r = 0; r < R0; ++r) if (r < rows_out) lane_to_global(out + out_off(r) + lane * LPT, v[r]);
+        }
+        return;
+    } else {
+        constexpr int LEG0 = G::leg(S0);
+        const cplx<T>* tw0 = P.f.twst + P.f.twoff[0];
+
+        // ---- first forward stage, operands straight from global memory (zero padding = skipped loads) ----
+        if (mode != CM_INV) {
+            const int n_in = P.n_in;
+            const bool zero_hi = is_pow2(R0) && n_in <= Ln / 2;
+#pragma unroll 1
+            for (int it = tid; it < S0 * NL; it += NT) {
+                const int lane = it % NL, j = it / NL;
+                const bool ok = (long)lane * LPT < nvalid;
+                const cplx<T>* gp = in + lane * LPT;
+                cplx<T> w[R0];
+                lane_twiddles<R0, S0>(w, tw0, j);
+                Lane<T> v[R0];
+                if (zero_hi) {
+#pragma unroll
+                    for (int r = 0; r < R0 / 2; ++r) {
+                        const int i = j + r * S0;
+                        v[r] = (ok && i < n_in) ? lane_from_global(gp + in_off(i)) : lzero<T>();
+                    }
+                    lbfly_zero_hi<R0, T>(v);
+                } else {
+#pragma unroll
+                    for (int r = 0; r < R0; ++r) {
+                        const int i = j + r * S0;
+                        v[r] = (ok && i < n_in) ? lane_from_global(gp + in_off(i)) : lzero<T>();
+                    }
+                    lbfly<R0, false, T>(v);
+                }
+#pragma unroll
+                for (int r = 1; r < R0; ++r) v[r] = lmul(v[r], w[r]);
+                Lane<T>* base = s + (G::slot(j) * NL + lane);
+#pragma unroll
+                for (int r = 0; r < R0; ++r) base[r * LEG0] = v[r];
+            }
+            __syncthreads();
+            LaneMidFwd<G, T, NL, NT, Ln / R0, 1, Rs...>::run(s, P.f, tid);
+        }
+
+        // ---- last forward stage + spectrum + first inverse stage: RLAST neighbouring positions, in registers ----
+        {
+#pragma unroll 1
+            for (int it = tid; it < (Ln / RLAST) * NL; it += NT) {
+                const int lane = it % NL, bf = it / NL;
+                const bool ok = (long)lane * LPT < nvalid;
+                const int p0 = bf * RLAST;
+                Lane<T>* base = s + (G::slot(p0) * NL + lane);
+                Lane<T> v[RLAST];
+                if (mode == CM_INV) {
+#pragma unroll
+                    for (int r = 0; r < RLAST; ++r) v[r] = ok ? lane_from_global(in + in_off(p0 + r) + lane * LPT) : lzero<T>();
+                } else {
+#pragma unroll
+                    for (int r = 0; r < RLAST; ++r) v[r] = base[r * NL];
+                    lbfly<RLAST, false, T>(v);
+                }
+                if (mode == CM_FUSED && ok) {
+                    const size_t sidx = (size_t)p0 * spitch + c0 + lane * LPT;
+#pragma unroll
+                    for (int r = 0; r < RLAST; ++r) v[r] = lane_spec(v[r], P.spec, P.spec_kind, sidx + (size_t)r * spitch);
+                }
+                if (mode == CM_FWD) {
+                    if (ok) {
+#pragma unroll
+                        for (int r = 0; r < RLAST; ++r) lane_to_global(out + out_off(p0 + r) + lane * LPT, v[r]);
+                    }
+                } else {
+                    lbfly<RLAST, true, T>(v);
+#pragma unroll
+                    for (int r = 0; r < RLAST; ++r) base[r * NL] = v[r];
+                }
+            }
+            if (mode == CM_FWD) return;
+            __syncthreads();
+        }
+
+        // ---- inverse middle stages, then the last inverse stage straight to global memory (crop = skipped stores) ----
+        LaneMidInv<G, T, NL, NT, Ln / R0, 1, Rs...>::run(s, P.f, tid);
+        {
+            const int n_out = P.n_out;
+            const bool out_lo = is_pow2(R0) && n_out <= Ln / 2;
+#pragma unroll 1
+            for (int it = tid; it < S0 * NL; it += NT) {
+                const int lane = it % NL, j = it / NL;
+                const bool ok = (long)lane * LPT < nvalid;
+                cplx<T> w[R0];
+                lane_twiddles<R0, S0>(w, tw0, j);
+                const Lane<T>* base = s + (G::slot(j) * NL + lane);
+                Lane<T> v[R0];
+#pragma unroll
+                for (int r = 0; r < R0; ++r) v[r] = base[r * LEG0];
+#pragma unroll
+                for (int r = 1; r < R0; ++r) v[r] = lmulc(v[r], w[r]);
+                cplx<T>* gp = out + lane * LPT;
+                if (out_lo) {          // outputs R0/2 .. R0-1 are cropped: the compiler drops their arithmetic
+                    lbfly<R0, true, T>(v);
+                    if (ok) {
+#pragma unroll
+                        for (int r = 0; r < R0 / 2; ++r) { const int i = j + r * S0; if (i < n_out) lane_to_global(gp + out_off(i), v[r]); }
+                    }
+                } else {
+                    lbfly<R0, true, T>(v);
+                    if (ok) {
+#pragma unroll
+                        for (int r = 0; r < R0; ++r) { const int i = j + r * S0; if (i < n_out) lane_to_global(gp + out_off(i), v[r]); }
+                    }
+                }
+            }
+        }
+    }
+}
+
+// =====================================================================================================
+// Row passes.  H = product of the radix list; a CTA owns NL lanes = NL * LPT rows.
+// =====================================================================================================
+template <class T, int NL, int NT, int MINB, int R0, int... Rs>
+__global__ void __launch_bounds__(NT, MINB) rows_fwd_fast_kernel(RowsParams<T> P) {
+    using G = TileGeo<T, NL, R0, Rs...>;
+    constexpr int H = G::Ln, NST = G::NST, RLAST = G::RLAST, LPT = LaneInfo<T>::LPT, NROW = NL * LPT, S0 = H / R0;
+    constexpr int LEG0 = G::leg(NST > 1 ? S0 : 1);
+    HIPGP_DYN_SMEM(smem_raw);
+    Lane<T>* s = reinterpret_cast<Lane<T>*>(smem_raw);
+    double* scratch = reinterpret_cast<double*>(smem_raw + G::smem_bytes());
+    const int tid = threadIdx.x;
     if (P.mode != RF_PLAIN && P.st.flags[0]) return;
-    const long g0 = (long)blockIdx.x * RB;
-    const long g1 = g0 + RB < P.total_rows ? g0 + RB : P.total_rows;
+    const long g0 = (long)blockIdx.x * NROW;
+    const long g1 = g0 + NROW < P.total_rows ? g0 + NROW : P.total_rows;
     const int nl = (int)(g1 - g0);
     const int n = P.n_real;
     const int mode = P.mode;
@@ -287,7 +231,7 @@ __global__ void __launch_bounds__(256) rows_fwd_fast_kernel(RowsParams<T> P) {
     // per-row scalars, computed once (the 64-bit divisions stay out of the element loops)
     __shared__ T s_coef[32];
     __shared__ long s_wbase[32];
-    if (tid < RB && tid < nl) {
+    if (tid < NROW && tid < nl) {
         const long gr = g0 + tid;
         const long b = gr / P.nrows;
         s_wbase[tid] = (b * P.W_rows + (gr - b * P.nrows)) * P.W_pitch;
@@ -298,237 +242,251 @@ __global__ void __launch_bounds__(256) rows_fwd_fast_kernel(RowsParams<T> P) {
     }
     __syncthreads();
 
-    // ---- first DIF stage fused with the load (and the PCG vector update); thread = butterfly j, loops over rows ----
+    // ---- first DIF stage fused with the load (and the PCG vector update) ----
     {
-        constexpr int NI = S0;                         // partial slots per row
-        auto process = [&](int j, int g, int G) {
-            cplx<T> w[R0];
-            if (NST > 1) load_twiddles<R0, S0, false>(w, P.f.twst + P.f.twoff[0], j);
-            const int rp0 = rpad<T>(j);
-            int o[R0];
-#pragma unroll
-            for (int r = 0; r < R0; ++r) o[r] = boff<T, H, S0>(0, j, r) - (is_pow2(H) ? 0 : rp0);
-            for (int row = g; row < RB; row += G) {
-                cplx<T> v[R0];
-                double accd = 0.0;
-                if (row < nl) {
-                    const size_t off = (size_t)(g0 + row) * n;
-                    const T coef = s_coef[row];
-#pragma unroll
-                    for (int r = 0; r < R0; ++r) {
-                        const int i = 2 * (j + r * S0);
-                        const bool ok0 = i < n, ok1 = i + 1 < n;
-                        T a = 0, b2 = 0;
-                        if (ok0) {
-                            if (mode == RF_PLAIN) {
-                                ld2(P.in + off + i, vec, a, b2, ok0, ok1);
-                            } else if (mode == RF_PUPDATE) {
-                                T z0, z1; ld2(P.in + off + i, vec, z0, z1, ok0, ok1);
-                                if (first_it) { a = z0; b2 = z1; }
-                                else { T p0, p1; ld2((const T*)P.v0 + off + i, vec, p0, p1, ok0, ok1); a = z0 + coef * p0; b2 = z1 + coef * p1; }
-                                st2(P.v0 + off + i, vec, a, b2, ok0, ok1);
-                            } else if (mode == RF_SELFDOT) {
-                                ld2(P.in + off + i, vec, a, b2, ok0, ok1);
-                                accd += (double)(a * a) + (double)(b2 * b2);
-                            } else {
-                                T p0, p1, x0, x1, r0, r1, q0, q1;
-                                ld2(P.v2 + off + i, vec, p0, p1, ok0, ok1);
-                                ld2((const T*)P.v1 + off + i, vec, x0, x1, ok0, ok1);
-                                ld2((const T*)P.v0 + off + i, vec, r0, r1, ok0, ok1);
-                                ld2(P.in + off + i, vec, q0, q1, ok0, ok1);
-                                st2(P.v1 + off + i, vec, x0 + coef * p0, x1 + coef * p1, ok0, ok1);
-                                a = r0 - coef * q0; b2 = ok1 ? r1 - coef * q1 : (T)0;
-                                st2(P.v0 + off + i, vec, a, b2, ok0, ok1);
-                                accd += (double)(a * a) + (double)(b2 * b2);
-                            }
-                        }
-                        v[r] = mk<T>(a, b2);
-                    }
+        const bool zero_hi = is_pow2(R0) && R0 > 1 && (n + 1) / 2 <= H / 2;
+        const cplx<T>* tw0 = P.f.twst + P.f.twoff[0];
+        // element loader: packed complex e = x[2e] + i x[2e+1] of row `row` (tile-local), with the fused vector update
+        auto load_elem = [&](int row, int e, double& accd) -> cplx<T> {
+            const int i = 2 * e;
+            const bool ok0 = i < n, ok1 = i + 1 < n;
+            T a = 0, b2 = 0;
+            if (row < nl && ok0) {
+                const size_t off = (size_t)(g0 + row) * n + i;
+                const T coef = s_coef[row];
+                if (mode == RF_PLAIN) {
+                    ld2(P.in + off, vec, a, b2, ok0, ok1);
+                } else if (mode == RF_PUPDATE) {
+                    T z0, z1; ld2(P.in + off, vec, z0, z1, ok0, ok1);
+                    if (first_it) { a = z0; b2 = z1; }
+                    else { T p0, p1; ld2((const T*)P.v0 + off, vec, p0, p1, ok0, ok1); a = z0 + coef * p0; b2 = z1 + coef * p1; }
+                    st2(P.v0 + off, vec, a, b2, ok0, ok1);
+                } else if (mode == RF_SELFDOT) {
+                    ld2(P.in + off, vec, a, b2, ok0, ok1);
+                    accd += (double)(a * a) + (double)(b2 * b2);
                 } else {
-#pragma unroll
-                    for (int r = 0; r < R0; ++r) v[r] = mk<T>(0, 0);
-                }
-                if (want_dot) scratch[row * NI + j] = accd;
-                if (P.do_fft) {
-                    bfly<R0, false>(v);
-                    if (NST > 1 && j != 0) {
-#pragma unroll
-                        for (int r = 1; r < R0; ++r) v[r] = v[r] * w[r];
-                    }
-                    cplx<T>* base = s + (row * RS + rp0);
-#pragma unroll
-                    for (int r = 0; r < R0; ++r) base[o[r]] = v[r];
+                    T p0, p1, x0, x1, r0, r1, q0, q1;
+                    ld2(P.v2 + off, vec, p0, p1, ok0, ok1);
+                    ld2((const T*)P.v1 + off, vec, x0, x1, ok0, ok1);
+                    ld2((const T*)P.v0 + off, vec, r0, r1, ok0, ok1);
+                    ld2(P.in + off, vec, q0, q1, ok0, ok1);
+                    st2(P.v1 + off, vec, x0 + coef * p0, x1 + coef * p1, ok0, ok1);
+                    a = r0 - coef * q0; b2 = ok1 ? r1 - coef * q1 : (T)0;
+                    st2(P.v0 + off, vec, a, b2, ok0, ok1);
+                    accd += (double)(a * a) + (double)(b2 * b2);
                 }
             }
+            return mk<T>(a, b2);
         };
-        if (nthreads >= S0) {
-            const int G = nthreads / S0, g = tid / S0;
-            if (g < G) process(tid % S0, g, G);
-        } else {
-            for (int j = tid; j < S0; j += nthreads) process(j, 0, 1);
+#pragma unroll 1
+        for (int it = tid; it < S0 * NL; it += NT) {
+            const int lane = it % NL, j = it / NL;
+            cplx<T> w[R0];
+            if (NST > 1) lane_twiddles<R0, S0>(w, tw0, j);
+            double accd[LPT];
+#pragma unroll
+            for (int l = 0; l < LPT; ++l) accd[l] = 0.0;
+            Lane<T> v[R0];
+            if (zero_hi) {
+#pragma unroll
+                for (int r = 0; r < R0 / 2; ++r) {
+#pragma unroll
+                    for (int l = 0; l < LPT; ++l) lane_set(v[r], l, load_elem(lane * LPT + l, j + r * S0, accd[l]));
+                }
+                lbfly_zero_hi<R0, T>(v);
+            } else {
+#pragma unroll
+                for (int r = 0; r < R0; ++r) {
+#pragma unroll
+                    for (int l = 0; l < LPT; ++l) lane_set(v[r], l, load_elem(lane * LPT + l, j + r * S0, accd[l]));
+                }
+                lbfly<R0, false, T>(v);
+            }
+            if (want_dot) {
+#pragma unroll
+                for (int l = 0; l < LPT; ++l) scratch[(lane * LPT + l) * S0 + j] = accd[l];
+            }
+            if (NST > 1) {
+#pragma unroll
+                for (int r = 1; r < R0; ++r) v[r] = lmul(v[r], w[r]);
+            }
+            Lane<T>* base = s + (G::slot(j) * NL + lane);
+#pragma unroll
+            for (int r = 0; r < R0; ++r) base[r * LEG0] = v[r];
         }
     }
     __syncthreads();
     if (want_dot) {
-        rows_reduce_partials(scratch, S0, nl, g0, P.st.partial, tid, nthreads);
-        pcg_finalize(P.st, mode == RF_XRUPDATE ? DOT_RR : DOT_ZR, g0, g1, P.nrows, tid, nthreads);
+        rows_reduce_partials(scratch, S0, nl, g0, P.st.partial, tid, NT);
+        pcg_finalize(P.st, mode == RF_XRUPDATE ? DOT_RR : DOT_ZR, g0, g1, P.nrows, tid, NT);
     }
-    if (!P.do_fft) return;
 
     if constexpr (NST > 1) {
-        MidFwd<T, H, H / R0, 1, Rs...>::run(s, RS, RB, P.f, tid, nthreads);
-        smem_stage<T, H, RLAST, RLAST, false>(s, RS, RB, P.f.twst, tid, nthreads);
+        LaneMidFwd<G, T, NL, NT, H / R0, 1, Rs...>::run(s, P.f, tid);
+        lane_stage<G, T, NL, NT, RLAST, RLAST, false>(s, P.f.twst, tid);
         __syncthreads();
     }
 
-    // ---- split (pairs k, H-k) straight to global: a warp walks a row; partner / twiddle tables are coalesced ----
+    // ---- r2c split on (k, H-k) pairs, straight to global memory ----
     {
-        const int warp = tid >> 5, lane = tid & 31, nwarps = nthreads >> 5;
-        for (int row = warp; row < nl; row += nwarps) {
-            cplx<T>* dst = P.W + s_wbase[row];
-            const cplx<T>* base = s + row * RS;
-            const cplx<T> z0 = base[0];
-            for (int q = lane; q <= H; q += 32) {
-                cplx<T> X;
-                if (q == H) {
-                    X = mk<T>((T)2 * (z0.x - z0.y), 0);
-                } else if (q == 0) {
-                    X = mk<T>((T)2 * (z0.x + z0.y), 0);
-                } else {
-                    const int q2 = P.part[q];
-                    const cplx<T> a = base[rpad<T>(q)], c = conj(base[rpad<T>(q2)]);
-                    const cplx<T> E = a + c, d = a - c;
-                    const cplx<T> O = mk<T>(d.y, -d.x);
-                    X = E + P.twLp[q] * O;
+#pragma unroll 1
+        for (int it = tid; it < (H / 2 + 1) * NL; it += NT) {
+            const int lane = it % NL, pi = it / NL;
+            const int q = P.pairq[pi];
+            Lane<T> Xa, Xb;
+            int qb;
+            bool two;
+            if (q == 0) {
+                const Lane<T> z = s[lane];
+                Lane<T> t; t.re = z.im; t.im = z.im;                 // (im, im)
+                Lane<T> u; u.re = z.re; u.im = z.re;                 // (re, re)
+                Xa = lscale(u + t, (T)2); Xb = lscale(u - t, (T)2);  // re parts are the values; im parts are zeroed below
+                Xa.im = lzero<T>().im; Xb.im = lzero<T>().im;
+                qb = H; two = true;
+            } else {
+                const int q2 = P.part[q];
+                const Lane<T> a = s[G::slot(q) * NL + lane], c = lconj(s[G::slot(q2) * NL + lane]);
+                const Lane<T> E = a + c;
+                const Lane<T> t = lmul(lmi<false>(a - c), P.twLp[q]);
+                Xa = E + t; Xb = lconj(E - t);
+                qb = q2; two = q2 != q;
+            }
+#pragma unroll
+            for (int l = 0; l < LPT; ++l) {
+                const int row = lane * LPT + l;
+                if (row < nl) {
+                    cplx<T>* dst = P.W + s_wbase[row];
+                    dst[q] = lane_get(Xa, l);
+                    if (two) dst[qb] = lane_get(Xb, l);
                 }
-                dst[q] = X;
             }
         }
     }
 }
 
-template <class T, int R0, int... Rs>
-__global__ void __launch_bounds__(256) rows_inv_fast_kernel(RowsParams<T> P) {
-    using List = RL<R0, Rs...>;
-    constexpr int H = RLInfo<List>::N;
-    constexpr int NST = RLInfo<List>::count;
-    constexpr int RLAST = RLLast<List>::value;
-    constexpr int S0 = H / R0;
-    constexpr int RS = line_stride<T>(H);
+template <class T, int NL, int NT, int MINB, int R0, int... Rs>
+__global__ void __launch_bounds__(NT, MINB) rows_inv_fast_kernel(RowsParams<T> P) {
+    using G = TileGeo<T, NL, R0, Rs...>;
+    constexpr int H = G::Ln, NST = G::NST, RLAST = G::RLAST, LPT = LaneInfo<T>::LPT, NROW = NL * LPT, S0 = H / R0;
+    constexpr int LEG0 = G::leg(NST > 1 ? S0 : 1);
     HIPGP_DYN_SMEM(smem_raw);
-    const int RB = P.RB;
-    cplx<T>* s = reinterpret_cast<cplx<T>*>(smem_raw);
-    double* scratch = reinterpret_cast<double*>(smem_raw + sizeof(cplx<T>) * (size_t)RS * RB);
-    const int tid = threadIdx.x, nthreads = blockDim.x;
+    Lane<T>* s = reinterpret_cast<Lane<T>*>(smem_raw);
+    double* scratch = reinterpret_cast<double*>(smem_raw + G::smem_bytes());
+    const int tid = threadIdx.x;
     if (P.mode != RI_PLAIN && P.st.flags[0]) return;
-    const long g0 = (long)blockIdx.x * RB;
-    const long g1 = g0 + RB < P.total_rows ? g0 + RB : P.total_rows;
+    const long g0 = (long)blockIdx.x * NROW;
+    const long g1 = g0 + NROW < P.total_rows ? g0 + NROW : P.total_rows;
     const int nl = (int)(g1 - g0);
     const int n = P.n_real;
 
     __shared__ long s_wbase[32];
-    if (tid < RB && tid < nl) {
+    if (tid < NROW && tid < nl) {
         const long gr = g0 + tid;
         const long b = gr / P.nrows;
         s_wbase[tid] = (b * P.W_rows + (gr - b * P.nrows)) * P.W_pitch;
     }
     __syncthreads();
-    // ---- async copy of the H+1 bins of every row into shared memory, then the merge pairwise in place ----
+
+    // ---- c2r merge on (k, H-k) pairs, straight from global memory into shared memory ----
     {
-        const int warp = tid >> 5, lane = tid & 31, nwarps = nthreads >> 5;
-        for (int row = warp; row < RB; row += nwarps) {
-            cplx<T>* base = s + row * RS;
-            if (row >= nl) {
-                for (int q = lane; q <= H; q += 32) base[rpad<T>(q)] = mk<T>(0, 0);
-                continue;
-            }
-            const cplx<T>* src = P.W + s_wbase[row];
-            for (int q = lane; q <= H; q += 32) cp_async<(int)sizeof(cplx<T>)>(base + rpad<T>(q), src + q);
-        }
-        cp_async_wait_all();
-        __syncthreads();
-        for (int row = warp; row < nl; row += nwarps) {
-            cplx<T>* base = s + row * RS;
-            for (int q = lane; q < H; q += 32) {
-                if (q == 0) {
-                    cplx<T> a = base[0], c = base[rpad<T>(H)];
-                    if (P.spec_kind != SPEC_NONE) { a = apply_spec(a, P.spec, P.spec_kind, (size_t)0); c = apply_spec(c, P.spec, P.spec_kind, (size_t)H); }
-                    base[0] = mk<T>(a.x + c.x, a.x - c.x);
-                    continue;
+        const int spec_kind = P.spec_kind;
+#pragma unroll 1
+        for (int it = tid; it < (H / 2 + 1) * NL; it += NT) {
+            const int lane = it % NL, pi = it / NL;
+            const int q = P.pairq[pi];
+            const int q2 = q == 0 ? H : P.part[q];
+            Lane<T> a = lzero<T>(), c = lzero<T>();
+#pragma unroll
+            for (int l = 0; l < LPT; ++l) {
+                const int row = lane * LPT + l;
+                if (row < nl) {
+                    const cplx<T>* src = P.W + s_wbase[row];
+                    cplx<T> ya = src[q], yc = src[q2];
+                    if (spec_kind != SPEC_NONE) { ya = apply_spec(ya, P.spec, spec_kind, (size_t)q); yc = apply_spec(yc, P.spec, spec_kind, (size_t)q2); }
+                    lane_set(a, l, ya); lane_set(c, l, yc);
                 }
-                const int q2 = P.part[q];
-                if (q > q2) continue;                       // the pair is handled by its smaller member
-                cplx<T> a = base[rpad<T>(q)], c = base[rpad<T>(q2)];
-                if (P.spec_kind != SPEC_NONE) { a = apply_spec(a, P.spec, P.spec_kind, (size_t)q); c = apply_spec(c, P.spec, P.spec_kind, (size_t)q2); }
+            }
+            if (q == 0) {
+                // Z[0] = (Y0 + YH) + i (Y0 - YH), real parts only
+                Lane<T> z; z.re = (a + c).re; z.im = (a - c).re;
+                s[lane] = z;
+            } else {
                 // bin q (frequency k):  E + i O with O = conj(w^k)(Y[k] - conj Y[k']);  bin q2 is conj(E - i O)
-                c = conj(c);
-                const cplx<T> E = a + c;
-                const cplx<T> O = mulc(a - c, P.twLp[q]);
-                const cplx<T> iO = mk<T>(-O.y, O.x);
-                base[rpad<T>(q)] = E + iO;
-                if (q != q2) base[rpad<T>(q2)] = conj(E - iO);
+                c = lconj(c);
+                const Lane<T> E = a + c;
+                const Lane<T> iO = lmi<true>(lmulc(a - c, P.twLp[q]));
+                s[G::slot(q) * NL + lane] = E + iO;
+                if (q2 != q) s[G::slot(q2) * NL + lane] = lconj(E - iO);
             }
         }
     }
     __syncthreads();
 
     if constexpr (NST > 1) {
-        smem_stage<T, H, RLAST, RLAST, true>(s, RS, RB, P.f.twst, tid, nthreads);
+        lane_stage<G, T, NL, NT, RLAST, RLAST, true>(s, P.f.twst, tid);
         __syncthreads();
-        MidInv<T, H, H / R0, 1, Rs...>::run(s, RS, RB, P.f, tid, nthreads);
+        LaneMidInv<G, T, NL, NT, H / R0, 1, Rs...>::run(s, P.f, tid);
     }
 
     // ---- last inverse stage fused with the store (crop) and the dot product ----
     const bool vec = ((n & 1) == 0) && P.vec_ok;
     const bool want_dot = P.mode == RI_DOT;
     {
-        auto process = [&](int j, int g, int G) {
-            cplx<T> w[R0];
-            if (NST > 1) load_twiddles<R0, S0, true>(w, P.f.twst + P.f.twoff[0], j);
-            const int rp0 = rpad<T>(j);
-            int o[R0];
-#pragma unroll
-            for (int r = 0; r < R0; ++r) o[r] = boff<T, H, S0>(0, j, r) - (is_pow2(H) ? 0 : rp0);
-            for (int row = g; row < RB; row += G) {
-                double accd = 0.0;
-                if (row < nl) {
-                    const cplx<T>* base = s + (row * RS + rp0);
-                    cplx<T> v[R0];
-#pragma unroll
-                    for (int r = 0; r < R0; ++r) v[r] = base[o[r]];
-                    if (NST > 1 && j != 0) {
-#pragma unroll
-                        for (int r = 1; r < R0; ++r) v[r] = v[r] * w[r];
-                    }
-                    bfly<R0, true>(v);
-                    const size_t off = (size_t)(g0 + row) * n;
-#pragma unroll
-                    for (int r = 0; r < R0; ++r) {
-                        const int i = 2 * (j + r * S0);
-                        const bool ok0 = i < n, ok1 = i + 1 < n;
-                        if (ok0) {
-                            st2(P.out + off + i, vec, v[r].x, v[r].y, ok0, ok1);
-                            if (want_dot) {
-                                T o0, o1; ld2((const T*)P.v0 + off + i, vec, o0, o1, ok0, ok1);
-                                accd += (double)(v[r].x * o0) + (ok1 ? (double)(v[r].y * o1) : 0.0);
-                            }
-                        }
-                    }
+        const bool out_lo = is_pow2(R0) && R0 > 1 && (n + 1) / 2 <= H / 2;
+        const cplx<T>* tw0 = P.f.twst + P.f.twoff[0];
+        auto store_elem = [&](int row, int e, cplx<T> val, double& accd) {
+            const int i = 2 * e;
+            const bool ok0 = i < n, ok1 = i + 1 < n;
+            if (row < nl && ok0) {
+                const size_t off = (size_t)(g0 + row) * n + i;
+                st2(P.out + off, vec, val.x, val.y, ok0, ok1);
+                if (want_dot) {
+                    T o0, o1; ld2((const T*)P.v0 + off, vec, o0, o1, ok0, ok1);
+                    accd += (double)(val.x * o0) + (ok1 ? (double)(val.y * o1) : 0.0);
                 }
-                if (want_dot) scratch[row * S0 + j] = accd;
             }
         };
-        if (nthreads >= S0) {
-            const int G = nthreads / S0, g = tid / S0;
-            if (g < G) process(tid % S0, g, G);
-        } else {
-            for (int j = tid; j < S0; j += nthreads) process(j, 0, 1);
+#pragma unroll 1
+        for (int it = tid; it < S0 * NL; it += NT) {
+            const int lane = it % NL, j = it / NL;
+            cplx<T> w[R0];
+            if (NST > 1) lane_twiddles<R0, S0>(w, tw0, j);
+            const Lane<T>* base = s + (G::slot(j) * NL + lane);
+            Lane<T> v[R0];
+#pragma unroll
+            for (int r = 0; r < R0; ++r) v[r] = base[r * LEG0];
+            if (NST > 1) {
+#pragma unroll
+                for (int r = 1; r < R0; ++r) v[r] = lmulc(v[r], w[r]);
+            }
+            double accd[LPT];
+#pragma unroll
+            for (int l = 0; l < LPT; ++l) accd[l] = 0.0;
+            if (out_lo) {
+                lbfly<R0, true, T>(v);
+#pragma unroll
+                for (int r = 0; r < R0 / 2; ++r) {
+#pragma unroll
+                    for (int l = 0; l < LPT; ++l) store_elem(lane * LPT + l, j + r * S0, lane_get(v[r], l), accd[l]);
+                }
+            } else {
+                lbfly<R0, true, T>(v);
+#pragma unroll
+                for (int r = 0; r < R0; ++r) {
+#pragma unroll
+                    for (int l = 0; l < LPT; ++l) store_elem(lane * LPT + l, j + r * S0, lane_get(v[r], l), accd[l]);
+                }
+            }
+            if (want_dot) {
+#pragma unroll
+                for (int l = 0; l < LPT; ++l) scratch[(lane * LPT + l) * S0 + j] = accd[l];
+            }
         }
     }
     if (want_dot) {
         __syncthreads();
-        rows_reduce_partials(scratch, S0, nl, g0, P.st.partial, tid, nthreads);
-        pcg_finalize(P.st, P.dot_kind, g0, g1, P.nrows, tid, nthreads);
+        rows_reduce_partials(scratch, S0, nl, g0, P.st.partial, tid, NT);
+        pcg_finalize(P.st, P.dot_kind, g0, g1, P.nrows, tid, NT);
     }
 }
 

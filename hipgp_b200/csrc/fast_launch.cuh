@@ -1,71 +1,85 @@
-// fast_launch.cuh -- launch code of the specialised kernels (included only by fast_inst.cu).
+// fast_launch.cuh -- tile configuration and launch code of the specialised kernels (included only by fast_inst.cu).
 #pragma once
 #include "plan_types.cuh"
 #include "fast_kernels.cuh"
 
 namespace hipgp {
-template <class T> constexpr int rows_pad(int pos) { return sizeof(T) == 4 ? pos + (pos >> 4) : pos + (pos >> 3) + (pos >> 6); }
 
-template <class T, int R0, int... Rs>
+#ifndef HIPGP_NL_MUL      /* developer knob: scale the lanes per CTA (and the threads with them) */
+#define HIPGP_NL_MUL 1
+#endif
+
+constexpr int cfg_min(int a, int b) { return a < b ? a : b; }
+constexpr int cfg_max(int a, int b) { return a > b ? a : b; }
+constexpr int pow2_floor(int x) { return x <= 1 ? 1 : 2 * pow2_floor(x / 2); }
+
+// Tile configuration of one (dtype, radix list): NL lanes per CTA so that the widest stage gives every one of ~256
+// threads one butterfly and the tile stays near 64 KB (two to three CTAs per SM); NT threads; register cap 128.
+template <class T, int... Rs>
+struct FastCfg {
+    using List = RL<Rs...>;
+    static constexpr int Ln = RLInfo<List>::N;
+    static constexpr int RMAX = RLMax<List>::value;
+    static constexpr int BFN = Ln / RMAX;                       // butterflies per line in the widest stage
+    static constexpr int NL0 = pow2_floor(cfg_max(1, cfg_min(256 / cfg_max(BFN, 1), 4096 / Ln)));
+    static constexpr int NL = cfg_max(1, cfg_min(16, NL0 * HIPGP_NL_MUL));
+    static constexpr int NT = cfg_min(512, cfg_max(32, (BFN * NL + 31) / 32 * 32));
+    static constexpr int MINB = cfg_max(1, 512 / NT);
+    static constexpr int LPT = LaneInfo<T>::LPT;
+    static constexpr int S0 = Ln / (RLInfo<List>::count ? RLFirst<List>::value : 1);
+};
+
+template <class T, int... Rs>
 static void launch_rows_fast_t(hipgp_plan* pl, bool inverse, RowsParams<T>& P, cudaStream_t st) {
-    constexpr int H = RLInfo<RL<R0, Rs...>>::N;
-    constexpr int S0 = H / R0;
-    const int RS = line_stride<T>(H);
-    auto smem_for = [&](int rb) { return sizeof(cplx<T>) * (size_t)RS * rb + sizeof(double) * (size_t)S0 * rb; };
-    int rb = 16;
-    while (rb > 1 && (smem_for(rb) > 72 * 1024 || P.total_rows < (long)rb * 148 * 2)) rb >>= 1;
-    if (smem_for(rb) > 220 * 1024) throw Error("row axis too long for the shared-memory FFT");
-    P.RB = rb; P.RBP = rb;
-    const size_t smem = smem_for(rb);
-    const long items = (long)S0 * rb;
-    int nth = items >= 256 ? 256 : (items >= 128 ? 128 : (items >= 64 ? 64 : 32));
-    dim3 grid((unsigned)((P.total_rows + rb - 1) / rb));
+    using C = FastCfg<T, Rs...>;
+    using G = TileGeo<T, C::NL, Rs...>;
+    constexpr int NROW = C::NL * C::LPT;
+    static_assert(NROW <= 32, "per-row scalars are held in 32-entry shared arrays");
+    P.RB = NROW; P.RBP = NROW;
+    const size_t smem = G::smem_bytes() + sizeof(double) * (size_t)C::S0 * NROW;
+    dim3 grid((unsigned)((P.total_rows + NROW - 1) / NROW));
     PROF_BEGIN(pl, inverse ? 2 : 0, st);
     if (inverse) {
-        auto k = rows_inv_fast_kernel<T, R0, Rs...>;
+        auto k = rows_inv_fast_kernel<T, C::NL, C::NT, C::MINB, Rs...>;
         if (smem > 48 * 1024) HIPGP_SET_MAX_SMEM(k, smem);
-        HIPGP_LAUNCH(k, grid, dim3(nth), smem, st, P);
+        HIPGP_LAUNCH(k, grid, dim3(C::NT), smem, st, P);
     } else {
-        auto k = rows_fwd_fast_kernel<T, R0, Rs...>;
+        auto k = rows_fwd_fast_kernel<T, C::NL, C::NT, C::MINB, Rs...>;
         if (smem > 48 * 1024) HIPGP_SET_MAX_SMEM(k, smem);
-        HIPGP_LAUNCH(k, grid, dim3(nth), smem, st, P);
+        HIPGP_LAUNCH(k, grid, dim3(C::NT), smem, st, P);
     }
     PROF_END(pl, st);
     CK_LAUNCH();
     pl->launches++;
 }
 
-#ifndef HIPGP_TB_SHIFT
-#define HIPGP_TB_SHIFT 0
-#endif
-template <class T> constexpr int cols_tb_base(int L);
-template <class T> constexpr int cols_tb(int L) { return cols_tb_base<T>(L) >> HIPGP_TB_SHIFT > 0 ? cols_tb_base<T>(L) >> HIPGP_TB_SHIFT : 1; }
-template <class T> constexpr int cols_tb_base(int L) {
-    // lines per CTA: keep the tile <= 128 KB and, where it fits, >= 64 B of contiguous lines per position
-    return sizeof(T) == 4 ? (L <= 256 ? 32 : (L <= 512 ? 16 : (L <= 2048 ? 8 : (L <= 4096 ? 4 : 2))))
-                          : (L <= 256 ? 16 : (L <= 512 ? 8 : (L <= 2048 ? 4 : (L <= 4096 ? 2 : 1))));
-}
-
-template <class T, int LEN, int R0, int... Rs>
+template <class T, int LEN, int... Rs>
 static void launch_cols_fast_t(hipgp_plan* pl, ColsParams<T>& P, long n_outer, long B, cudaStream_t st) {
-    constexpr int TB = cols_tb<T>(LEN);
-    static_assert(RLInfo<RL<R0, Rs...>>::N == LEN, "radix list does not multiply to the length");
-    P.TB = TB; P.TBP = TB;
-    const size_t smem = sizeof(cplx<T>) * (size_t)line_stride<T>(LEN) * TB;
-    const long items = (long)LEN * TB / 16;
-    int nth = items >= 512 ? 512 : (items >= 256 ? 256 : (items >= 128 ? 128 : (items >= 64 ? 64 : 32)));
-    static const char* env_nth = getenv("HIPGP_COLS_NTH");
-    if (env_nth) nth = atoi(env_nth);
-    dim3 grid((unsigned)((P.inner + TB - 1) / TB), (unsigned)n_outer, (unsigned)B);
-    auto k = cols_fast_kernel<T, TB, R0, Rs...>;
+    using C = FastCfg<T, Rs...>;
+    using G = TileGeo<T, C::NL, Rs...>;
+    static_assert(C::Ln == LEN, "radix list does not multiply to the length");
+    constexpr int TBL = C::NL * C::LPT;
+    P.TB = TBL; P.TBP = TBL;
+    const size_t smem = G::smem_bytes();
+    dim3 grid((unsigned)((P.inner + TBL - 1) / TBL), (unsigned)n_outer, (unsigned)B);
+    auto k = cols_fast_kernel<T, C::NL, C::NT, C::MINB, Rs...>;
     if (smem > 48 * 1024) HIPGP_SET_MAX_SMEM(k, smem);
     PROF_BEGIN(pl, 1, st);
-    HIPGP_LAUNCH(k, grid, dim3(nth), smem, st, P);
+    HIPGP_LAUNCH(k, grid, dim3(C::NT), smem, st, P);
     PROF_END(pl, st);
     CK_LAUNCH();
     pl->launches++;
 }
 
+// the lane kernels move 16-byte lanes: pointers and strides must keep every lane aligned
+template <class T>
+static bool cols_lane_aligned(const ColsParams<T>& P) {
+    constexpr long A = 16 / (long)sizeof(cplx<T>);          // complex elements per 16 bytes (2 for fp32, 1 for fp64)
+    auto al = [&](long v) { return v % A == 0; };
+    return ((uintptr_t)P.in % 16 == 0) && ((uintptr_t)P.out % 16 == 0) && ((uintptr_t)P.spec % 16 == 0) && al(P.pitch) && al(P.in_ostride) &&
+           al(P.in_bstride) && al(P.out_ostride) && al(P.out_bstride) && al(P.in_split_stride) && al(P.out_split_stride) &&
+           al(P.spec_pitch);
+}
 
 template <class T, int LEN> struct FastList;
 #define X(LEN, ...)                                                                                         \
@@ -76,5 +90,9 @@ template <class T, int LEN> struct FastList;
 HIPGP_FAST_LIST(X)
 #undef X
 template <class T, int LEN> void launch_rows_fast_len(hipgp_plan* pl, bool inverse, RowsParams<T>& P, cudaStream_t st) { FastList<T, LEN>::rows(pl, inverse, P, st); }
-template <class T, int LEN> void launch_cols_fast_len(hipgp_plan* pl, ColsParams<T>& P, long n_outer, long B, cudaStream_t st) { FastList<T, LEN>::cols(pl, P, n_outer, B, st); }
+template <class T, int LEN> bool launch_cols_fast_len(hipgp_plan* pl, ColsParams<T>& P, long n_outer, long B, cudaStream_t st) {
+    if (!cols_lane_aligned<T>(P)) return false;
+    FastList<T, LEN>::cols(pl, P, n_outer, B, st);
+    return true;
+}
 }  // namespace hipgp

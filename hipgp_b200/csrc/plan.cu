@@ -67,7 +67,7 @@ template <class T>
 static bool launch_cols_fast(hipgp_plan* pl, ColsParams<T>& P, long n_outer, long B, cudaStream_t st) {
     if (g_no_fast) return false;
     switch (P.f.Ln) {
-#define X(LEN, ...) case LEN: launch_cols_fast_len<T, LEN>(pl, P, n_outer, B, st); return true;
+#define X(LEN, ...) case LEN: return launch_cols_fast_len<T, LEN>(pl, P, n_outer, B, st);
         HIPGP_FAST_LIST(X)
 #undef X
         default: return false;
@@ -126,7 +126,7 @@ static void run_pipeline(hipgp_plan* pl, Geom<T>& g, const int* n_in, const int*
 
     RowsParams<T> R{};
     R.W = W1; R.L = g.L[D - 1]; R.H = g.H; R.W_pitch = P; R.W_rows = (int)Wrows;
-    R.f = g.frow.dev; R.twL = g.twL.template as<cplx<T>>(); R.twLp = g.twLp.template as<cplx<T>>(); R.part = g.part.template as<int>(); R.st = st;
+    R.f = g.frow.dev; R.twL = g.twL.template as<cplx<T>>(); R.twLp = g.twLp.template as<cplx<T>>(); R.part = g.part.template as<int>(); R.pairq = g.pairq.template as<int>(); R.st = st;
     // forward rows
     R.in = (const T*)ff.in; R.v0 = (T*)ff.v0; R.v1 = (T*)ff.v1; R.v2 = (const T*)ff.v2;
     R.mode = ff.mode; R.do_fft = 1; R.total_rows = B * rows_in; R.nrows = (int)rows_in; R.n_real = n_in[D - 1];
@@ -177,7 +177,7 @@ static void forward_full(hipgp_plan* pl, Geom<double>& g, const double* h, cudaS
     cplx<double>* W = pl->W1.as<cplx<double>>();
     RowsParams<double> R{};
     R.in = h; R.W = W; R.L = g.L[D - 1]; R.H = g.H; R.W_pitch = g.P; R.W_rows = (int)rows;
-    R.f = g.frow.dev; R.twL = g.twL.as<cplx<double>>(); R.twLp = g.twLp.as<cplx<double>>(); R.part = g.part.as<int>(); R.mode = RF_PLAIN; R.do_fft = 1;
+    R.f = g.frow.dev; R.twL = g.twL.as<cplx<double>>(); R.twLp = g.twLp.as<cplx<double>>(); R.part = g.part.as<int>(); R.pairq = g.pairq.as<int>(); R.mode = RF_PLAIN; R.do_fft = 1;
     R.total_rows = rows; R.nrows = (int)rows; R.n_real = g.L[D - 1];
     launch_rows<double>(pl, false, R, s);
     if (D >= 2) {
@@ -259,18 +259,13 @@ static void build_spectrum(hipgp_plan* pl, bool wide, const double* col, DevBuf&
     const long n = g.spec_elems();
     double scale = 0.25;
     for (int d = 0; d < g.D; ++d) scale /= (double)g.L[d];
-    // the specialised column pass reads the spectrum transposed ([line][position of axis 0])
-    const bool transposed = g.D >= 2 && !g_no_fast && !fast_radices(g.L[0]).empty();
-    const long L0 = g.L[0], inner = n / L0;
     const unsigned nblk = (unsigned)((n + 255) / 256);
     if (complex_spec) {
         dst.ensure(sizeof(cplx<T>) * (size_t)n, &pl->dev_bytes);
-        if (transposed) { auto k = store_spec_cplx_T_kernel<T>; HIPGP_LAUNCH(k, dim3(nblk), dim3(256), 0, s, pl->W1.as<cplx<double>>(), dst.as<cplx<T>>(), L0, inner, scale); }
-        else { auto k = store_spec_cplx_kernel<T>; HIPGP_LAUNCH(k, dim3(nblk), dim3(256), 0, s, pl->W1.as<cplx<double>>(), dst.as<cplx<T>>(), n, scale); }
+        auto k = store_spec_cplx_kernel<T>; HIPGP_LAUNCH(k, dim3(nblk), dim3(256), 0, s, pl->W1.as<cplx<double>>(), dst.as<cplx<T>>(), n, scale);
     } else {
         dst.ensure(sizeof(T) * (size_t)n, &pl->dev_bytes);
-        if (transposed) { auto k = store_spec_real_T_kernel<T>; HIPGP_LAUNCH(k, dim3(nblk), dim3(256), 0, s, pl->W1.as<cplx<double>>(), dst.as<T>(), L0, inner, scale); }
-        else { auto k = store_spec_real_kernel<T>; HIPGP_LAUNCH(k, dim3(nblk), dim3(256), 0, s, pl->W1.as<cplx<double>>(), dst.as<T>(), n, scale); }
+        auto k = store_spec_real_kernel<T>; HIPGP_LAUNCH(k, dim3(nblk), dim3(256), 0, s, pl->W1.as<cplx<double>>(), dst.as<T>(), n, scale);
     }
     CK_LAUNCH(); pl->launches++;
 }
@@ -363,7 +358,7 @@ static void slab_stage1(hipgp_plan* pl, const void* in_slab, void* send_buf, cud
     cplx<T>* W1 = pl->W1.as<cplx<T>>();
     RowsParams<T> R{};
     R.in = (const T*)in_slab; R.W = W1; R.L = g.L[2]; R.H = g.H; R.W_pitch = g.P; R.W_rows = (int)rows;
-    R.f = g.frow.dev; R.twL = g.twL.template as<cplx<T>>(); R.twLp = g.twLp.template as<cplx<T>>(); R.part = g.part.template as<int>();
+    R.f = g.frow.dev; R.twL = g.twL.template as<cplx<T>>(); R.twLp = g.twLp.template as<cplx<T>>(); R.part = g.part.template as<int>(); R.pairq = g.pairq.template as<int>();
     R.mode = RF_PLAIN; R.do_fft = 1; R.total_rows = rows; R.nrows = (int)rows; R.n_real = pl->m[2]; R.st = null_state();
     launch_rows<T>(pl, false, R, s);
     ColsParams<T> C{};
@@ -378,12 +373,11 @@ template <class T>
 static void slab_stage2(hipgp_plan* pl, int mode, void* buf, cudaStream_t s) {
     Geom<T>& g = geom(pl, false, Tag<T>());
     const SlabGeo q = slab_geo<T>(pl, g);
-    const bool transposed = !g_no_fast && !fast_radices(g.L[0]).empty();
-    if (!transposed) throw Error("slab mode needs a specialised column kernel for the axis-0 length");
-    const T* spec = (mode == HIPGP_MV_K ? pl->specK.as<T>() : pl->specCinv.as<T>()) + (size_t)pl->slab_rank * q.chunk * g.L[0];
+    // this rank's chunk of lines inside the full [L0][L1 * P3] spectrum
+    const T* spec = (mode == HIPGP_MV_K ? pl->specK.as<T>() : pl->specCinv.as<T>()) + (size_t)pl->slab_rank * q.chunk;
     ColsParams<T> C{};
     C.in = (cplx<T>*)buf; C.out = (cplx<T>*)buf; C.n_in = pl->m[0]; C.n_out = pl->m[0]; C.inner = q.chunk; C.pitch = q.chunk;
-    C.f = g.fcol[0].dev; C.mode = CM_FUSED; C.spec = spec; C.spec_kind = SPEC_REAL;
+    C.f = g.fcol[0].dev; C.mode = CM_FUSED; C.spec = spec; C.spec_kind = SPEC_REAL; C.spec_pitch = (long)g.L[1] * q.P3;
     launch_cols<T>(pl, C, 1, 1, s);
 }
 
@@ -401,7 +395,7 @@ static void slab_stage3(hipgp_plan* pl, const void* recv_buf, void* out_slab, cu
     launch_cols<T>(pl, C, q.n0_loc, 1, s);
     RowsParams<T> R{};
     R.out = (T*)out_slab; R.W = W1; R.L = g.L[2]; R.H = g.H; R.W_pitch = g.P; R.W_rows = (int)rows;
-    R.f = g.frow.dev; R.twL = g.twL.template as<cplx<T>>(); R.twLp = g.twLp.template as<cplx<T>>(); R.part = g.part.template as<int>();
+    R.f = g.frow.dev; R.twL = g.twL.template as<cplx<T>>(); R.twLp = g.twLp.template as<cplx<T>>(); R.part = g.part.template as<int>(); R.pairq = g.pairq.template as<int>();
     R.mode = RI_PLAIN; R.total_rows = rows; R.nrows = (int)rows; R.n_real = pl->m[2]; R.st = null_state();
     R.spec = nullptr; R.spec_kind = SPEC_NONE;
     launch_rows<T>(pl, true, R, s);

@@ -177,7 +177,7 @@ struct Geom {
     long P = 0;         // row pitch in complex elements (>= H + 1)
     LineFftHost<T> fcol[2];
     LineFftHost<T> frow;
-    DevBuf twL, twLp, part;
+    DevBuf twL, twLp, part, pairq;
     bool built = false;
     void build(int D_, const int* L_, size_t* total) {
         D = D_;
@@ -199,13 +199,18 @@ struct Geom {
             wp[q] = w[k];
             pt[q] = k == 0 ? 0 : frow.hpos_[H - k];
         }
+        std::vector<int> pq;
+        for (int q = 0; q < H; ++q) if (q <= pt[q]) pq.push_back(q);
+        if ((int)pq.size() != H / 2 + 1) throw Error("internal: r2c pair table has the wrong size");
+        pairq.ensure(sizeof(int) * pq.size(), total);
+        CK(cudaMemcpy(pairq.p, pq.data(), sizeof(int) * pq.size(), cudaMemcpyHostToDevice));
         twLp.ensure(sizeof(cplx<T>) * H, total); part.ensure(sizeof(int) * H, total);
         CK(cudaMemcpy(twLp.p, wp.data(), sizeof(cplx<T>) * H, cudaMemcpyHostToDevice));
         CK(cudaMemcpy(part.p, pt.data(), sizeof(int) * H, cudaMemcpyHostToDevice));
         built = true;
     }
     long spec_elems() const { long n = P; for (int d = 0; d + 1 < D; ++d) n *= L[d]; return n; }
-    void release(size_t* total) { for (auto& f : fcol) f.release(total); frow.release(total); twL.release(total); twLp.release(total); part.release(total); built = false; }
+    void release(size_t* total) { for (auto& f : fcol) f.release(total); frow.release(total); twL.release(total); twLp.release(total); part.release(total); pairq.release(total); built = false; }
 };
 
 struct RowsFusion {
@@ -269,5 +274,5 @@ struct hipgp_plan {
 // instantiated by fast_inst.cu (compiled once per length group so that the build runs in parallel). ----
 namespace hipgp {
 template <class T, int LEN> void launch_rows_fast_len(hipgp_plan* pl, bool inverse, RowsParams<T>& P, cudaStream_t st);
-template <class T, int LEN> void launch_cols_fast_len(hipgp_plan* pl, ColsParams<T>& P, long n_outer, long B, cudaStream_t st);
+template <class T, int LEN> bool launch_cols_fast_len(hipgp_plan* pl, ColsParams<T>& P, long n_outer, long B, cudaStream_t st);   // false: lanes not 16-byte aligned
 }

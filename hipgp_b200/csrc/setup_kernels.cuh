@@ -106,23 +106,6 @@ __global__ void store_spec_cplx_kernel(const cplx<double>* __restrict__ raw, cpl
     if (i < n) out[i] = mk<T>((T)(raw[i].x * scale), (T)(raw[i].y * scale));
 }
 
-// transposed variants for the specialised column pass: raw [L0][inner] -> out [inner][L0]
-template <class T>
-__global__ void store_spec_real_T_kernel(const cplx<double>* __restrict__ raw, T* __restrict__ out, long L0, long inner, double scale) {
-    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= L0 * inner) return;
-    const long c = i / L0, p = i - c * L0;
-    out[i] = (T)(raw[p * inner + c].x * scale);
-}
-template <class T>
-__global__ void store_spec_cplx_T_kernel(const cplx<double>* __restrict__ raw, cplx<T>* __restrict__ out, long L0, long inner, double scale) {
-    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= L0 * inner) return;
-    const long c = i / L0, p = i - c * L0;
-    const cplx<double> v = raw[p * inner + c];
-    out[i] = mk<T>((T)(v.x * scale), (T)(v.y * scale));
-}
-
 // D-shaped (m_1..m_D) fp64 -> reference layout (N_1..N_D) in the plan dtype (even extension), for the
 // `D`, `D_sqrt`, `Di` attributes of the drop-in ToeplitzTensor.
 template <class T>
