@@ -117,6 +117,11 @@ struct RowsParams {
     const cplx<T>* twLp;  // twL in position order: twLp[q] = twL[rev[q]]
     const int* part;      // partner position of q in the r2c split: pos[H - rev[q]] (q > 0)
     const int* pairq;     // the H/2 + 1 positions q with q <= part[q] (one per (k, H-k) pair), ascending
+    // specialised kernels: (k, H-k) pairs as records {q, q2} + twLp[q], in pairq order (the first npair0 = digit group
+    // 0, or all of them when the list has one stage), and quads {a, b} + (twLp[a], twLp[a+1]): even positions whose
+    // bins (a, a+1) mirror onto (b+1, b), a <= b
+    const int* pairs; const cplx<T>* pairw; int npair0;
+    const int* quadq; const cplx<T>* quadw; int nquad;
     int RB, RBP;          // rows per CTA, padded smem line count
     int mode, dot_kind, do_fft;
     int vec_ok;           // all row pointers are aligned for 2-element vector access
@@ -316,6 +321,8 @@ struct ColsParams {
     int mode;
     const void* spec; int spec_kind;   // FUSED: spectrum indexed [pos * spec_pitch + line]
     long spec_pitch;              // 0 = same as pitch
+    int spec_stage;               // specialised kernels: real spectrum tile staged through shared memory
+    int dbg;                      // developer experiments (0 in production)
     const int* done_flag;         // optional PCG early-exit flag
     // slab-decomposed grids: rows of the output (FWD) / input (INV) are scattered / gathered in blocks of `split_len`
     // positions, `split_stride` elements apart, so that the pass writes (reads) the all-to-all buffer directly
@@ -351,7 +358,7 @@ __global__ void __launch_bounds__(512) cols_pass_kernel(ColsParams<T> P) {
     if (P.mode == CM_FUSED) {
         for (int w = tid; w < L * TB; w += nthreads) {
             const int c = w % TB, i = w / TB;
-            if (c < nc) s[(size_t)i * TBP + c] = apply_spec(s[(size_t)i * TBP + c], P.spec, P.spec_kind, (size_t)i * P.pitch + c0 + c);
+            if (c < nc) s[(size_t)i * TBP + c] = apply_spec(s[(size_t)i * TBP + c], P.spec, P.spec_kind, (size_t)i * (P.spec_pitch ? P.spec_pitch : P.pitch) + c0 + c);
         }
         __syncthreads();
     }

@@ -1,29 +1,34 @@
 // fast_kernels.cuh -- compile-time specialised versions of the three matvec passes on the lane engine (lane_fft.cuh).
 //
-// Same math and the same digit-reversed layouts as conv_kernels.cuh (the generic, runtime-radix kernels stay as the
+// Same math and the same digit-reversed ordering as conv_kernels.cuh (the generic, runtime-radix kernels stay as the
 // fallback for lengths without an instantiation).  What is different:
 //   * a thread owns (butterfly, lane): 16-byte lanes (two fp32 lines / one fp64 line), LDS.128 / STS.128 only, packed
 //     f32x2 arithmetic across the two lines of a lane, all butterfly legs at [base + immediate];
+//   * the frequency workspace is kept in LANE layout (lane_fft.cuh), so the column pass moves lanes between global
+//     memory and registers with plain 16-byte accesses;
 //   * the first forward stage reads its operands straight from global memory (zero padding = skipped loads and a
 //     pruned butterfly when the upper half of the inputs is padding; PCG vector updates fused into the row loads) and
 //     the last inverse stage writes straight to global memory (crop = skipped stores, dot products fused);
-//   * column pass: last forward stage, spectrum multiply and first inverse stage run back to back in registers;
-//   * row passes: the r2c split / c2r merge works on (k, H-k) PAIRS (one thread produces both members from one pair of
-//     shared-memory reads) straight to / from global memory;
-//   * tiles are small (64-72 KB) so that two or three CTAs are resident per SM and one CTA's global traffic overlaps
-//     another's butterflies.
+//   * column pass: last forward stage, spectrum multiply and first inverse stage run back to back in registers; the
+//     spectrum tile is fetched with cp.async into shared memory at kernel start, so its latency hides behind the
+//     forward stages;
+//   * row passes: the r2c split / c2r merge works on QUADS -- two neighbouring bins and their two mirror bins -- so
+//     one thread turns four shared-memory lanes into 16-byte global accesses (the few bins of digit group 0, whose
+//     mirrors are irregular, go through a scalar path);
+//   * tiles are small (64-110 KB) so that two CTAs are resident per SM and one CTA's global traffic overlaps the
+//     other's butterflies.
 #pragma once
 #include "lane_fft.cuh"
 
 namespace hipgp {
 
 template <class T> __device__ __forceinline__ void ld2(const T* p, bool vec, T& a, T& b, bool ok0, bool ok1) {
-    if (vec && ok1) { const cplx<T> t = *reinterpret_cast<const cplx<T>*>(p); a = t.x; b = t.y; }
-    else { a = ok0 ? p[0] : (T)0; b = ok1 ? p[1] : (T)0; }
+    if (vec && ok1) { const cplx<T> t = ld_stream(reinterpret_cast<const cplx<T>*>(p)); a = t.x; b = t.y; }
+    else { a = ok0 ? ld_stream(p) : (T)0; b = ok1 ? ld_stream(p + 1) : (T)0; }
 }
 template <class T> __device__ __forceinline__ void st2(T* p, bool vec, T a, T b, bool ok0, bool ok1) {
-    if (vec && ok1) { *reinterpret_cast<cplx<T>*>(p) = mk<T>(a, b); }
-    else { if (ok0) p[0] = a; if (ok1) p[1] = b; }
+    if (vec && ok1) { st_stream(reinterpret_cast<cplx<T>*>(p), mk<T>(a, b)); }
+    else { if (ok0) st_stream(p, a); if (ok1) st_stream(p + 1, b); }
 }
 
 // deterministic per-row reduction of per-thread partials in smem scratch: warp `row` sums scratch[row*NI .. +NI)
@@ -37,24 +42,28 @@ __device__ __forceinline__ void rows_reduce_partials(const double* scratch, int 
     }
 }
 
-// spectrum factor(s) of one lane: `idx` = index of the lane's first line in the spectrum array
+// spectrum factor(s) of one lane, read from global memory: `idx` = index of the lane's first line in the spectrum
 __device__ __forceinline__ Lane<float> lane_spec(Lane<float> v, const void* spec, int kind, size_t idx) {
     if (kind == SPEC_REAL) {
-        const cplx<float> sv = ldg_c(reinterpret_cast<const cplx<float>*>(reinterpret_cast<const float*>(spec) + idx));   // two reals
+        const cplx<float> sv = ld_stream(reinterpret_cast<const cplx<float>*>(reinterpret_cast<const float*>(spec) + idx));   // two reals
         return lmul_real2(v, sv.x, sv.y);
     }
     const cplx<float>* sp = reinterpret_cast<const cplx<float>*>(spec) + idx;
-    const cplx<float> w0 = ldg_c(sp), w1 = ldg_c(sp + 1);
+    const cplx<float> w0 = ld_stream(sp), w1 = ld_stream(sp + 1);
     return kind == SPEC_CPLX ? lmul_cplx2<false>(v, w0, w1) : lmul_cplx2<true>(v, w0, w1);
 }
 __device__ __forceinline__ Lane<double> lane_spec(Lane<double> v, const void* spec, int kind, size_t idx) {
-    if (kind == SPEC_REAL) return lscale(v, __ldg(reinterpret_cast<const double*>(spec) + idx));
-    const cplx<double> w = ldg_c(reinterpret_cast<const cplx<double>*>(spec) + idx);
+    if (kind == SPEC_REAL) return lscale(v, ld_stream(reinterpret_cast<const double*>(spec) + idx));
+    const cplx<double> w = ld_stream(reinterpret_cast<const cplx<double>*>(spec) + idx);
     return kind == SPEC_CPLX ? lmul(v, w) : lmulc(v, w);
 }
+// real spectrum factor(s) of one lane staged in shared memory (8 bytes per lane)
+__device__ __forceinline__ Lane<float> lane_spec_smem(Lane<float> v, const void* p) { const cplx<float> sv = *reinterpret_cast<const cplx<float>*>(p); return lmul_real2(v, sv.x, sv.y); }
+__device__ __forceinline__ Lane<double> lane_spec_smem(Lane<double> v, const void* p) { return lscale(v, *reinterpret_cast<const double*>(p)); }
 
 // =====================================================================================================
 // Column pass.  A CTA owns NL lanes (= NL * LPT neighbouring lines) of one (outer, batch) slice.
+// Dynamic shared memory: the tile, then (P.spec_stage) NL * 8 bytes per padded position for the real spectrum tile.
 // =====================================================================================================
 template <class T, int NL, int NT, int MINB, int R0, int... Rs>
 __global__ void __launch_bounds__(NT, MINB) cols_fast_kernel(ColsParams<T> P) {
@@ -69,10 +78,8 @@ __global__ void __launch_bounds__(NT, MINB) cols_fast_kernel(ColsParams<T> P) {
     const cplx<T>* in = P.in + (size_t)blockIdx.y * P.in_ostride + (size_t)blockIdx.z * P.in_bstride + c0;
     cplx<T>* out = P.out + (size_t)blockIdx.y * P.out_ostride + (size_t)blockIdx.z * P.out_bstride + c0;
     const int mode = P.mode;
-    const long pitch = P.pitch;
+    const size_t pitch = (size_t)P.pitch;
     const size_t spitch = P.spec_pitch ? (size_t)P.spec_pitch : (size_t)P.pitch;
-    auto in_off = [&](int i) { return cols_rowoff<T>(i, pitch, P.in_split_len, P.in_split_stride); };
-    auto out_off = [&](int i) { return cols_rowoff<T>(i, pitch, P.out_split_len, P.out_split_stride); };
 
     if constexpr (NST == 1) {
         // the whole line lives in one thread's registers
@@ -82,7 +89,8 @@ __global__ void __launch_bounds__(NT, MINB) cols_fast_kernel(ColsParams<T> P) {
             const int rows_out = mode == CM_FWD ? Ln : P.n_out;
             Lane<T> v[R0];
 #pragma unroll
-            for (int r = 0; r < R0; ++r) v[r] = r < rows_in ? lane_from_global(in + in_off(r) + lane * LPT) : lzero<T>();
+            for (int r = 0; r < R0; ++r)
+                v[r] = r < rows_in ? lane_from_global(in + cols_rowoff<T>(r, P.pitch, P.in_split_len, P.in_split_stride) + lane * LPT) : lzero<T>();
             if (mode != CM_INV) lbfly<R0, false, T>(v);
             if (mode == CM_FUSED) {
 #pragma unroll
@@ -90,38 +98,53 @@ __global__ void __launch_bounds__(NT, MINB) cols_fast_kernel(ColsParams<T> P) {
             }
             if (mode != CM_FWD) lbfly<R0, true, T>(v);
 #pragma unroll
-            for (int r = 0; r < R0; ++r) if (r < rows_out) lane_to_global(out + out_off(r) + lane * LPT, v[r]);
+            for (int r = 0; r < R0; ++r)
+                if (r < rows_out) lane_to_global(out + cols_rowoff<T>(r, P.pitch, P.out_split_len, P.out_split_stride) + lane * LPT, v[r]);
         }
         return;
     } else {
         constexpr int LEG0 = G::leg(S0);
+        constexpr int SPEC_LANE = 8;                                  // bytes of real spectrum per lane (2 x fp32 or 1 x fp64)
+        unsigned char* sspec = smem_raw + G::smem_bytes();
+        auto sslot = [](int p) { return p + (p >> G::LOGRL); };       // padded position of the staged spectrum
         const cplx<T>* tw0 = P.f.twst + P.f.twoff[0];
+        const bool spec_smem = P.spec_stage != 0;
+
+        // ---- spectrum tile -> shared memory, asynchronously (consumed after the forward stages) ----
+        if (spec_smem) {
+            const unsigned char* sp = reinterpret_cast<const unsigned char*>(P.spec) + (size_t)c0 * sizeof(T);
+            constexpr int ROWB = NL * SPEC_LANE;                      // bytes per position
+            constexpr int CH = ROWB >= 16 ? 16 : 8, NCH = ROWB / CH;
+            constexpr int NIT = (Ln * NCH + NT - 1) / NT;
+#pragma unroll
+            for (int k = 0; k < NIT; ++k) {
+                const int w = tid + k * NT;
+                const int p = w / NCH, c = w - p * NCH;
+                if (w < Ln * NCH) cp_async<CH>(sspec + (size_t)sslot(p) * ROWB + c * CH, sp + (size_t)p * spitch * sizeof(T) + c * CH);
+            }
+            cp_async_commit();
+        }
 
         // ---- first forward stage, operands straight from global memory (zero padding = skipped loads) ----
         if (mode != CM_INV) {
             const int n_in = P.n_in;
             const bool zero_hi = is_pow2(R0) && n_in <= Ln / 2;
+            const size_t rstep = (size_t)S0 * pitch;
 #pragma unroll 1
             for (int it = tid; it < S0 * NL; it += NT) {
                 const int lane = it % NL, j = it / NL;
                 const bool ok = (long)lane * LPT < nvalid;
-                const cplx<T>* gp = in + lane * LPT;
+                const cplx<T>* gp = in + (size_t)j * pitch + lane * LPT;
                 cplx<T> w[R0];
                 lane_twiddles<R0, S0>(w, tw0, j);
                 Lane<T> v[R0];
                 if (zero_hi) {
 #pragma unroll
-                    for (int r = 0; r < R0 / 2; ++r) {
-                        const int i = j + r * S0;
-                        v[r] = (ok && i < n_in) ? lane_from_global(gp + in_off(i)) : lzero<T>();
-                    }
+                    for (int r = 0; r < R0 / 2; ++r) v[r] = (ok && j + r * S0 < n_in && !(P.dbg & 2)) ? lane_from_global(gp + r * rstep) : lzero<T>();
                     lbfly_zero_hi<R0, T>(v);
                 } else {
 #pragma unroll
-                    for (int r = 0; r < R0; ++r) {
-                        const int i = j + r * S0;
-                        v[r] = (ok && i < n_in) ? lane_from_global(gp + in_off(i)) : lzero<T>();
-                    }
+                    for (int r = 0; r < R0; ++r) v[r] = (ok && j + r * S0 < n_in) ? lane_from_global(gp + r * rstep) : lzero<T>();
                     lbfly<R0, false, T>(v);
                 }
 #pragma unroll
@@ -131,11 +154,12 @@ __global__ void __launch_bounds__(NT, MINB) cols_fast_kernel(ColsParams<T> P) {
                 for (int r = 0; r < R0; ++r) base[r * LEG0] = v[r];
             }
             __syncthreads();
-            LaneMidFwd<G, T, NL, NT, Ln / R0, 1, Rs...>::run(s, P.f, tid);
+            if (!(P.dbg & 1)) LaneMidFwd<G, T, NL, NT, Ln / R0, 1, Rs...>::run(s, P.f, tid);
         }
+        if (spec_smem) { cp_async_wait_all(); __syncthreads(); }
 
         // ---- last forward stage + spectrum + first inverse stage: RLAST neighbouring positions, in registers ----
-        {
+        if (!(P.dbg & 1)) {
 #pragma unroll 1
             for (int it = tid; it < (Ln / RLAST) * NL; it += NT) {
                 const int lane = it % NL, bf = it / NL;
@@ -144,22 +168,31 @@ __global__ void __launch_bounds__(NT, MINB) cols_fast_kernel(ColsParams<T> P) {
                 Lane<T>* base = s + (G::slot(p0) * NL + lane);
                 Lane<T> v[RLAST];
                 if (mode == CM_INV) {
+                    // (slab grids: rows may be gathered in blocks of in_split_len positions, a multiple of RLAST)
+                    const cplx<T>* gp = in + cols_rowoff<T>(p0, P.pitch, P.in_split_len, P.in_split_stride) + lane * LPT;
 #pragma unroll
-                    for (int r = 0; r < RLAST; ++r) v[r] = ok ? lane_from_global(in + in_off(p0 + r) + lane * LPT) : lzero<T>();
+                    for (int r = 0; r < RLAST; ++r) v[r] = ok ? lane_from_global(gp + r * pitch) : lzero<T>();
                 } else {
 #pragma unroll
                     for (int r = 0; r < RLAST; ++r) v[r] = base[r * NL];
                     lbfly<RLAST, false, T>(v);
                 }
-                if (mode == CM_FUSED && ok) {
-                    const size_t sidx = (size_t)p0 * spitch + c0 + lane * LPT;
+                if (mode == CM_FUSED) {
+                    if (spec_smem) {
+                        const unsigned char* sp = sspec + ((size_t)sslot(p0) * NL + lane) * SPEC_LANE;
 #pragma unroll
-                    for (int r = 0; r < RLAST; ++r) v[r] = lane_spec(v[r], P.spec, P.spec_kind, sidx + (size_t)r * spitch);
+                        for (int r = 0; r < RLAST; ++r) v[r] = lane_spec_smem(v[r], sp + r * NL * SPEC_LANE);
+                    } else if (ok) {
+                        const size_t sidx = (size_t)p0 * spitch + c0 + lane * LPT;
+#pragma unroll
+                        for (int r = 0; r < RLAST; ++r) v[r] = lane_spec(v[r], P.spec, P.spec_kind, sidx + (size_t)r * spitch);
+                    }
                 }
                 if (mode == CM_FWD) {
                     if (ok) {
+                        cplx<T>* gp = out + cols_rowoff<T>(p0, P.pitch, P.out_split_len, P.out_split_stride) + lane * LPT;
 #pragma unroll
-                        for (int r = 0; r < RLAST; ++r) lane_to_global(out + out_off(p0 + r) + lane * LPT, v[r]);
+                        for (int r = 0; r < RLAST; ++r) lane_to_global(gp + r * pitch, v[r]);
                     }
                 } else {
                     lbfly<RLAST, true, T>(v);
@@ -172,10 +205,11 @@ __global__ void __launch_bounds__(NT, MINB) cols_fast_kernel(ColsParams<T> P) {
         }
 
         // ---- inverse middle stages, then the last inverse stage straight to global memory (crop = skipped stores) ----
-        LaneMidInv<G, T, NL, NT, Ln / R0, 1, Rs...>::run(s, P.f, tid);
+        if (!(P.dbg & 1)) LaneMidInv<G, T, NL, NT, Ln / R0, 1, Rs...>::run(s, P.f, tid);
         {
             const int n_out = P.n_out;
             const bool out_lo = is_pow2(R0) && n_out <= Ln / 2;
+            const size_t rstep = (size_t)S0 * pitch;
 #pragma unroll 1
             for (int it = tid; it < S0 * NL; it += NT) {
                 const int lane = it % NL, j = it / NL;
@@ -188,18 +222,18 @@ __global__ void __launch_bounds__(NT, MINB) cols_fast_kernel(ColsParams<T> P) {
                 for (int r = 0; r < R0; ++r) v[r] = base[r * LEG0];
 #pragma unroll
                 for (int r = 1; r < R0; ++r) v[r] = lmulc(v[r], w[r]);
-                cplx<T>* gp = out + lane * LPT;
+                cplx<T>* gp = out + (size_t)j * pitch + lane * LPT;
                 if (out_lo) {          // outputs R0/2 .. R0-1 are cropped: the compiler drops their arithmetic
                     lbfly<R0, true, T>(v);
-                    if (ok) {
+                    if (ok && !(P.dbg & 4)) {
 #pragma unroll
-                        for (int r = 0; r < R0 / 2; ++r) { const int i = j + r * S0; if (i < n_out) lane_to_global(gp + out_off(i), v[r]); }
+                        for (int r = 0; r < R0 / 2; ++r) if (j + r * S0 < n_out) lane_to_global(gp + r * rstep, v[r]);
                     }
                 } else {
                     lbfly<R0, true, T>(v);
                     if (ok) {
 #pragma unroll
-                        for (int r = 0; r < R0; ++r) { const int i = j + r * S0; if (i < n_out) lane_to_global(gp + out_off(i), v[r]); }
+                        for (int r = 0; r < R0; ++r) if (j + r * S0 < n_out) lane_to_global(gp + r * rstep, v[r]);
                     }
                 }
             }
@@ -210,6 +244,8 @@ __global__ void __launch_bounds__(NT, MINB) cols_fast_kernel(ColsParams<T> P) {
 // =====================================================================================================
 // Row passes.  H = product of the radix list; a CTA owns NL lanes = NL * LPT rows.
 // =====================================================================================================
+struct __align__(8) QuadIdx { int a, b; };     // even positions of a quad: bins (a, a+1) mirror bins (b+1, b)
+
 template <class T, int NL, int NT, int MINB, int R0, int... Rs>
 __global__ void __launch_bounds__(NT, MINB) rows_fwd_fast_kernel(RowsParams<T> P) {
     using G = TileGeo<T, NL, R0, Rs...>;
@@ -246,62 +282,84 @@ __global__ void __launch_bounds__(NT, MINB) rows_fwd_fast_kernel(RowsParams<T> P
     {
         const bool zero_hi = is_pow2(R0) && R0 > 1 && (n + 1) / 2 <= H / 2;
         const cplx<T>* tw0 = P.f.twst + P.f.twoff[0];
-        // element loader: packed complex e = x[2e] + i x[2e+1] of row `row` (tile-local), with the fused vector update
-        auto load_elem = [&](int row, int e, double& accd) -> cplx<T> {
-            const int i = 2 * e;
-            const bool ok0 = i < n, ok1 = i + 1 < n;
-            T a = 0, b2 = 0;
-            if (row < nl && ok0) {
-                const size_t off = (size_t)(g0 + row) * n + i;
-                const T coef = s_coef[row];
-                if (mode == RF_PLAIN) {
-                    ld2(P.in + off, vec, a, b2, ok0, ok1);
-                } else if (mode == RF_PUPDATE) {
-                    T z0, z1; ld2(P.in + off, vec, z0, z1, ok0, ok1);
-                    if (first_it) { a = z0; b2 = z1; }
-                    else { T p0, p1; ld2((const T*)P.v0 + off, vec, p0, p1, ok0, ok1); a = z0 + coef * p0; b2 = z1 + coef * p1; }
-                    st2(P.v0 + off, vec, a, b2, ok0, ok1);
-                } else if (mode == RF_SELFDOT) {
-                    ld2(P.in + off, vec, a, b2, ok0, ok1);
-                    accd += (double)(a * a) + (double)(b2 * b2);
-                } else {
-                    T p0, p1, x0, x1, r0, r1, q0, q1;
-                    ld2(P.v2 + off, vec, p0, p1, ok0, ok1);
-                    ld2((const T*)P.v1 + off, vec, x0, x1, ok0, ok1);
-                    ld2((const T*)P.v0 + off, vec, r0, r1, ok0, ok1);
-                    ld2(P.in + off, vec, q0, q1, ok0, ok1);
-                    st2(P.v1 + off, vec, x0 + coef * p0, x1 + coef * p1, ok0, ok1);
-                    a = r0 - coef * q0; b2 = ok1 ? r1 - coef * q1 : (T)0;
-                    st2(P.v0 + off, vec, a, b2, ok0, ok1);
-                    accd += (double)(a * a) + (double)(b2 * b2);
-                }
-            }
-            return mk<T>(a, b2);
-        };
 #pragma unroll 1
         for (int it = tid; it < S0 * NL; it += NT) {
             const int lane = it % NL, j = it / NL;
             cplx<T> w[R0];
             if (NST > 1) lane_twiddles<R0, S0>(w, tw0, j);
             double accd[LPT];
+            size_t off[LPT];
+            bool rok[LPT];
+            T coef[LPT];
 #pragma unroll
-            for (int l = 0; l < LPT; ++l) accd[l] = 0.0;
-            Lane<T> v[R0];
-            if (zero_hi) {
-#pragma unroll
-                for (int r = 0; r < R0 / 2; ++r) {
-#pragma unroll
-                    for (int l = 0; l < LPT; ++l) lane_set(v[r], l, load_elem(lane * LPT + l, j + r * S0, accd[l]));
+            for (int l = 0; l < LPT; ++l) {
+                const int row = lane * LPT + l;
+                accd[l] = 0.0; rok[l] = row < nl; off[l] = (size_t)(g0 + row) * n + 2 * j; coef[l] = s_coef[row];
+            }
+            // element loaders: packed complex e = j + r*S0  ->  x[2e] + i x[2e+1] of line l, with the fused vector update
+            auto ld_plain = [&](int l, int r) -> cplx<T> {
+                const int i = 2 * (j + r * S0); const bool ok0 = rok[l] && i < n, ok1 = rok[l] && i + 1 < n;
+                T a = 0, b2 = 0;
+                if (ok0) ld2(P.in + off[l] + 2 * r * S0, vec, a, b2, ok0, ok1);
+                return mk<T>(a, b2);
+            };
+            auto ld_pupdate = [&](int l, int r) -> cplx<T> {
+                const int i = 2 * (j + r * S0); const bool ok0 = rok[l] && i < n, ok1 = rok[l] && i + 1 < n;
+                T a = 0, b2 = 0;
+                if (ok0) {
+                    const size_t o = off[l] + 2 * r * S0;
+                    ld2(P.in + o, vec, a, b2, ok0, ok1);
+                    if (!first_it) { T p0, p1; ld2((const T*)P.v0 + o, vec, p0, p1, ok0, ok1); a = a + coef[l] * p0; b2 = b2 + coef[l] * p1; }
+                    st2(P.v0 + o, vec, a, b2, ok0, ok1);
                 }
+                return mk<T>(a, b2);
+            };
+            auto ld_selfdot = [&](int l, int r) -> cplx<T> {
+                const int i = 2 * (j + r * S0); const bool ok0 = rok[l] && i < n, ok1 = rok[l] && i + 1 < n;
+                T a = 0, b2 = 0;
+                if (ok0) { ld2(P.in + off[l] + 2 * r * S0, vec, a, b2, ok0, ok1); accd[l] += (double)(a * a) + (double)(b2 * b2); }
+                return mk<T>(a, b2);
+            };
+            auto ld_xrupdate = [&](int l, int r) -> cplx<T> {
+                const int i = 2 * (j + r * S0); const bool ok0 = rok[l] && i < n, ok1 = rok[l] && i + 1 < n;
+                T a = 0, b2 = 0;
+                if (ok0) {
+                    const size_t o = off[l] + 2 * r * S0;
+                    T p0, p1, x0, x1, r0, r1, q0, q1;
+                    ld2(P.v2 + o, vec, p0, p1, ok0, ok1);
+                    ld2((const T*)P.v1 + o, vec, x0, x1, ok0, ok1);
+                    ld2((const T*)P.v0 + o, vec, r0, r1, ok0, ok1);
+                    ld2(P.in + o, vec, q0, q1, ok0, ok1);
+                    st2(P.v1 + o, vec, x0 + coef[l] * p0, x1 + coef[l] * p1, ok0, ok1);
+                    a = r0 - coef[l] * q0; b2 = ok1 ? r1 - coef[l] * q1 : (T)0;
+                    st2(P.v0 + o, vec, a, b2, ok0, ok1);
+                    accd[l] += (double)(a * a) + (double)(b2 * b2);
+                }
+                return mk<T>(a, b2);
+            };
+            Lane<T> v[R0];
+            // (each line's loader runs exactly once per element: the fused updates have side effects)
+            auto fill1 = [&](auto& ld, int r) -> Lane<T> {
+                const cplx<T> e0 = ld(0, r);
+                if constexpr (LPT == 2) { const cplx<T> e1 = ld(1, r); return lane_make(e0, e1); }
+                else return lane_make(e0, e0);
+            };
+#define HIPGP_FILL(RC, LD)                                                                                  \
+            _Pragma("unroll") for (int r = 0; r < (RC); ++r) v[r] = fill1(LD, r);
+            if (zero_hi) {
+                if (mode == RF_PLAIN) { HIPGP_FILL(R0 / 2, ld_plain) }
+                else if (mode == RF_PUPDATE) { HIPGP_FILL(R0 / 2, ld_pupdate) }
+                else if (mode == RF_XRUPDATE) { HIPGP_FILL(R0 / 2, ld_xrupdate) }
+                else { HIPGP_FILL(R0 / 2, ld_selfdot) }
                 lbfly_zero_hi<R0, T>(v);
             } else {
-#pragma unroll
-                for (int r = 0; r < R0; ++r) {
-#pragma unroll
-                    for (int l = 0; l < LPT; ++l) lane_set(v[r], l, load_elem(lane * LPT + l, j + r * S0, accd[l]));
-                }
+                auto ld_any = [&](int l, int r) -> cplx<T> {
+                    return mode == RF_PLAIN ? ld_plain(l, r) : (mode == RF_PUPDATE ? ld_pupdate(l, r) : (mode == RF_XRUPDATE ? ld_xrupdate(l, r) : ld_selfdot(l, r)));
+                };
+                HIPGP_FILL(R0, ld_any)
                 lbfly<R0, false, T>(v);
             }
+#undef HIPGP_FILL
             if (want_dot) {
 #pragma unroll
                 for (int l = 0; l < LPT; ++l) scratch[(lane * LPT + l) * S0 + j] = accd[l];
@@ -327,37 +385,77 @@ __global__ void __launch_bounds__(NT, MINB) rows_fwd_fast_kernel(RowsParams<T> P
         __syncthreads();
     }
 
-    // ---- r2c split on (k, H-k) pairs, straight to global memory ----
-    {
+    // ---- r2c split, straight to global memory ----
+    // (a) pairs (k, H-k) of digit group 0 (all pairs when the list has a single stage): scalar W accesses
+    constexpr int NPAIR0 = NST > 1 ? RLAST / 2 + 1 : H / 2 + 1;
+    constexpr int NQUAD = NST > 1 ? (H - RLAST) / 4 : 0;
 #pragma unroll 1
-        for (int it = tid; it < (H / 2 + 1) * NL; it += NT) {
-            const int lane = it % NL, pi = it / NL;
-            const int q = P.pairq[pi];
-            Lane<T> Xa, Xb;
-            int qb;
-            bool two;
-            if (q == 0) {
-                const Lane<T> z = s[lane];
-                Lane<T> t; t.re = z.im; t.im = z.im;                 // (im, im)
-                Lane<T> u; u.re = z.re; u.im = z.re;                 // (re, re)
-                Xa = lscale(u + t, (T)2); Xb = lscale(u - t, (T)2);  // re parts are the values; im parts are zeroed below
-                Xa.im = lzero<T>().im; Xb.im = lzero<T>().im;
-                qb = H; two = true;
-            } else {
-                const int q2 = P.part[q];
-                const Lane<T> a = s[G::slot(q) * NL + lane], c = lconj(s[G::slot(q2) * NL + lane]);
-                const Lane<T> E = a + c;
-                const Lane<T> t = lmul(lmi<false>(a - c), P.twLp[q]);
-                Xa = E + t; Xb = lconj(E - t);
-                qb = q2; two = q2 != q;
-            }
+    for (int it = tid; it < NPAIR0 * NL; it += NT) {
+        const int lane = it % NL, pi = it / NL;
+        const QuadIdx pq = reinterpret_cast<const QuadIdx*>(P.pairs)[pi];
+        const int q = pq.a, q2 = pq.b;
+        Lane<T> Xa, Xb;
+        bool two;
+        if (q == 0) {
+            const Lane<T> z = s[lane];
+            Lane<T> zs; zs.re = z.im; zs.im = z.re;
+            Xa = lscale(z + zs, (T)2); Xb = lscale(z - zs, (T)2);       // .re = 2 (re +- im); imaginary parts are zero
+            Xa.im = lzero<T>().im; Xb.im = lzero<T>().im;
+            two = true;
+        } else {
+            const cplx<T> wq = ldg_c(P.pairw + pi);
+            const Lane<T> a = s[G::slot(q) * NL + lane], c = lconj(s[G::slot(q2) * NL + lane]);
+            const Lane<T> E = a + c;
+            const Lane<T> t = lmul(lmi<false>(a - c), wq);
+            Xa = E + t; Xb = lconj(E - t);
+            two = q2 != q;
+        }
 #pragma unroll
-            for (int l = 0; l < LPT; ++l) {
-                const int row = lane * LPT + l;
-                if (row < nl) {
-                    cplx<T>* dst = P.W + s_wbase[row];
-                    dst[q] = lane_get(Xa, l);
-                    if (two) dst[qb] = lane_get(Xb, l);
+        for (int l = 0; l < LPT; ++l) {
+            const int row = lane * LPT + l;
+            if (row < nl) {
+                cplx<T>* dst = P.W + s_wbase[row];
+                WRow<T>::store1(dst, q, lane_get(Xa, l));
+                if (two) WRow<T>::store1(dst, q2, lane_get(Xb, l));
+            }
+        }
+    }
+    // (b) quads: bins (a, a+1) and their mirrors (b+1, b): four lanes in, 16-byte stores out.  The table loads of
+    //     all of a thread's quads are issued up front.
+    if constexpr (NQUAD > 0) {
+        constexpr int QIT = (NQUAD * NL + NT - 1) / NT;
+        QuadIdx qq[QIT]; cplx<T> wa[QIT], wa1[QIT];
+#pragma unroll
+        for (int k = 0; k < QIT; ++k) {
+            const int it = tid + k * NT, qi = it / NL;
+            if (it < NQUAD * NL) { qq[k] = reinterpret_cast<const QuadIdx*>(P.quadq)[qi]; wa[k] = ldg_c(P.quadw + 2 * qi); wa1[k] = ldg_c(P.quadw + 2 * qi + 1); }
+        }
+#pragma unroll
+        for (int k = 0; k < QIT; ++k) {
+            const int it = tid + k * NT, lane = it % NL;
+            if (it < NQUAD * NL) {
+                const Lane<T>* pa = s + (G::slot(qq[k].a) * NL + lane);
+                const Lane<T>* pb = s + (G::slot(qq[k].b) * NL + lane);
+                const Lane<T> za = pa[0], za1 = pa[NL], zb = pb[0], zb1 = pb[NL];
+                // bin a with mirror b+1
+                Lane<T> c = lconj(zb1);
+                Lane<T> E = za + c;
+                Lane<T> t = lmul(lmi<false>(za - c), wa[k]);
+                const Lane<T> Xa = E + t, Xb1 = lconj(E - t);
+                // bin a+1 with mirror b
+                c = lconj(zb);
+                E = za1 + c;
+                t = lmul(lmi<false>(za1 - c), wa1[k]);
+                const Lane<T> Xa1 = E + t, Xb = lconj(E - t);
+                const bool self = qq[k].a == qq[k].b;    // the quad mirrors onto itself: bins (a, a+1) are each other's mirror
+#pragma unroll
+                for (int l = 0; l < LPT; ++l) {
+                    const int row = lane * LPT + l;
+                    if (row < nl) {
+                        cplx<T>* dst = P.W + s_wbase[row];
+                        if (self) WRow<T>::store2(dst, qq[k].a, lane_get(Xa, l), lane_get(Xb1, l));
+                        else { WRow<T>::store2(dst, qq[k].a, lane_get(Xa, l), lane_get(Xa1, l)); WRow<T>::store2(dst, qq[k].b, lane_get(Xb, l), lane_get(Xb1, l)); }
+                    }
                 }
             }
         }
@@ -387,36 +485,89 @@ __global__ void __launch_bounds__(NT, MINB) rows_inv_fast_kernel(RowsParams<T> P
     }
     __syncthreads();
 
-    // ---- c2r merge on (k, H-k) pairs, straight from global memory into shared memory ----
-    {
-        const int spec_kind = P.spec_kind;
+    // ---- c2r merge, straight from global memory into shared memory ----
+    const int spec_kind = P.spec_kind;
+    constexpr int NPAIR0 = NST > 1 ? RLAST / 2 + 1 : H / 2 + 1;
+    constexpr int NQUAD = NST > 1 ? (H - RLAST) / 4 : 0;
+    // (a) pairs of digit group 0 (all pairs when the list has a single stage)
 #pragma unroll 1
-        for (int it = tid; it < (H / 2 + 1) * NL; it += NT) {
-            const int lane = it % NL, pi = it / NL;
-            const int q = P.pairq[pi];
-            const int q2 = q == 0 ? H : P.part[q];
-            Lane<T> a = lzero<T>(), c = lzero<T>();
+    for (int it = tid; it < NPAIR0 * NL; it += NT) {
+        const int lane = it % NL, pi = it / NL;
+        const QuadIdx pq = reinterpret_cast<const QuadIdx*>(P.pairs)[pi];
+        const int q = pq.a, q2 = pq.b;
+        const cplx<T> wq = ldg_c(P.pairw + pi);
+        cplx<T> ya[LPT], yc[LPT];
 #pragma unroll
-            for (int l = 0; l < LPT; ++l) {
-                const int row = lane * LPT + l;
-                if (row < nl) {
-                    const cplx<T>* src = P.W + s_wbase[row];
-                    cplx<T> ya = src[q], yc = src[q2];
-                    if (spec_kind != SPEC_NONE) { ya = apply_spec(ya, P.spec, spec_kind, (size_t)q); yc = apply_spec(yc, P.spec, spec_kind, (size_t)q2); }
-                    lane_set(a, l, ya); lane_set(c, l, yc);
-                }
+        for (int l = 0; l < LPT; ++l) {
+            const int row = lane * LPT + l;
+            ya[l] = mk<T>(0, 0); yc[l] = mk<T>(0, 0);
+            if (row < nl) {
+                const cplx<T>* src = P.W + s_wbase[row];
+                ya[l] = WRow<T>::load1(src, q); yc[l] = WRow<T>::load1(src, q2);
+                if (spec_kind != SPEC_NONE) { ya[l] = apply_spec(ya[l], P.spec, spec_kind, (size_t)q); yc[l] = apply_spec(yc[l], P.spec, spec_kind, (size_t)q2); }
             }
-            if (q == 0) {
-                // Z[0] = (Y0 + YH) + i (Y0 - YH), real parts only
-                Lane<T> z; z.re = (a + c).re; z.im = (a - c).re;
-                s[lane] = z;
-            } else {
-                // bin q (frequency k):  E + i O with O = conj(w^k)(Y[k] - conj Y[k']);  bin q2 is conj(E - i O)
-                c = lconj(c);
-                const Lane<T> E = a + c;
-                const Lane<T> iO = lmi<true>(lmulc(a - c, P.twLp[q]));
-                s[G::slot(q) * NL + lane] = E + iO;
-                if (q2 != q) s[G::slot(q2) * NL + lane] = lconj(E - iO);
+        }
+        const Lane<T> a = lane_make(ya[0], ya[LPT - 1]);
+        Lane<T> c = lane_make(yc[0], yc[LPT - 1]);
+        if (q == 0) {
+            // Z[0] = (Y0 + YH) + i (Y0 - YH), real parts only
+            Lane<T> z; z.re = (a + c).re; z.im = (a - c).re;
+            s[lane] = z;
+        } else {
+            // bin q (frequency k):  E + i O with O = conj(w^k)(Y[k] - conj Y[k']);  bin q2 is conj(E - i O)
+            c = lconj(c);
+            const Lane<T> E = a + c;
+            const Lane<T> iO = lmi<true>(lmulc(a - c, wq));
+            s[G::slot(q) * NL + lane] = E + iO;
+            if (q2 != q) s[G::slot(q2) * NL + lane] = lconj(E - iO);
+        }
+    }
+    // (b) quads: table and workspace loads of all of a thread's quads are issued up front
+    if constexpr (NQUAD > 0) {
+        constexpr int QIT = (NQUAD * NL + NT - 1) / NT;
+        QuadIdx qq[QIT]; cplx<T> wa[QIT], wa1[QIT];
+#pragma unroll
+        for (int k = 0; k < QIT; ++k) {
+            const int it = tid + k * NT, qi = it / NL;
+            if (it < NQUAD * NL) { qq[k] = reinterpret_cast<const QuadIdx*>(P.quadq)[qi]; wa[k] = ldg_c(P.quadw + 2 * qi); wa1[k] = ldg_c(P.quadw + 2 * qi + 1); }
+        }
+#pragma unroll
+        for (int k = 0; k < QIT; ++k) {
+            const int it = tid + k * NT, lane = it % NL;
+            if (it < NQUAD * NL) {
+                const bool self = qq[k].a == qq[k].b;
+                cplx<T> ya[LPT], ya1[LPT], yb[LPT], yb1[LPT];
+#pragma unroll
+                for (int l = 0; l < LPT; ++l) {
+                    const int row = lane * LPT + l;
+                    ya[l] = ya1[l] = yb[l] = yb1[l] = mk<T>(0, 0);
+                    if (row < nl) {
+                        const cplx<T>* src = P.W + s_wbase[row];
+                        WRow<T>::load2(src, qq[k].a, ya[l], ya1[l]);
+                        if (self) { yb[l] = ya[l]; yb1[l] = ya1[l]; } else WRow<T>::load2(src, qq[k].b, yb[l], yb1[l]);
+                        if (spec_kind != SPEC_NONE) {
+                            ya[l] = apply_spec(ya[l], P.spec, spec_kind, (size_t)qq[k].a); ya1[l] = apply_spec(ya1[l], P.spec, spec_kind, (size_t)qq[k].a + 1);
+                            yb[l] = apply_spec(yb[l], P.spec, spec_kind, (size_t)qq[k].b); yb1[l] = apply_spec(yb1[l], P.spec, spec_kind, (size_t)qq[k].b + 1);
+                        }
+                    }
+                }
+                const Lane<T> A = lane_make(ya[0], ya[LPT - 1]), A1 = lane_make(ya1[0], ya1[LPT - 1]);
+                const Lane<T> Bn = lane_make(yb[0], yb[LPT - 1]), B1 = lane_make(yb1[0], yb1[LPT - 1]);
+                Lane<T>* pa = s + (G::slot(qq[k].a) * NL + lane);
+                Lane<T>* pb = s + (G::slot(qq[k].b) * NL + lane);
+                // bin a with mirror b+1
+                Lane<T> c = lconj(B1);
+                Lane<T> E = A + c;
+                Lane<T> iO = lmi<true>(lmulc(A - c, wa[k]));
+                pa[0] = E + iO;
+                pb[NL] = lconj(E - iO);
+                if (!self) {   // bin a+1 with mirror b
+                    c = lconj(Bn);
+                    E = A1 + c;
+                    iO = lmi<true>(lmulc(A1 - c, wa1[k]));
+                    pa[NL] = E + iO;
+                    pb[0] = lconj(E - iO);
+                }
             }
         }
     }
@@ -434,18 +585,6 @@ __global__ void __launch_bounds__(NT, MINB) rows_inv_fast_kernel(RowsParams<T> P
     {
         const bool out_lo = is_pow2(R0) && R0 > 1 && (n + 1) / 2 <= H / 2;
         const cplx<T>* tw0 = P.f.twst + P.f.twoff[0];
-        auto store_elem = [&](int row, int e, cplx<T> val, double& accd) {
-            const int i = 2 * e;
-            const bool ok0 = i < n, ok1 = i + 1 < n;
-            if (row < nl && ok0) {
-                const size_t off = (size_t)(g0 + row) * n + i;
-                st2(P.out + off, vec, val.x, val.y, ok0, ok1);
-                if (want_dot) {
-                    T o0, o1; ld2((const T*)P.v0 + off, vec, o0, o1, ok0, ok1);
-                    accd += (double)(val.x * o0) + (ok1 ? (double)(val.y * o1) : 0.0);
-                }
-            }
-        };
 #pragma unroll 1
         for (int it = tid; it < S0 * NL; it += NT) {
             const int lane = it % NL, j = it / NL;
@@ -460,23 +599,28 @@ __global__ void __launch_bounds__(NT, MINB) rows_inv_fast_kernel(RowsParams<T> P
                 for (int r = 1; r < R0; ++r) v[r] = lmulc(v[r], w[r]);
             }
             double accd[LPT];
+            size_t off[LPT];
+            bool rok[LPT];
 #pragma unroll
-            for (int l = 0; l < LPT; ++l) accd[l] = 0.0;
-            if (out_lo) {
-                lbfly<R0, true, T>(v);
-#pragma unroll
-                for (int r = 0; r < R0 / 2; ++r) {
-#pragma unroll
-                    for (int l = 0; l < LPT; ++l) store_elem(lane * LPT + l, j + r * S0, lane_get(v[r], l), accd[l]);
+            for (int l = 0; l < LPT; ++l) { const int row = lane * LPT + l; accd[l] = 0.0; rok[l] = row < nl; off[l] = (size_t)(g0 + row) * n + 2 * j; }
+            auto st_elem = [&](int l, int r, cplx<T> val, bool dot) {
+                const int i = 2 * (j + r * S0);
+                const bool ok0 = rok[l] && i < n, ok1 = rok[l] && i + 1 < n;
+                if (ok0) {
+                    const size_t o = off[l] + 2 * r * S0;
+                    st2(P.out + o, vec, val.x, val.y, ok0, ok1);
+                    if (dot) {
+                        T o0, o1; ld2((const T*)P.v0 + o, vec, o0, o1, ok0, ok1);
+                        accd[l] += (double)(val.x * o0) + (ok1 ? (double)(val.y * o1) : 0.0);
+                    }
                 }
-            } else {
-                lbfly<R0, true, T>(v);
-#pragma unroll
-                for (int r = 0; r < R0; ++r) {
-#pragma unroll
-                    for (int l = 0; l < LPT; ++l) store_elem(lane * LPT + l, j + r * S0, lane_get(v[r], l), accd[l]);
-                }
-            }
+            };
+            lbfly<R0, true, T>(v);
+#define HIPGP_DRAIN(RC, DOT)                                                                                \
+            _Pragma("unroll") for (int r = 0; r < (RC); ++r) { _Pragma("unroll") for (int l = 0; l < LPT; ++l) st_elem(l, r, lane_get(v[r], l), DOT); }
+            if (out_lo) { if (want_dot) { HIPGP_DRAIN(R0 / 2, true) } else { HIPGP_DRAIN(R0 / 2, false) } }
+            else { if (want_dot) { HIPGP_DRAIN(R0, true) } else { HIPGP_DRAIN(R0, false) } }
+#undef HIPGP_DRAIN
             if (want_dot) {
 #pragma unroll
                 for (int l = 0; l < LPT; ++l) scratch[(lane * LPT + l) * S0 + j] = accd[l];

@@ -5,8 +5,11 @@
 
 namespace hipgp {
 
-#ifndef HIPGP_NL_MUL      /* developer knob: scale the lanes per CTA (and the threads with them) */
+#ifndef HIPGP_NL_MUL      /* developer knobs: scale the lanes per CTA (and the threads with them) */
 #define HIPGP_NL_MUL 1
+#endif
+#ifndef HIPGP_NL_DIV
+#define HIPGP_NL_DIV 1
 #endif
 
 constexpr int cfg_min(int a, int b) { return a < b ? a : b; }
@@ -22,9 +25,13 @@ struct FastCfg {
     static constexpr int RMAX = RLMax<List>::value;
     static constexpr int BFN = Ln / RMAX;                       // butterflies per line in the widest stage
     static constexpr int NL0 = pow2_floor(cfg_max(1, cfg_min(256 / cfg_max(BFN, 1), 4096 / Ln)));
-    static constexpr int NL = cfg_max(1, cfg_min(16, NL0 * HIPGP_NL_MUL));
+    static constexpr int NL = cfg_max(1, cfg_min(16, NL0 * HIPGP_NL_MUL / HIPGP_NL_DIV));
     static constexpr int NT = cfg_min(512, cfg_max(32, (BFN * NL + 31) / 32 * 32));
+#ifdef HIPGP_MINB
+    static constexpr int MINB = HIPGP_MINB;
+#else
     static constexpr int MINB = cfg_max(1, 512 / NT);
+#endif
     static constexpr int LPT = LaneInfo<T>::LPT;
     static constexpr int S0 = Ln / (RLInfo<List>::count ? RLFirst<List>::value : 1);
 };
@@ -36,6 +43,11 @@ static void launch_rows_fast_t(hipgp_plan* pl, bool inverse, RowsParams<T>& P, c
     constexpr int NROW = C::NL * C::LPT;
     static_assert(NROW <= 32, "per-row scalars are held in 32-entry shared arrays");
     P.RB = NROW; P.RBP = NROW;
+    {   // the kernels take the pair / quad structure of the digit-reversed order as compile-time facts
+        constexpr int NST = G::NST, H = C::Ln;
+        const int want_q = NST > 1 ? (H - G::RLAST) / 4 : 0, want_p = NST > 1 ? G::RLAST / 2 + 1 : H / 2 + 1;
+        if (P.nquad != want_q || P.npair0 != want_p) throw Error("internal: unexpected r2c pair structure for H = " + std::to_string(H));
+    }
     const size_t smem = G::smem_bytes() + sizeof(double) * (size_t)C::S0 * NROW;
     dim3 grid((unsigned)((P.total_rows + NROW - 1) / NROW));
     PROF_BEGIN(pl, inverse ? 2 : 0, st);
@@ -60,7 +72,15 @@ static void launch_cols_fast_t(hipgp_plan* pl, ColsParams<T>& P, long n_outer, l
     static_assert(C::Ln == LEN, "radix list does not multiply to the length");
     constexpr int TBL = C::NL * C::LPT;
     P.TB = TBL; P.TBP = TBL;
-    const size_t smem = G::smem_bytes();
+    if ((P.in_split_len && (P.mode != CM_INV || P.in_split_len % G::RLAST)) || (P.out_split_len && (P.mode != CM_FWD || P.out_split_len % G::RLAST)))
+        throw Error("split row blocks are supported for forward-only outputs / inverse-only inputs, in multiples of the last radix");
+    // real spectrum tile through shared memory (8 bytes per lane and padded position) when two CTAs still fit an SM
+    const size_t spec_bytes = (size_t)(C::Ln + C::Ln / G::RLAST) * C::NL * 8;
+    static const char* env_ns = getenv("HIPGP_NO_SPEC_STAGE");
+    P.spec_stage = (G::NST > 1 && P.mode == CM_FUSED && P.spec_kind == SPEC_REAL && C::MINB * (G::smem_bytes() + spec_bytes + 1024) <= 227 * 1024 && !env_ns) ? 1 : 0;
+    static const char* env_dbg = getenv("HIPGP_DBG");
+    P.dbg = env_dbg ? atoi(env_dbg) : 0;
+    const size_t smem = G::smem_bytes() + (P.spec_stage ? spec_bytes : 0);
     dim3 grid((unsigned)((P.inner + TBL - 1) / TBL), (unsigned)n_outer, (unsigned)B);
     auto k = cols_fast_kernel<T, C::NL, C::NT, C::MINB, Rs...>;
     if (smem > 48 * 1024) HIPGP_SET_MAX_SMEM(k, smem);
@@ -91,7 +111,7 @@ HIPGP_FAST_LIST(X)
 #undef X
 template <class T, int LEN> void launch_rows_fast_len(hipgp_plan* pl, bool inverse, RowsParams<T>& P, cudaStream_t st) { FastList<T, LEN>::rows(pl, inverse, P, st); }
 template <class T, int LEN> bool launch_cols_fast_len(hipgp_plan* pl, ColsParams<T>& P, long n_outer, long B, cudaStream_t st) {
-    if (!cols_lane_aligned<T>(P)) return false;
+    if (!cols_lane_aligned<T>(P)) throw Error("column pass: pointers / strides are not 16-byte aligned");
     FastList<T, LEN>::cols(pl, P, n_outer, B, st);
     return true;
 }

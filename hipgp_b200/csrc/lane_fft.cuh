@@ -95,21 +95,122 @@ __device__ __forceinline__ cplx<double> lane_get(const Lane<double>& a, int) { r
 __device__ __forceinline__ void lane_set(Lane<float>& a, int l, cplx<float> v) { if (l) { a.re.y = v.x; a.im.y = v.y; } else { a.re.x = v.x; a.im.x = v.y; } }
 __device__ __forceinline__ void lane_set(Lane<double>& a, int, cplx<double> v) { a.re = v.x; a.im = v.y; }
 
-// 16-byte global accesses of LPT interleaved complex numbers (lines c, c+1 of one row position)
+// ---- frequency-workspace layout ------------------------------------------------------------------------------
+// The specialised kernels keep the frequency workspace W in LANE layout: for fp32 the two neighbouring bins (2c, 2c+1)
+// of a row are stored as (re_2c, re_2c+1, im_2c, im_2c+1), i.e. exactly one Lane<float>, so the column pass moves
+// lanes with plain 16-byte accesses and no register shuffling; for fp64 a lane is one interleaved complex number.
+// (The generic kernels of conv_kernels.cuh use interleaved complex for both, so an fp32 pipeline is either all
+// specialised or all generic -- see run_pipeline.)
 struct __align__(16) Raw16f { float a, b, c, d; };
+// Streaming data (vectors, the frequency workspace, spectrum tiles) is moved with L2-only cache policy (ld/st.global.cg)
+// so that it does not evict the small twiddle / pairing tables, which are read through L1 by every CTA of an SM.
+// (.cg loads are coherent at L2: fine for the in-place column pass.)
+#ifdef HIPGP_EMU
+template <class V> __device__ __forceinline__ V ld_stream(const V* p) { return *p; }
+template <class V> __device__ __forceinline__ void st_stream(V* p, V v) { *p = v; }
+#else
+__device__ __forceinline__ float ld_stream(const float* p) { return __ldcg(p); }
+__device__ __forceinline__ double ld_stream(const double* p) { return __ldcg(p); }
+__device__ __forceinline__ cplx<float> ld_stream(const cplx<float>* p) { const float2 t = __ldcg(reinterpret_cast<const float2*>(p)); return mk<float>(t.x, t.y); }
+__device__ __forceinline__ cplx<double> ld_stream(const cplx<double>* p) { const double2 t = __ldcg(reinterpret_cast<const double2*>(p)); return mk<double>(t.x, t.y); }
+__device__ __forceinline__ void st_stream(float* p, float v) { __stcg(p, v); }
+__device__ __forceinline__ void st_stream(double* p, double v) { __stcg(p, v); }
+__device__ __forceinline__ void st_stream(cplx<float>* p, cplx<float> v) { __stcg(reinterpret_cast<float2*>(p), make_float2(v.x, v.y)); }
+__device__ __forceinline__ void st_stream(cplx<double>* p, cplx<double> v) { __stcg(reinterpret_cast<double2*>(p), make_double2(v.x, v.y)); }
+#endif
 __device__ __forceinline__ Lane<float> lane_from_global(const cplx<float>* p) {
-    // plain (coherent) load: the column pass runs in place, so the data is not read-only for the kernel
-    const Raw16f q = *reinterpret_cast<const Raw16f*>(p);
-    Lane<float> r; r.re = make_float2(q.a, q.c); r.im = make_float2(q.b, q.d); return r;
+#ifdef HIPGP_EMU
+    return *reinterpret_cast<const Lane<float>*>(p);
+#else
+    const float4 t = __ldcg(reinterpret_cast<const float4*>(p));
+    Lane<float> r; r.re = make_float2(t.x, t.y); r.im = make_float2(t.z, t.w); return r;
+#endif
 }
 __device__ __forceinline__ Lane<double> lane_from_global(const cplx<double>* p) {
+#ifdef HIPGP_EMU
     return *reinterpret_cast<const Lane<double>*>(p);
+#else
+    const double2 t = __ldcg(reinterpret_cast<const double2*>(p));
+    Lane<double> r; r.re = t.x; r.im = t.y; return r;
+#endif
 }
 __device__ __forceinline__ void lane_to_global(cplx<float>* p, Lane<float> v) {
-    Raw16f q; q.a = v.re.x; q.b = v.im.x; q.c = v.re.y; q.d = v.im.y;
-    *reinterpret_cast<Raw16f*>(p) = q;
+#ifdef HIPGP_EMU
+    *reinterpret_cast<Lane<float>*>(p) = v;
+#else
+    __stcg(reinterpret_cast<float4*>(p), make_float4(v.re.x, v.re.y, v.im.x, v.im.y));
+#endif
 }
-__device__ __forceinline__ void lane_to_global(cplx<double>* p, Lane<double> v) { *reinterpret_cast<Lane<double>*>(p) = v; }
+__device__ __forceinline__ void lane_to_global(cplx<double>* p, Lane<double> v) {
+#ifdef HIPGP_EMU
+    *reinterpret_cast<Lane<double>*>(p) = v;
+#else
+    __stcg(reinterpret_cast<double2*>(p), make_double2(v.re, v.im));
+#endif
+}
+
+// one pairing of two scalars into a packed register pair (opaque to the optimiser, so it happens once per value)
+__device__ __forceinline__ float2 pack2(float a, float b) {
+#ifdef HIPGP_EMU
+    return make_float2(a, b);
+#else
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    float2 o;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(o.x), "=f"(o.y) : "l"(r));
+    return o;
+#endif
+}
+// a lane from the complex values of its LPT lines
+__device__ __forceinline__ Lane<float> lane_make(cplx<float> v0, cplx<float> v1) { Lane<float> r; r.re = pack2(v0.x, v1.x); r.im = pack2(v0.y, v1.y); return r; }
+__device__ __forceinline__ Lane<double> lane_make(cplx<double> v0, cplx<double>) { Lane<double> r; r.re = v0.x; r.im = v0.y; return r; }
+
+// row accessors of W for the row kernels (q = bin index along the row)
+template <class T> struct WRow;
+template <> struct WRow<float> {
+    static __device__ __forceinline__ void store1(cplx<float>* row, int q, cplx<float> v) {
+        float* f = reinterpret_cast<float*>(row) + 4 * (q >> 1) + (q & 1); st_stream(f, v.x); st_stream(f + 2, v.y);
+    }
+    static __device__ __forceinline__ cplx<float> load1(const cplx<float>* row, int q) {
+        const float* f = reinterpret_cast<const float*>(row) + 4 * (q >> 1) + (q & 1); return mk<float>(ld_stream(f), ld_stream(f + 2));
+    }
+    // bins (q, q + 1), q even
+    static __device__ __forceinline__ void store2(cplx<float>* row, int q, cplx<float> v0, cplx<float> v1) {
+        Lane<float> t; t.re = make_float2(v0.x, v1.x); t.im = make_float2(v0.y, v1.y);
+        lane_to_global(row + q, t);
+    }
+    static __device__ __forceinline__ void load2(const cplx<float>* row, int q, cplx<float>& v0, cplx<float>& v1) {
+        const Lane<float> t = lane_from_global(row + q);
+        v0 = mk<float>(t.re.x, t.im.x); v1 = mk<float>(t.re.y, t.im.y);
+    }
+};
+template <> struct WRow<double> {
+    static __device__ __forceinline__ void store1(cplx<double>* row, int q, cplx<double> v) { st_stream(row + q, v); }
+    static __device__ __forceinline__ cplx<double> load1(const cplx<double>* row, int q) { return ld_stream(row + q); }
+    static __device__ __forceinline__ void store2(cplx<double>* row, int q, cplx<double> v0, cplx<double> v1) { st_stream(row + q, v0); st_stream(row + q + 1, v1); }
+    static __device__ __forceinline__ void load2(const cplx<double>* row, int q, cplx<double>& v0, cplx<double>& v1) { v0 = ld_stream(row + q); v1 = ld_stream(row + q + 1); }
+};
+
+// ---- asynchronous global -> shared copies (LDGSTS): no register staging, all requests in flight at once ----
+template <int BYTES> __device__ __forceinline__ void cp_async(void* smem_dst, const void* gmem_src) {
+#ifdef HIPGP_EMU
+    std::memcpy(smem_dst, gmem_src, BYTES);
+#else
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    if (BYTES == 16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem_src));
+    else asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gmem_src));
+#endif
+}
+__device__ __forceinline__ void cp_async_commit() {
+#ifndef HIPGP_EMU
+    asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+#ifndef HIPGP_EMU
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+#endif
+}
 
 // ---------------------------------------------------------------------------------------------------------
 // butterflies on lanes:  v[q] = sum_r v[r] w_R^{qr},  w_R = exp(-+ 2 pi i / R)
@@ -252,34 +353,43 @@ __device__ __forceinline__ void lane_twiddles(cplx<T>* w, const cplx<T>* __restr
 }
 
 // one in-place shared-memory stage of sub-transform length Nt, radix R, over the whole tile
+template <class G, class T, int NL, int Nt, int R, bool INV>
+__device__ __forceinline__ void lane_stage_item(Lane<T>* s, const cplx<T>* __restrict__ tab, int it) {
+    constexpr int S = Nt / R, LEG = G::leg(S);
+    const int lane = it % NL, bf = it / NL;
+    const int blk = bf / S, j = bf - blk * S;
+    Lane<T>* base = s + (G::slot(blk * Nt + j) * NL + lane);
+    cplx<T> w[R];
+    if (S > 1) lane_twiddles<R, S>(w, tab, j);
+    Lane<T> v[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) v[r] = base[r * LEG];
+    if (INV) {
+        if (S > 1) {
+#pragma unroll
+            for (int r = 1; r < R; ++r) v[r] = lmulc(v[r], w[r]);
+        }
+        lbfly<R, true, T>(v);
+    } else {
+        lbfly<R, false, T>(v);
+        if (S > 1) {
+#pragma unroll
+            for (int r = 1; r < R; ++r) v[r] = lmul(v[r], w[r]);
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) base[r * LEG] = v[r];
+}
 template <class G, class T, int NL, int NT, int Nt, int R, bool INV>
 __device__ __forceinline__ void lane_stage(Lane<T>* s, const cplx<T>* __restrict__ tab, int tid) {
-    constexpr int S = Nt / R, NB = G::Ln / R, ITEMS = NB * NL, LEG = G::leg(S);
+    constexpr int ITEMS = (G::Ln / R) * NL, NIT = (ITEMS + NT - 1) / NT;
+    if constexpr (ITEMS % NT == 0 && NIT * R <= 16) {
+        // few small butterflies per thread: unrolled, so that the table and shared-memory loads of all of them overlap
+#pragma unroll
+        for (int k = 0; k < NIT; ++k) lane_stage_item<G, T, NL, Nt, R, INV>(s, tab, tid + k * NT);
+    } else {
 #pragma unroll 1
-    for (int it = tid; it < ITEMS; it += NT) {
-        const int lane = it % NL, bf = it / NL;
-        const int blk = bf / S, j = bf - blk * S;
-        Lane<T>* base = s + (G::slot(blk * Nt + j) * NL + lane);
-        cplx<T> w[R];
-        if (S > 1) lane_twiddles<R, S>(w, tab, j);
-        Lane<T> v[R];
-#pragma unroll
-        for (int r = 0; r < R; ++r) v[r] = base[r * LEG];
-        if (INV) {
-            if (S > 1) {
-#pragma unroll
-                for (int r = 1; r < R; ++r) v[r] = lmulc(v[r], w[r]);
-            }
-            lbfly<R, true, T>(v);
-        } else {
-            lbfly<R, false, T>(v);
-            if (S > 1) {
-#pragma unroll
-                for (int r = 1; r < R; ++r) v[r] = lmul(v[r], w[r]);
-            }
-        }
-#pragma unroll
-        for (int r = 0; r < R; ++r) base[r * LEG] = v[r];
+        for (int it = tid; it < ITEMS; it += NT) lane_stage_item<G, T, NL, Nt, R, INV>(s, tab, it);
     }
 }
 

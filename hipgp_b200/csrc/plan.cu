@@ -40,10 +40,21 @@ static bool launch_rows_fast(hipgp_plan* pl, bool inverse, RowsParams<T>& P, cud
     }
 }
 
+// Does every pass of this geometry have a specialised kernel?  fp32 pipelines keep the frequency workspace in lane
+// layout (lane_fft.cuh), which the generic kernels do not read, so an fp32 pipeline is all specialised or all generic;
+// fp64 lanes are plain interleaved complex numbers and the choice is made kernel by kernel.
 template <class T>
-static void launch_rows(hipgp_plan* pl, bool inverse, RowsParams<T>& P, cudaStream_t st) {
+static bool geom_allows_fast(const Geom<T>& g) {
+    if (sizeof(T) == 8) return true;
+    if (g_no_fast || fast_radices(g.H).empty()) return false;
+    for (int d = 0; d + 1 < g.D; ++d) if (fast_radices(g.L[d]).empty()) return false;
+    return true;
+}
+
+template <class T>
+static void launch_rows(hipgp_plan* pl, bool inverse, RowsParams<T>& P, cudaStream_t st, bool allow_fast = true) {
     P.vec_ok = (aligned2<T>(P.in) && aligned2<T>(P.out) && aligned2<T>(P.v0) && aligned2<T>(P.v1) && aligned2<T>(P.v2)) ? 1 : 0;
-    if (P.do_fft && launch_rows_fast<T>(pl, inverse, P, st)) return;
+    if (allow_fast && P.do_fft && launch_rows_fast<T>(pl, inverse, P, st)) return;
     int nth;
     pick_rows_tiling<T>(P.total_rows, P.H, &P.RB, &P.RBP, &nth);
     const size_t smem = rows_smem<T>(P.H, P.RBP);
@@ -75,8 +86,8 @@ static bool launch_cols_fast(hipgp_plan* pl, ColsParams<T>& P, long n_outer, lon
 }
 
 template <class T>
-static void launch_cols(hipgp_plan* pl, ColsParams<T>& P, long n_outer, long B, cudaStream_t st) {
-    if (launch_cols_fast<T>(pl, P, n_outer, B, st)) return;
+static void launch_cols(hipgp_plan* pl, ColsParams<T>& P, long n_outer, long B, cudaStream_t st, bool allow_fast = true) {
+    if (allow_fast && launch_cols_fast<T>(pl, P, n_outer, B, st)) return;
     const int L = P.f.Ln;
     int tb = sizeof(T) == 4 ? 16 : 8;
     while (tb > 1 && sizeof(cplx<T>) * (size_t)L * (tb + 1) > 100 * 1024) tb >>= 1;
@@ -95,6 +106,16 @@ static void launch_cols(hipgp_plan* pl, ColsParams<T>& P, long n_outer, long B, 
     PROF_END(pl, st);
     CK_LAUNCH();
     pl->launches++;
+}
+
+// the row-axis tables of a geometry
+template <class T>
+static void rows_geom(RowsParams<T>& R, Geom<T>& g) {
+    R.L = g.L[g.D - 1]; R.H = g.H; R.W_pitch = g.P;
+    R.f = g.frow.dev; R.twL = g.twL.template as<cplx<T>>(); R.twLp = g.twLp.template as<cplx<T>>();
+    R.part = g.part.template as<int>(); R.pairq = g.pairq.template as<int>();
+    R.pairs = g.pairs.template as<int>(); R.pairw = g.pairw.template as<cplx<T>>(); R.npair0 = g.npair0;
+    R.quadq = g.quadq.template as<int>(); R.quadw = g.quadw.template as<cplx<T>>(); R.nquad = g.nquad;
 }
 
 // workspace requirement (complex elements) for a pipeline with the given extents
@@ -119,26 +140,27 @@ static void run_pipeline(hipgp_plan* pl, Geom<T>& g, const int* n_in, const int*
     cplx<T>* W2 = pl->W2.as<cplx<T>>();
     const long P = g.P;
     const int* done = gated ? st.flags : nullptr;
+    const bool fast = geom_allows_fast(g);
 
     long rows_in = 1, rows_out = 1;
     for (int d = 0; d + 1 < D; ++d) { rows_in *= n_in[d]; rows_out *= n_out[d]; }
     const long Wrows = std::max(rows_in, rows_out);
 
     RowsParams<T> R{};
-    R.W = W1; R.L = g.L[D - 1]; R.H = g.H; R.W_pitch = P; R.W_rows = (int)Wrows;
-    R.f = g.frow.dev; R.twL = g.twL.template as<cplx<T>>(); R.twLp = g.twLp.template as<cplx<T>>(); R.part = g.part.template as<int>(); R.pairq = g.pairq.template as<int>(); R.st = st;
+    rows_geom(R, g);
+    R.W = W1; R.W_rows = (int)Wrows; R.st = st;
     // forward rows
     R.in = (const T*)ff.in; R.v0 = (T*)ff.v0; R.v1 = (T*)ff.v1; R.v2 = (const T*)ff.v2;
     R.mode = ff.mode; R.do_fft = 1; R.total_rows = B * rows_in; R.nrows = (int)rows_in; R.n_real = n_in[D - 1];
     R.spec = nullptr; R.spec_kind = SPEC_NONE;
-    launch_rows<T>(pl, false, R, s);
+    launch_rows<T>(pl, false, R, s, fast);
 
     if (D == 2) {
         ColsParams<T> C{};
         C.in = W1; C.out = W1; C.n_in = n_in[0]; C.n_out = n_out[0]; C.inner = g.H + 1; C.pitch = P;
         C.in_ostride = C.out_ostride = 0; C.in_bstride = C.out_bstride = Wrows * P;
         C.f = g.fcol[0].dev; C.mode = CM_FUSED; C.spec = spec; C.spec_kind = spec_kind; C.done_flag = done;
-        launch_cols<T>(pl, C, 1, B, s);
+        launch_cols<T>(pl, C, 1, B, s, fast);
     } else if (D == 3) {
         const long R0 = std::max(n_in[0], n_out[0]);
         const long L1 = g.L[1];
@@ -148,24 +170,24 @@ static void run_pipeline(hipgp_plan* pl, Geom<T>& g, const int* n_in, const int*
         C.in = W1; C.out = W2; C.n_in = n_in[1]; C.n_out = n_in[1]; C.inner = g.H + 1; C.pitch = P;
         C.in_ostride = (long)n_in[1] * P; C.in_bstride = Wrows * P; C.out_ostride = L1 * P; C.out_bstride = R0 * L1 * P;
         C.f = g.fcol[1].dev; C.mode = CM_FWD;
-        launch_cols<T>(pl, C, n_in[0], B, s);
+        launch_cols<T>(pl, C, n_in[0], B, s, fast);
         // axis 0 fused, in place on W2
         C.in = W2; C.out = W2; C.n_in = n_in[0]; C.n_out = n_out[0]; C.inner = L1 * P; C.pitch = L1 * P;
         C.in_ostride = C.out_ostride = 0; C.in_bstride = C.out_bstride = R0 * L1 * P;
         C.f = g.fcol[0].dev; C.mode = CM_FUSED; C.spec = spec; C.spec_kind = spec_kind;
-        launch_cols<T>(pl, C, 1, B, s);
+        launch_cols<T>(pl, C, 1, B, s, fast);
         // axis 1 inverse: W2 -> W1[b][i0][n_out1][P]
         C.in = W2; C.out = W1; C.n_in = n_out[1]; C.n_out = n_out[1]; C.inner = g.H + 1; C.pitch = P;
         C.in_ostride = L1 * P; C.in_bstride = R0 * L1 * P; C.out_ostride = (long)n_out[1] * P; C.out_bstride = Wrows * P;
         C.f = g.fcol[1].dev; C.mode = CM_INV; C.spec = nullptr; C.spec_kind = SPEC_NONE;
-        launch_cols<T>(pl, C, n_out[0], B, s);
+        launch_cols<T>(pl, C, n_out[0], B, s, fast);
     }
 
     // inverse rows
     R.out = (T*)fi.out; R.v0 = (T*)fi.v0; R.mode = fi.mode; R.dot_kind = fi.dot_kind;
     R.total_rows = B * rows_out; R.nrows = (int)rows_out; R.n_real = n_out[D - 1];
     if (D == 1) { R.spec = spec; R.spec_kind = spec_kind; }
-    launch_rows<T>(pl, true, R, s);
+    launch_rows<T>(pl, true, R, s, fast);
 }
 
 // forward-only transform of a real (L_0..L_{D-1}) fp64 array into W1 (raw spectrum, pipeline layout)
@@ -176,8 +198,8 @@ static void forward_full(hipgp_plan* pl, Geom<double>& g, const double* h, cudaS
     pl->W1.ensure(sizeof(cplx<double>) * (size_t)rows * g.P, &pl->dev_bytes);
     cplx<double>* W = pl->W1.as<cplx<double>>();
     RowsParams<double> R{};
-    R.in = h; R.W = W; R.L = g.L[D - 1]; R.H = g.H; R.W_pitch = g.P; R.W_rows = (int)rows;
-    R.f = g.frow.dev; R.twL = g.twL.as<cplx<double>>(); R.twLp = g.twLp.as<cplx<double>>(); R.part = g.part.as<int>(); R.pairq = g.pairq.as<int>(); R.mode = RF_PLAIN; R.do_fft = 1;
+    rows_geom(R, g);
+    R.in = h; R.W = W; R.W_rows = (int)rows; R.mode = RF_PLAIN; R.do_fft = 1;
     R.total_rows = rows; R.nrows = (int)rows; R.n_real = g.L[D - 1];
     launch_rows<double>(pl, false, R, s);
     if (D >= 2) {
@@ -357,16 +379,16 @@ static void slab_stage1(hipgp_plan* pl, const void* in_slab, void* send_buf, cud
     pl->W1.ensure(sizeof(cplx<T>) * (size_t)rows * g.P, &pl->dev_bytes);
     cplx<T>* W1 = pl->W1.as<cplx<T>>();
     RowsParams<T> R{};
-    R.in = (const T*)in_slab; R.W = W1; R.L = g.L[2]; R.H = g.H; R.W_pitch = g.P; R.W_rows = (int)rows;
-    R.f = g.frow.dev; R.twL = g.twL.template as<cplx<T>>(); R.twLp = g.twLp.template as<cplx<T>>(); R.part = g.part.template as<int>(); R.pairq = g.pairq.template as<int>();
+    rows_geom(R, g);
+    R.in = (const T*)in_slab; R.W = W1; R.W_rows = (int)rows;
     R.mode = RF_PLAIN; R.do_fft = 1; R.total_rows = rows; R.nrows = (int)rows; R.n_real = pl->m[2]; R.st = null_state();
-    launch_rows<T>(pl, false, R, s);
+    launch_rows<T>(pl, false, R, s, geom_allows_fast(g));
     ColsParams<T> C{};
     C.in = W1; C.out = (cplx<T>*)send_buf; C.n_in = pl->m[1]; C.n_out = pl->m[1]; C.inner = g.H + 1; C.pitch = g.P;
     C.in_ostride = (long)pl->m[1] * g.P; C.in_bstride = 0; C.out_ostride = q.chunk; C.out_bstride = 0;
     C.out_split_len = (int)q.Lq; C.out_split_stride = q.n0_loc * q.chunk;
     C.f = g.fcol[1].dev; C.mode = CM_FWD;
-    launch_cols<T>(pl, C, q.n0_loc, 1, s);
+    launch_cols<T>(pl, C, q.n0_loc, 1, s, geom_allows_fast(g));
 }
 
 template <class T>
@@ -378,7 +400,7 @@ static void slab_stage2(hipgp_plan* pl, int mode, void* buf, cudaStream_t s) {
     ColsParams<T> C{};
     C.in = (cplx<T>*)buf; C.out = (cplx<T>*)buf; C.n_in = pl->m[0]; C.n_out = pl->m[0]; C.inner = q.chunk; C.pitch = q.chunk;
     C.f = g.fcol[0].dev; C.mode = CM_FUSED; C.spec = spec; C.spec_kind = SPEC_REAL; C.spec_pitch = (long)g.L[1] * q.P3;
-    launch_cols<T>(pl, C, 1, 1, s);
+    launch_cols<T>(pl, C, 1, 1, s, geom_allows_fast(g));
 }
 
 template <class T>
@@ -392,13 +414,13 @@ static void slab_stage3(hipgp_plan* pl, const void* recv_buf, void* out_slab, cu
     C.in_ostride = q.chunk; C.in_bstride = 0; C.out_ostride = (long)pl->m[1] * g.P; C.out_bstride = 0;
     C.in_split_len = (int)q.Lq; C.in_split_stride = q.n0_loc * q.chunk;
     C.f = g.fcol[1].dev; C.mode = CM_INV;
-    launch_cols<T>(pl, C, q.n0_loc, 1, s);
+    launch_cols<T>(pl, C, q.n0_loc, 1, s, geom_allows_fast(g));
     RowsParams<T> R{};
-    R.out = (T*)out_slab; R.W = W1; R.L = g.L[2]; R.H = g.H; R.W_pitch = g.P; R.W_rows = (int)rows;
-    R.f = g.frow.dev; R.twL = g.twL.template as<cplx<T>>(); R.twLp = g.twLp.template as<cplx<T>>(); R.part = g.part.template as<int>(); R.pairq = g.pairq.template as<int>();
-    R.mode = RI_PLAIN; R.total_rows = rows; R.nrows = (int)rows; R.n_real = pl->m[2]; R.st = null_state();
+    rows_geom(R, g);
+    R.out = (T*)out_slab; R.W = W1; R.W_rows = (int)rows;
+    R.mode = RI_PLAIN; R.do_fft = 1; R.total_rows = rows; R.nrows = (int)rows; R.n_real = pl->m[2]; R.st = null_state();
     R.spec = nullptr; R.spec_kind = SPEC_NONE;
-    launch_rows<T>(pl, true, R, s);
+    launch_rows<T>(pl, true, R, s, geom_allows_fast(g));
 }
 
 template <class T>
@@ -422,6 +444,22 @@ static void matvec(hipgp_plan* pl, int mode, const void* in, void* out, long B, 
         case HIPGP_MV_RT: spec = pl->specW.p; kind = SPEC_CPLX; break;
         case HIPGP_MV_R: spec = pl->specW.p; kind = SPEC_CPLX_CONJ; break;
         default: throw Error("unknown matvec mode");
+    }
+    {
+        // EXPERIMENT: process the right-hand sides in chunks so that the frequency workspace of a chunk stays in L2
+        static const char* env = getenv("HIPGP_BCHUNK");
+        const long chunk = env ? atol(env) : 0;
+        if (chunk > 0 && chunk < B) {
+            long in_sz = 1, out_sz = 1;
+            for (int d = 0; d < pl->D; ++d) { in_sz *= n_in[d]; out_sz *= n_out[d]; }
+            for (long b0 = 0; b0 < B; b0 += chunk) {
+                const long nb = std::min(chunk, B - b0);
+                RowsFusion f2 = ff, i2 = fi;
+                f2.in = (const T*)in + b0 * in_sz; i2.out = (T*)out + b0 * out_sz;
+                run_pipeline<T>(pl, g, n_in, n_out, spec, kind, nb, f2, i2, null_state(), false, s);
+            }
+            return;
+        }
     }
     run_pipeline<T>(pl, g, n_in, n_out, spec, kind, B, ff, fi, null_state(), false, s);
 }

@@ -177,7 +177,8 @@ struct Geom {
     long P = 0;         // row pitch in complex elements (>= H + 1)
     LineFftHost<T> fcol[2];
     LineFftHost<T> frow;
-    DevBuf twL, twLp, part, pairq;
+    DevBuf twL, twLp, part, pairq, pairs, pairw, quadq, quadw;
+    int npair0 = 0, nquad = 0;
     bool built = false;
     void build(int D_, const int* L_, size_t* total) {
         D = D_;
@@ -204,13 +205,41 @@ struct Geom {
         if ((int)pq.size() != H / 2 + 1) throw Error("internal: r2c pair table has the wrong size");
         pairq.ensure(sizeof(int) * pq.size(), total);
         CK(cudaMemcpy(pairq.p, pq.data(), sizeof(int) * pq.size(), cudaMemcpyHostToDevice));
+        // quads for the specialised row kernels: even positions a >= RL (RL = last radix) whose bins (a, a+1) mirror
+        // onto (b+1, b) with b even: true for every digit group but group 0 when the list has more than one stage
+        {
+            const std::vector<int> rad = H > 1 ? choose_radices(H) : std::vector<int>();
+            const int RL = rad.empty() ? 1 : rad.back();
+            bool ok = rad.size() > 1 && RL % 2 == 0 && H % 2 == 0;
+            std::vector<int> qd; std::vector<cplx<T>> qw;
+            for (int qa = RL; ok && qa < H; qa += 2) {
+                const int pa = pt[qa], pa1 = pt[qa + 1];
+                if (pa != pa1 + 1 || (pa1 & 1) || pa1 < RL) { ok = false; break; }
+                if (qa <= pa1) { qd.push_back(qa); qd.push_back(pa1); qw.push_back(wp[qa]); qw.push_back(wp[qa + 1]); }
+            }
+            if (!ok) { qd.clear(); qw.clear(); }
+            nquad = (int)(qd.size() / 2);
+            npair0 = 0;
+            if (ok) { for (int q : pq) if (q < RL) ++npair0; } else npair0 = (int)pq.size();
+            if (npair0 + 2 * nquad - (ok ? 0 : 0) < 0) throw Error("internal: quad table");
+            std::vector<int> pr; std::vector<cplx<T>> pw;
+            for (int q : pq) { pr.push_back(q); pr.push_back(q == 0 ? H : pt[q]); pw.push_back(wp[q]); }
+            pairs.ensure(sizeof(int) * pr.size(), total); pairw.ensure(sizeof(cplx<T>) * pw.size(), total);
+            CK(cudaMemcpy(pairs.p, pr.data(), sizeof(int) * pr.size(), cudaMemcpyHostToDevice));
+            CK(cudaMemcpy(pairw.p, pw.data(), sizeof(cplx<T>) * pw.size(), cudaMemcpyHostToDevice));
+            quadq.ensure(sizeof(int) * std::max<size_t>(qd.size(), 2), total); quadw.ensure(sizeof(cplx<T>) * std::max<size_t>(qw.size(), 2), total);
+            if (!qd.empty()) {
+                CK(cudaMemcpy(quadq.p, qd.data(), sizeof(int) * qd.size(), cudaMemcpyHostToDevice));
+                CK(cudaMemcpy(quadw.p, qw.data(), sizeof(cplx<T>) * qw.size(), cudaMemcpyHostToDevice));
+            }
+        }
         twLp.ensure(sizeof(cplx<T>) * H, total); part.ensure(sizeof(int) * H, total);
         CK(cudaMemcpy(twLp.p, wp.data(), sizeof(cplx<T>) * H, cudaMemcpyHostToDevice));
         CK(cudaMemcpy(part.p, pt.data(), sizeof(int) * H, cudaMemcpyHostToDevice));
         built = true;
     }
     long spec_elems() const { long n = P; for (int d = 0; d + 1 < D; ++d) n *= L[d]; return n; }
-    void release(size_t* total) { for (auto& f : fcol) f.release(total); frow.release(total); twL.release(total); twLp.release(total); part.release(total); pairq.release(total); built = false; }
+    void release(size_t* total) { for (auto& f : fcol) f.release(total); frow.release(total); twL.release(total); twLp.release(total); part.release(total); pairq.release(total); pairs.release(total); pairw.release(total); quadq.release(total); quadw.release(total); built = false; }
 };
 
 struct RowsFusion {

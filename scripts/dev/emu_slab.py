@@ -1,0 +1,52 @@
+"""Developer check: slab-decomposed matvec stages on the CPU emulation build vs the undecomposed plan (emulated ranks)."""
+import ctypes as C, sys, os
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+from hipgp_b200 import _lib as L
+import emu_build
+lib = emu_build.load()
+def ptr(a): return a.ctypes.data_as(C.c_void_p)
+def mkplan(dims, dt, col, slab=None):
+    plan = C.c_void_p(); mm = np.array(dims, dtype=np.int64)
+    assert lib.hipgp_plan_create(3, mm.ctypes.data_as(L._pi64), L.F32 if dt == np.float32 else L.F64, 0, C.byref(plan)) == 0
+    if slab: assert lib.hipgp_plan_set_slab(plan, slab[0], slab[1]) == 0, lib.hipgp_last_error()
+    ncl = C.c_int64()
+    assert lib.hipgp_plan_set_first_row(plan, ptr(col), 1e-6, C.byref(ncl), None) == 0, lib.hipgp_last_error()
+    return plan
+def run(dims, nranks, dt):
+    g = np.meshgrid(*[np.linspace(0, 1 + d, k) for d, k in enumerate(dims)], indexing="ij")
+    r = np.sqrt(sum((x - x.flat[0]) ** 2 for x in g)); col = ((1 + np.sqrt(3) * r / 0.4) * np.exp(-np.sqrt(3) * r / 0.4)).reshape(-1); col[0] += 1e-2
+    col = col.astype(dt)
+    full = mkplan(dims, dt, col)
+    plans = [mkplan(dims, dt, col, (rk, nranks)) for rk in range(nranks)]
+    a, b = C.c_int64(), C.c_int64()
+    lib.hipgp_slab_sizes(plans[0], C.byref(a), C.byref(b)); slab_elems, exch = a.value, b.value
+    rng = np.random.default_rng(0); M = int(np.prod(dims))
+    v = rng.standard_normal((1, M)).astype(dt)
+    n0 = dims[0] // nranks
+    slabs = [np.ascontiguousarray(v.reshape(dims)[rk * n0:(rk + 1) * n0]).reshape(-1) for rk in range(nranks)]
+    cdt = np.complex64 if dt == np.float32 else np.complex128
+    def exchange(bufs):
+        blk = exch // nranks
+        return [np.concatenate([bufs[q][rk * blk:(rk + 1) * blk] for q in range(nranks)]) for rk in range(nranks)]
+    ok = True
+    for mode in (0, 1):
+        ref = np.zeros((1, M), dtype=dt)
+        assert lib.hipgp_matvec(full, mode, ptr(v), ptr(ref), 1, None) == 0
+        bufs = []
+        for p, x in zip(plans, slabs):
+            send = np.zeros(exch, dtype=cdt); assert lib.hipgp_slab_stage1(p, ptr(x), ptr(send), None) == 0, lib.hipgp_last_error(); bufs.append(send)
+        bufs = exchange(bufs)
+        for p, bb in zip(plans, bufs): assert lib.hipgp_slab_stage2(p, mode, ptr(bb), None) == 0, lib.hipgp_last_error()
+        bufs = exchange(bufs)
+        outs = []
+        for p, bb in zip(plans, bufs):
+            o = np.zeros(slab_elems, dtype=dt); assert lib.hipgp_slab_stage3(p, ptr(bb), ptr(o), None) == 0, lib.hipgp_last_error(); outs.append(o)
+        got = np.concatenate(outs).reshape(1, -1)
+        e = np.linalg.norm(got - ref) / np.linalg.norm(ref)
+        print(dims, nranks, dt.__name__, "mode", mode, "err %.2e" % e); ok &= e < (1e-5 if dt == np.float32 else 1e-10)
+    return ok
+if __name__ == "__main__":
+    ok = run((16, 12, 20), 2, np.float64) & run((16, 12, 20), 4, np.float32)
+    sys.exit(0 if ok else 1)
