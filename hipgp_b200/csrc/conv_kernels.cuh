@@ -125,6 +125,7 @@ struct RowsParams {
     int RB, RBP;          // rows per CTA, padded smem line count
     int mode, dot_kind, do_fft;
     int vec_ok;           // all row pointers are aligned for 2-element vector access
+    int vec16_ok;         // ... and for 16-byte access (specialised kernels stream rows in 16-byte chunks)
     const void* spec; int spec_kind;   // rows_inv only (1-D grids)
     PcgDev st;
 };
@@ -322,7 +323,8 @@ struct ColsParams {
     const void* spec; int spec_kind;   // FUSED: spectrum indexed [pos * spec_pitch + line]
     long spec_pitch;              // 0 = same as pitch
     int spec_stage;               // specialised kernels: real spectrum tile staged through shared memory
-    int dbg;                      // developer experiments (0 in production)
+    int in_stage;                 // specialised kernels: input rows prefetched through the shared-memory side buffer
+    int nx, ny, nz;               // specialised (persistent) kernels: tile grid = line tiles x outer x batch
     const int* done_flag;         // optional PCG early-exit flag
     // slab-decomposed grids: rows of the output (FWD) / input (INV) are scattered / gathered in blocks of `split_len`
     // positions, `split_stride` elements apart, so that the pass writes (reads) the all-to-all buffer directly

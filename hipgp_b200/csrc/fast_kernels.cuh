@@ -62,8 +62,12 @@ __device__ __forceinline__ Lane<float> lane_spec_smem(Lane<float> v, const void*
 __device__ __forceinline__ Lane<double> lane_spec_smem(Lane<double> v, const void* p) { return lscale(v, *reinterpret_cast<const double*>(p)); }
 
 // =====================================================================================================
-// Column pass.  A CTA owns NL lanes (= NL * LPT neighbouring lines) of one (outer, batch) slice.
-// Dynamic shared memory: the tile, then (P.spec_stage) NL * 8 bytes per padded position for the real spectrum tile.
+// Column pass.  PERSISTENT: the grid is sized to the machine and every CTA walks tiles t = blockIdx.x, + gridDim.x, ...
+// A tile = NL lanes (= NL * LPT neighbouring lines) of one (outer, batch) slice; tile index = ((bz * ny) + by) * nx + bx,
+// so CTAs that run side by side work on neighbouring lines (their 32-byte row segments share DRAM bursts).
+// Dynamic shared memory: the tile, then a SIDE buffer that is time-shared: it receives the next tile's input rows with
+// cp.async while this tile is in its inverse stages, and this tile's (real) spectrum while it is in its forward stages,
+// so neither latency sits on the critical path.
 // =====================================================================================================
 template <class T, int NL, int NT, int MINB, int R0, int... Rs>
 __global__ void __launch_bounds__(NT, MINB) cols_fast_kernel(ColsParams<T> P) {
@@ -73,167 +77,220 @@ __global__ void __launch_bounds__(NT, MINB) cols_fast_kernel(ColsParams<T> P) {
     Lane<T>* s = reinterpret_cast<Lane<T>*>(smem_raw);
     const int tid = threadIdx.x;
     if (P.done_flag && *P.done_flag) return;
-    const long c0 = (long)blockIdx.x * TBL;
-    const long nvalid = P.inner - c0;                       // lines of this tile that exist
-    const cplx<T>* in = P.in + (size_t)blockIdx.y * P.in_ostride + (size_t)blockIdx.z * P.in_bstride + c0;
-    cplx<T>* out = P.out + (size_t)blockIdx.y * P.out_ostride + (size_t)blockIdx.z * P.out_bstride + c0;
     const int mode = P.mode;
     const size_t pitch = (size_t)P.pitch;
     const size_t spitch = P.spec_pitch ? (size_t)P.spec_pitch : (size_t)P.pitch;
+    const long ntiles = (long)P.nx * P.ny * P.nz;
+    auto tile_origin = [&](long t, long& c0, size_t& ioff, size_t& ooff) {
+        const long bx = t % P.nx, r = t / P.nx;
+        const long by = r % P.ny, bz = r / P.ny;
+        c0 = bx * TBL;
+        ioff = (size_t)by * P.in_ostride + (size_t)bz * P.in_bstride + c0;
+        ooff = (size_t)by * P.out_ostride + (size_t)bz * P.out_bstride + c0;
+    };
 
     if constexpr (NST == 1) {
         // the whole line lives in one thread's registers
-        for (int lane = tid; lane < NL; lane += NT) {
-            if ((long)lane * LPT >= nvalid) continue;
-            const int rows_in = mode == CM_INV ? Ln : P.n_in;
-            const int rows_out = mode == CM_FWD ? Ln : P.n_out;
-            Lane<T> v[R0];
+        for (long t = blockIdx.x; t < ntiles; t += gridDim.x) {
+            long c0; size_t ioff, ooff;
+            tile_origin(t, c0, ioff, ooff);
+            const long nvalid = P.inner - c0;
+            const cplx<T>* in = P.in + ioff;
+            cplx<T>* out = P.out + ooff;
+            for (int lane = tid; lane < NL; lane += NT) {
+                if ((long)lane * LPT >= nvalid) continue;
+                const int rows_in = mode == CM_INV ? Ln : P.n_in;
+                const int rows_out = mode == CM_FWD ? Ln : P.n_out;
+                Lane<T> v[R0];
 #pragma unroll
-            for (int r = 0; r < R0; ++r)
-                v[r] = r < rows_in ? lane_from_global(in + cols_rowoff<T>(r, P.pitch, P.in_split_len, P.in_split_stride) + lane * LPT) : lzero<T>();
-            if (mode != CM_INV) lbfly<R0, false, T>(v);
-            if (mode == CM_FUSED) {
+                for (int r = 0; r < R0; ++r)
+                    v[r] = r < rows_in ? lane_from_global(in + cols_rowoff<T>(r, P.pitch, P.in_split_len, P.in_split_stride) + lane * LPT) : lzero<T>();
+                if (mode != CM_INV) lbfly<R0, false, T>(v);
+                if (mode == CM_FUSED) {
 #pragma unroll
-                for (int r = 0; r < R0; ++r) v[r] = lane_spec(v[r], P.spec, P.spec_kind, (size_t)r * spitch + c0 + lane * LPT);
+                    for (int r = 0; r < R0; ++r) v[r] = lane_spec(v[r], P.spec, P.spec_kind, (size_t)r * spitch + c0 + lane * LPT);
+                }
+                if (mode != CM_FWD) lbfly<R0, true, T>(v);
+#pragma unroll
+                for (int r = 0; r < R0; ++r)
+                    if (r < rows_out) lane_to_global(out + cols_rowoff<T>(r, P.pitch, P.out_split_len, P.out_split_stride) + lane * LPT, v[r]);
             }
-            if (mode != CM_FWD) lbfly<R0, true, T>(v);
-#pragma unroll
-            for (int r = 0; r < R0; ++r)
-                if (r < rows_out) lane_to_global(out + cols_rowoff<T>(r, P.pitch, P.out_split_len, P.out_split_stride) + lane * LPT, v[r]);
         }
         return;
     } else {
         constexpr int LEG0 = G::leg(S0);
         constexpr int SPEC_LANE = 8;                                  // bytes of real spectrum per lane (2 x fp32 or 1 x fp64)
-        unsigned char* sspec = smem_raw + G::smem_bytes();
+        constexpr int SIDE_SLOTS = Ln + Ln / RLAST;                   // side buffer: SIDE_SLOTS * NL * 8 bytes
+        constexpr int SIDE_LANES = SIDE_SLOTS * NL / 2;               // ... = this many 16-byte lanes
+        unsigned char* side = smem_raw + G::smem_bytes();
         auto sslot = [](int p) { return p + (p >> G::LOGRL); };       // padded position of the staged spectrum
         const cplx<T>* tw0 = P.f.twst + P.f.twoff[0];
-        const bool spec_smem = P.spec_stage != 0;
+        const bool spec_smem = P.spec_stage != 0;                     // FUSED with a real spectrum
+        const int n_in = P.n_in, n_out = P.n_out;
+        const bool stage_in = P.in_stage != 0;                        // input rows go through the side buffer
+        const bool zero_hi = is_pow2(R0) && n_in <= Ln / 2;
+        const bool out_lo = is_pow2(R0) && n_out <= Ln / 2;
+        const size_t rstep = (size_t)S0 * pitch;
 
-        // ---- spectrum tile -> shared memory, asynchronously (consumed after the forward stages) ----
-        if (spec_smem) {
-            const unsigned char* sp = reinterpret_cast<const unsigned char*>(P.spec) + (size_t)c0 * sizeof(T);
-            constexpr int ROWB = NL * SPEC_LANE;                      // bytes per position
-            constexpr int CH = ROWB >= 16 ? 16 : 8, NCH = ROWB / CH;
-            constexpr int NIT = (Ln * NCH + NT - 1) / NT;
+        // asynchronous copy of a tile's input rows (row i, lane l -> side lane i * NL + l)
+        auto prefetch_input = [&](long t) {
+            long c0; size_t ioff, ooff;
+            tile_origin(t, c0, ioff, ooff);
+            const long nvalid = P.inner - c0;
+            const cplx<T>* in = P.in + ioff;
+            constexpr int NIT = (SIDE_LANES + NT - 1) / NT;
+            const int total = n_in * NL;
 #pragma unroll
             for (int k = 0; k < NIT; ++k) {
                 const int w = tid + k * NT;
-                const int p = w / NCH, c = w - p * NCH;
-                if (w < Ln * NCH) cp_async<CH>(sspec + (size_t)sslot(p) * ROWB + c * CH, sp + (size_t)p * spitch * sizeof(T) + c * CH);
+                const int i = w / NL, lane = w - i * NL;
+                if (w < total && (long)lane * LPT < nvalid) cp_async<16>(side + (size_t)w * 16, in + (size_t)i * pitch + lane * LPT);
             }
             cp_async_commit();
-        }
+        };
 
-        // ---- first forward stage, operands straight from global memory (zero padding = skipped loads) ----
-        if (mode != CM_INV) {
-            const int n_in = P.n_in;
-            const bool zero_hi = is_pow2(R0) && n_in <= Ln / 2;
-            const size_t rstep = (size_t)S0 * pitch;
-#pragma unroll 1
-            for (int it = tid; it < S0 * NL; it += NT) {
-                const int lane = it % NL, j = it / NL;
-                const bool ok = (long)lane * LPT < nvalid;
-                const cplx<T>* gp = in + (size_t)j * pitch + lane * LPT;
-                cplx<T> w[R0];
-                lane_twiddles<R0, S0>(w, tw0, j);
-                Lane<T> v[R0];
-                if (zero_hi) {
-#pragma unroll
-                    for (int r = 0; r < R0 / 2; ++r) v[r] = (ok && j + r * S0 < n_in && !(P.dbg & 2)) ? lane_from_global(gp + r * rstep) : lzero<T>();
-                    lbfly_zero_hi<R0, T>(v);
-                } else {
-#pragma unroll
-                    for (int r = 0; r < R0; ++r) v[r] = (ok && j + r * S0 < n_in) ? lane_from_global(gp + r * rstep) : lzero<T>();
-                    lbfly<R0, false, T>(v);
-                }
-#pragma unroll
-                for (int r = 1; r < R0; ++r) v[r] = lmul(v[r], w[r]);
-                Lane<T>* base = s + (G::slot(j) * NL + lane);
-#pragma unroll
-                for (int r = 0; r < R0; ++r) base[r * LEG0] = v[r];
-            }
+        long t = blockIdx.x;
+        if (stage_in && t < ntiles) prefetch_input(t);
+        for (; t < ntiles; t += gridDim.x) {
+            long c0; size_t ioff, ooff;
+            tile_origin(t, c0, ioff, ooff);
+            const long nvalid = P.inner - c0;                   // lines of this tile that exist
+            const cplx<T>* in = P.in + ioff;
+            cplx<T>* out = P.out + ooff;
+            // the previous tile's last stage has to be done with the tile buffer, and this tile's input must have landed
+            cp_async_wait_all();
             __syncthreads();
-            if (!(P.dbg & 1)) LaneMidFwd<G, T, NL, NT, Ln / R0, 1, Rs...>::run(s, P.f, tid);
-        }
-        if (spec_smem) { cp_async_wait_all(); __syncthreads(); }
 
-        // ---- last forward stage + spectrum + first inverse stage: RLAST neighbouring positions, in registers ----
-        if (!(P.dbg & 1)) {
+            // ---- first forward stage: operands from the side buffer or straight from global memory (zero padding = skipped loads) ----
+            if (mode != CM_INV) {
 #pragma unroll 1
-            for (int it = tid; it < (Ln / RLAST) * NL; it += NT) {
-                const int lane = it % NL, bf = it / NL;
-                const bool ok = (long)lane * LPT < nvalid;
-                const int p0 = bf * RLAST;
-                Lane<T>* base = s + (G::slot(p0) * NL + lane);
-                Lane<T> v[RLAST];
-                if (mode == CM_INV) {
-                    // (slab grids: rows may be gathered in blocks of in_split_len positions, a multiple of RLAST)
-                    const cplx<T>* gp = in + cols_rowoff<T>(p0, P.pitch, P.in_split_len, P.in_split_stride) + lane * LPT;
+                for (int it = tid; it < S0 * NL; it += NT) {
+                    const int lane = it % NL, j = it / NL;
+                    const bool ok = (long)lane * LPT < nvalid;
+                    cplx<T> w[R0];
+                    lane_twiddles<R0, S0>(w, tw0, j);
+                    Lane<T> v[R0];
+                    if (stage_in) {
+                        const Lane<T>* sp = reinterpret_cast<const Lane<T>*>(side) + (j * NL + lane);
+                        if (zero_hi) {
 #pragma unroll
-                    for (int r = 0; r < RLAST; ++r) v[r] = ok ? lane_from_global(gp + r * pitch) : lzero<T>();
-                } else {
+                            for (int r = 0; r < R0 / 2; ++r) v[r] = (ok && j + r * S0 < n_in) ? sp[r * S0 * NL] : lzero<T>();
+                            lbfly_zero_hi<R0, T>(v);
+                        } else {
 #pragma unroll
-                    for (int r = 0; r < RLAST; ++r) v[r] = base[r * NL];
-                    lbfly<RLAST, false, T>(v);
-                }
-                if (mode == CM_FUSED) {
-                    if (spec_smem) {
-                        const unsigned char* sp = sspec + ((size_t)sslot(p0) * NL + lane) * SPEC_LANE;
+                            for (int r = 0; r < R0; ++r) v[r] = (ok && j + r * S0 < n_in) ? sp[r * S0 * NL] : lzero<T>();
+                            lbfly<R0, false, T>(v);
+                        }
+                    } else {
+                        const cplx<T>* gp = in + (size_t)j * pitch + lane * LPT;
+                        if (zero_hi) {
 #pragma unroll
-                        for (int r = 0; r < RLAST; ++r) v[r] = lane_spec_smem(v[r], sp + r * NL * SPEC_LANE);
-                    } else if (ok) {
-                        const size_t sidx = (size_t)p0 * spitch + c0 + lane * LPT;
+                            for (int r = 0; r < R0 / 2; ++r) v[r] = (ok && j + r * S0 < n_in) ? lane_from_global(gp + r * rstep) : lzero<T>();
+                            lbfly_zero_hi<R0, T>(v);
+                        } else {
 #pragma unroll
-                        for (int r = 0; r < RLAST; ++r) v[r] = lane_spec(v[r], P.spec, P.spec_kind, sidx + (size_t)r * spitch);
+                            for (int r = 0; r < R0; ++r) v[r] = (ok && j + r * S0 < n_in) ? lane_from_global(gp + r * rstep) : lzero<T>();
+                            lbfly<R0, false, T>(v);
+                        }
                     }
-                }
-                if (mode == CM_FWD) {
-                    if (ok) {
-                        cplx<T>* gp = out + cols_rowoff<T>(p0, P.pitch, P.out_split_len, P.out_split_stride) + lane * LPT;
 #pragma unroll
-                        for (int r = 0; r < RLAST; ++r) lane_to_global(gp + r * pitch, v[r]);
+                    for (int r = 1; r < R0; ++r) v[r] = lmul(v[r], w[r]);
+                    Lane<T>* base = s + (G::slot(j) * NL + lane);
+#pragma unroll
+                    for (int r = 0; r < R0; ++r) base[r * LEG0] = v[r];
+                }
+                __syncthreads();
+                // ---- spectrum tile -> side buffer (free now), asynchronously behind the forward middle stages ----
+                if (spec_smem) {
+                    const unsigned char* sp = reinterpret_cast<const unsigned char*>(P.spec) + (size_t)c0 * sizeof(T);
+                    constexpr int ROWB = NL * SPEC_LANE;                      // bytes per position
+                    constexpr int CH = ROWB >= 16 ? 16 : 8, NCH = ROWB / CH;
+                    constexpr int NIT = (Ln * NCH + NT - 1) / NT;
+#pragma unroll
+                    for (int k = 0; k < NIT; ++k) {
+                        const int w = tid + k * NT;
+                        const int p = w / NCH, c = w - p * NCH;
+                        if (w < Ln * NCH) cp_async<CH>(side + (size_t)sslot(p) * ROWB + c * CH, sp + (size_t)p * spitch * sizeof(T) + c * CH);
                     }
-                } else {
-                    lbfly<RLAST, true, T>(v);
-#pragma unroll
-                    for (int r = 0; r < RLAST; ++r) base[r * NL] = v[r];
+                    cp_async_commit();
                 }
+                LaneMidFwd<G, T, NL, NT, Ln / R0, 1, Rs...>::run(s, P.f, tid);
+                if (spec_smem) { cp_async_wait_all(); __syncthreads(); }
             }
-            if (mode == CM_FWD) return;
-            __syncthreads();
-        }
 
-        // ---- inverse middle stages, then the last inverse stage straight to global memory (crop = skipped stores) ----
-        if (!(P.dbg & 1)) LaneMidInv<G, T, NL, NT, Ln / R0, 1, Rs...>::run(s, P.f, tid);
-        {
-            const int n_out = P.n_out;
-            const bool out_lo = is_pow2(R0) && n_out <= Ln / 2;
-            const size_t rstep = (size_t)S0 * pitch;
+            // ---- last forward stage + spectrum + first inverse stage: RLAST neighbouring positions, in registers ----
+            {
 #pragma unroll 1
-            for (int it = tid; it < S0 * NL; it += NT) {
-                const int lane = it % NL, j = it / NL;
-                const bool ok = (long)lane * LPT < nvalid;
-                cplx<T> w[R0];
-                lane_twiddles<R0, S0>(w, tw0, j);
-                const Lane<T>* base = s + (G::slot(j) * NL + lane);
-                Lane<T> v[R0];
+                for (int it = tid; it < (Ln / RLAST) * NL; it += NT) {
+                    const int lane = it % NL, bf = it / NL;
+                    const bool ok = (long)lane * LPT < nvalid;
+                    const int p0 = bf * RLAST;
+                    Lane<T>* base = s + (G::slot(p0) * NL + lane);
+                    Lane<T> v[RLAST];
+                    if (mode == CM_INV) {
+                        // (slab grids: rows may be gathered in blocks of in_split_len positions, a multiple of RLAST)
+                        const cplx<T>* gp = in + cols_rowoff<T>(p0, P.pitch, P.in_split_len, P.in_split_stride) + lane * LPT;
 #pragma unroll
-                for (int r = 0; r < R0; ++r) v[r] = base[r * LEG0];
+                        for (int r = 0; r < RLAST; ++r) v[r] = ok ? lane_from_global(gp + r * pitch) : lzero<T>();
+                    } else {
 #pragma unroll
-                for (int r = 1; r < R0; ++r) v[r] = lmulc(v[r], w[r]);
-                cplx<T>* gp = out + (size_t)j * pitch + lane * LPT;
-                if (out_lo) {          // outputs R0/2 .. R0-1 are cropped: the compiler drops their arithmetic
-                    lbfly<R0, true, T>(v);
-                    if (ok && !(P.dbg & 4)) {
-#pragma unroll
-                        for (int r = 0; r < R0 / 2; ++r) if (j + r * S0 < n_out) lane_to_global(gp + r * rstep, v[r]);
+                        for (int r = 0; r < RLAST; ++r) v[r] = base[r * NL];
+                        lbfly<RLAST, false, T>(v);
                     }
-                } else {
+                    if (mode == CM_FUSED) {
+                        if (spec_smem) {
+                            const unsigned char* sp = side + ((size_t)sslot(p0) * NL + lane) * SPEC_LANE;
+#pragma unroll
+                            for (int r = 0; r < RLAST; ++r) v[r] = lane_spec_smem(v[r], sp + r * NL * SPEC_LANE);
+                        } else if (ok) {
+                            const size_t sidx = (size_t)p0 * spitch + c0 + lane * LPT;
+#pragma unroll
+                            for (int r = 0; r < RLAST; ++r) v[r] = lane_spec(v[r], P.spec, P.spec_kind, sidx + (size_t)r * spitch);
+                        }
+                    }
+                    if (mode == CM_FWD) {
+                        if (ok) {
+                            cplx<T>* gp = out + cols_rowoff<T>(p0, P.pitch, P.out_split_len, P.out_split_stride) + lane * LPT;
+#pragma unroll
+                            for (int r = 0; r < RLAST; ++r) lane_to_global(gp + r * pitch, v[r]);
+                        }
+                    } else {
+                        lbfly<RLAST, true, T>(v);
+#pragma unroll
+                        for (int r = 0; r < RLAST; ++r) base[r * NL] = v[r];
+                    }
+                }
+                __syncthreads();
+            }
+            // ---- the side buffer is free again: next tile's input rows travel behind the inverse stages ----
+            if (stage_in && t + gridDim.x < ntiles) prefetch_input(t + gridDim.x);
+            if (mode == CM_FWD) continue;
+
+            // ---- inverse middle stages, then the last inverse stage straight to global memory (crop = skipped stores) ----
+            LaneMidInv<G, T, NL, NT, Ln / R0, 1, Rs...>::run(s, P.f, tid);
+            {
+#pragma unroll 1
+                for (int it = tid; it < S0 * NL; it += NT) {
+                    const int lane = it % NL, j = it / NL;
+                    const bool ok = (long)lane * LPT < nvalid;
+                    cplx<T> w[R0];
+                    lane_twiddles<R0, S0>(w, tw0, j);
+                    const Lane<T>* base = s + (G::slot(j) * NL + lane);
+                    Lane<T> v[R0];
+#pragma unroll
+                    for (int r = 0; r < R0; ++r) v[r] = base[r * LEG0];
+#pragma unroll
+                    for (int r = 1; r < R0; ++r) v[r] = lmulc(v[r], w[r]);
+                    cplx<T>* gp = out + (size_t)j * pitch + lane * LPT;
                     lbfly<R0, true, T>(v);
                     if (ok) {
+                        if (out_lo) {
 #pragma unroll
-                        for (int r = 0; r < R0; ++r) if (j + r * S0 < n_out) lane_to_global(gp + r * rstep, v[r]);
+                            for (int r = 0; r < R0 / 2; ++r) if (j + r * S0 < n_out) lane_to_global(gp + r * rstep, v[r]);
+                        } else {
+#pragma unroll
+                            for (int r = 0; r < R0; ++r) if (j + r * S0 < n_out) lane_to_global(gp + r * rstep, v[r]);
+                        }
                     }
                 }
             }
@@ -267,6 +324,7 @@ __global__ void __launch_bounds__(NT, MINB) rows_fwd_fast_kernel(RowsParams<T> P
     // per-row scalars, computed once (the 64-bit divisions stay out of the element loops)
     __shared__ T s_coef[32];
     __shared__ long s_wbase[32];
+    __shared__ double s_part[32];
     if (tid < NROW && tid < nl) {
         const long gr = g0 + tid;
         const long b = gr / P.nrows;
@@ -278,7 +336,122 @@ __global__ void __launch_bounds__(NT, MINB) rows_fwd_fast_kernel(RowsParams<T> P
     }
     __syncthreads();
 
-    // ---- first DIF stage fused with the load (and the PCG vector update) ----
+    // ---- streaming phase: one warp per row, 16-byte accesses; the fused PCG vector update happens here; the FFT input
+    //      row goes to the side buffer (row-major, SROW reals per row, zero-filled behind n); deterministic row sums ----
+    const int SROW = (n + 3) & ~3;
+    T* side = reinterpret_cast<T*>(smem_raw + G::smem_bytes());
+    {
+        constexpr int CH = 16 / (int)sizeof(T);
+        // WPR warps share a row when there are more warps than rows; a row's chunks are dealt out over its TW lanes
+        constexpr int NW = NT / 32, WPR = NW > NROW ? NW / NROW : 1, TW = 32 * WPR;
+        const int warp = tid >> 5, ln = (tid & 31) + 32 * (warp % WPR);
+        const bool chunked = P.vec16_ok && (n % CH == 0);
+        for (int row = warp / WPR; row < nl; row += NW / WPR) {
+            T* srow = side + (size_t)row * SROW;
+            const size_t off = (size_t)(g0 + row) * n;
+            const T coef = s_coef[row];
+            double acc = 0.0;
+            if (chunked) {
+                // batches of BS chunks per lane: all loads of a batch are in flight before the first use
+                const int nch = n / CH;
+                auto finish = [&](int c, Vec16<T> a) {
+                    if (want_dot) {
+#pragma unroll
+                        for (int k = 0; k < CH; ++k) acc += (double)(a.v[k] * a.v[k]);
+                    }
+                    *reinterpret_cast<Vec16<T>*>(srow + c * CH) = a;
+                };
+                if (mode == RF_XRUPDATE) {
+                    constexpr int BS = 4;
+                    for (int cb = ln; cb < nch; cb += TW * BS) {
+                        Vec16<T> a[BS], pv[BS], xv[BS], rv[BS];
+#pragma unroll
+                        for (int k = 0; k < BS; ++k) {
+                            const int c = cb + TW * k;
+                            if (c < nch) {
+                                const size_t o = off + (size_t)c * CH;
+                                a[k] = ldv_stream(P.in + o); pv[k] = ldv_stream(P.v2 + o); xv[k] = ldv_stream((const T*)P.v1 + o); rv[k] = ldv_stream((const T*)P.v0 + o);
+                            }
+                        }
+#pragma unroll
+                        for (int k = 0; k < BS; ++k) {
+                            const int c = cb + TW * k;
+                            if (c < nch) {
+                                const size_t o = off + (size_t)c * CH;
+#pragma unroll
+                                for (int e = 0; e < CH; ++e) { xv[k].v[e] = xv[k].v[e] + coef * pv[k].v[e]; a[k].v[e] = rv[k].v[e] - coef * a[k].v[e]; }
+                                stv_stream(P.v1 + o, xv[k]);
+                                stv_stream(P.v0 + o, a[k]);
+                                finish(c, a[k]);
+                            }
+                        }
+                    }
+                } else if (mode == RF_PUPDATE && !first_it) {
+                    constexpr int BS = 8;
+                    for (int cb = ln; cb < nch; cb += TW * BS) {
+                        Vec16<T> a[BS], pv[BS];
+#pragma unroll
+                        for (int k = 0; k < BS; ++k) {
+                            const int c = cb + TW * k;
+                            if (c < nch) { const size_t o = off + (size_t)c * CH; a[k] = ldv_stream(P.in + o); pv[k] = ldv_stream((const T*)P.v0 + o); }
+                        }
+#pragma unroll
+                        for (int k = 0; k < BS; ++k) {
+                            const int c = cb + TW * k;
+                            if (c < nch) {
+#pragma unroll
+                                for (int e = 0; e < CH; ++e) a[k].v[e] = a[k].v[e] + coef * pv[k].v[e];
+                                stv_stream(P.v0 + off + (size_t)c * CH, a[k]);
+                                finish(c, a[k]);
+                            }
+                        }
+                    }
+                } else {
+                    constexpr int BS = 8;
+                    const bool wr = mode == RF_PUPDATE;      // first iteration: p = z
+                    for (int cb = ln; cb < nch; cb += TW * BS) {
+                        Vec16<T> a[BS];
+#pragma unroll
+                        for (int k = 0; k < BS; ++k) { const int c = cb + TW * k; if (c < nch) a[k] = ldv_stream(P.in + off + (size_t)c * CH); }
+#pragma unroll
+                        for (int k = 0; k < BS; ++k) {
+                            const int c = cb + TW * k;
+                            if (c < nch) { if (wr) stv_stream(P.v0 + off + (size_t)c * CH, a[k]); finish(c, a[k]); }
+                        }
+                    }
+                }
+            } else {
+                for (int i = ln; i < n; i += TW) {
+                    const size_t o = off + i;
+                    T a = ld_stream(P.in + o);
+                    if (mode == RF_PUPDATE) {
+                        if (!first_it) a = a + coef * ld_stream((const T*)P.v0 + o);
+                        st_stream(P.v0 + o, a);
+                    } else if (mode == RF_XRUPDATE) {
+                        const T pv = ld_stream(P.v2 + o);
+                        st_stream(P.v1 + o, ld_stream((const T*)P.v1 + o) + coef * pv);
+                        a = ld_stream((const T*)P.v0 + o) - coef * a;
+                        st_stream(P.v0 + o, a);
+                    }
+                    if (want_dot) acc += (double)(a * a);
+                    srow[i] = a;
+                }
+            }
+            for (int i = n + ln; i < SROW; i += TW) srow[i] = (T)0;
+            if (want_dot) {
+                acc = warp_sum(acc);
+                if ((tid & 31) == 0) s_part[row * WPR + warp % WPR] = acc;
+            }
+        }
+        if (want_dot) {      // fixed-order sum of the WPR partials of a row
+            __syncthreads();
+            if (tid < nl) { double a = 0.0; for (int k = 0; k < WPR; ++k) a += s_part[tid * WPR + k]; P.st.partial[g0 + tid] = a; }
+        }
+    }
+    __syncthreads();
+    if (want_dot) pcg_finalize(P.st, mode == RF_XRUPDATE ? DOT_RR : DOT_ZR, g0, g1, P.nrows, tid, NT);
+
+    // ---- first DIF stage, operands from the side buffer (packed complex e = x[2e] + i x[2e+1]; zero padding = skipped reads) ----
     {
         const bool zero_hi = is_pow2(R0) && R0 > 1 && (n + 1) / 2 <= H / 2;
         const cplx<T>* tw0 = P.f.twst + P.f.twoff[0];
@@ -287,82 +460,25 @@ __global__ void __launch_bounds__(NT, MINB) rows_fwd_fast_kernel(RowsParams<T> P
             const int lane = it % NL, j = it / NL;
             cplx<T> w[R0];
             if (NST > 1) lane_twiddles<R0, S0>(w, tw0, j);
-            double accd[LPT];
-            size_t off[LPT];
-            bool rok[LPT];
-            T coef[LPT];
-#pragma unroll
-            for (int l = 0; l < LPT; ++l) {
-                const int row = lane * LPT + l;
-                accd[l] = 0.0; rok[l] = row < nl; off[l] = (size_t)(g0 + row) * n + 2 * j; coef[l] = s_coef[row];
-            }
-            // element loaders: packed complex e = j + r*S0  ->  x[2e] + i x[2e+1] of line l, with the fused vector update
-            auto ld_plain = [&](int l, int r) -> cplx<T> {
-                const int i = 2 * (j + r * S0); const bool ok0 = rok[l] && i < n, ok1 = rok[l] && i + 1 < n;
-                T a = 0, b2 = 0;
-                if (ok0) ld2(P.in + off[l] + 2 * r * S0, vec, a, b2, ok0, ok1);
-                return mk<T>(a, b2);
-            };
-            auto ld_pupdate = [&](int l, int r) -> cplx<T> {
-                const int i = 2 * (j + r * S0); const bool ok0 = rok[l] && i < n, ok1 = rok[l] && i + 1 < n;
-                T a = 0, b2 = 0;
-                if (ok0) {
-                    const size_t o = off[l] + 2 * r * S0;
-                    ld2(P.in + o, vec, a, b2, ok0, ok1);
-                    if (!first_it) { T p0, p1; ld2((const T*)P.v0 + o, vec, p0, p1, ok0, ok1); a = a + coef[l] * p0; b2 = b2 + coef[l] * p1; }
-                    st2(P.v0 + o, vec, a, b2, ok0, ok1);
-                }
-                return mk<T>(a, b2);
-            };
-            auto ld_selfdot = [&](int l, int r) -> cplx<T> {
-                const int i = 2 * (j + r * S0); const bool ok0 = rok[l] && i < n, ok1 = rok[l] && i + 1 < n;
-                T a = 0, b2 = 0;
-                if (ok0) { ld2(P.in + off[l] + 2 * r * S0, vec, a, b2, ok0, ok1); accd[l] += (double)(a * a) + (double)(b2 * b2); }
-                return mk<T>(a, b2);
-            };
-            auto ld_xrupdate = [&](int l, int r) -> cplx<T> {
-                const int i = 2 * (j + r * S0); const bool ok0 = rok[l] && i < n, ok1 = rok[l] && i + 1 < n;
-                T a = 0, b2 = 0;
-                if (ok0) {
-                    const size_t o = off[l] + 2 * r * S0;
-                    T p0, p1, x0, x1, r0, r1, q0, q1;
-                    ld2(P.v2 + o, vec, p0, p1, ok0, ok1);
-                    ld2((const T*)P.v1 + o, vec, x0, x1, ok0, ok1);
-                    ld2((const T*)P.v0 + o, vec, r0, r1, ok0, ok1);
-                    ld2(P.in + o, vec, q0, q1, ok0, ok1);
-                    st2(P.v1 + o, vec, x0 + coef[l] * p0, x1 + coef[l] * p1, ok0, ok1);
-                    a = r0 - coef[l] * q0; b2 = ok1 ? r1 - coef[l] * q1 : (T)0;
-                    st2(P.v0 + o, vec, a, b2, ok0, ok1);
-                    accd[l] += (double)(a * a) + (double)(b2 * b2);
-                }
-                return mk<T>(a, b2);
+            const T* srow0 = side + (size_t)(lane * LPT) * SROW;
+            const T* srow1 = side + (size_t)(lane * LPT + LPT - 1) * SROW;
+            const bool ok0 = lane * LPT < nl, ok1 = lane * LPT + LPT - 1 < nl;
+            auto elem = [&](int r) -> Lane<T> {
+                const int i = 2 * (j + r * S0);
+                const bool in_row = i < SROW;
+                const cplx<T> e0 = (ok0 && in_row) ? *reinterpret_cast<const cplx<T>*>(srow0 + i) : mk<T>(0, 0);
+                const cplx<T> e1 = (LPT == 2 && ok1 && in_row) ? *reinterpret_cast<const cplx<T>*>(srow1 + i) : mk<T>(0, 0);
+                return lane_make(e0, e1);
             };
             Lane<T> v[R0];
-            // (each line's loader runs exactly once per element: the fused updates have side effects)
-            auto fill1 = [&](auto& ld, int r) -> Lane<T> {
-                const cplx<T> e0 = ld(0, r);
-                if constexpr (LPT == 2) { const cplx<T> e1 = ld(1, r); return lane_make(e0, e1); }
-                else return lane_make(e0, e0);
-            };
-#define HIPGP_FILL(RC, LD)                                                                                  \
-            _Pragma("unroll") for (int r = 0; r < (RC); ++r) v[r] = fill1(LD, r);
             if (zero_hi) {
-                if (mode == RF_PLAIN) { HIPGP_FILL(R0 / 2, ld_plain) }
-                else if (mode == RF_PUPDATE) { HIPGP_FILL(R0 / 2, ld_pupdate) }
-                else if (mode == RF_XRUPDATE) { HIPGP_FILL(R0 / 2, ld_xrupdate) }
-                else { HIPGP_FILL(R0 / 2, ld_selfdot) }
+#pragma unroll
+                for (int r = 0; r < R0 / 2; ++r) v[r] = elem(r);
                 lbfly_zero_hi<R0, T>(v);
             } else {
-                auto ld_any = [&](int l, int r) -> cplx<T> {
-                    return mode == RF_PLAIN ? ld_plain(l, r) : (mode == RF_PUPDATE ? ld_pupdate(l, r) : (mode == RF_XRUPDATE ? ld_xrupdate(l, r) : ld_selfdot(l, r)));
-                };
-                HIPGP_FILL(R0, ld_any)
-                lbfly<R0, false, T>(v);
-            }
-#undef HIPGP_FILL
-            if (want_dot) {
 #pragma unroll
-                for (int l = 0; l < LPT; ++l) scratch[(lane * LPT + l) * S0 + j] = accd[l];
+                for (int r = 0; r < R0; ++r) v[r] = elem(r);
+                lbfly<R0, false, T>(v);
             }
             if (NST > 1) {
 #pragma unroll
@@ -374,10 +490,6 @@ __global__ void __launch_bounds__(NT, MINB) rows_fwd_fast_kernel(RowsParams<T> P
         }
     }
     __syncthreads();
-    if (want_dot) {
-        rows_reduce_partials(scratch, S0, nl, g0, P.st.partial, tid, NT);
-        pcg_finalize(P.st, mode == RF_XRUPDATE ? DOT_RR : DOT_ZR, g0, g1, P.nrows, tid, NT);
-    }
 
     if constexpr (NST > 1) {
         LaneMidFwd<G, T, NL, NT, H / R0, 1, Rs...>::run(s, P.f, tid);
@@ -478,6 +590,7 @@ __global__ void __launch_bounds__(NT, MINB) rows_inv_fast_kernel(RowsParams<T> P
     const int n = P.n_real;
 
     __shared__ long s_wbase[32];
+    __shared__ double s_part[32];
     if (tid < NROW && tid < nl) {
         const long gr = g0 + tid;
         const long b = gr / P.nrows;
@@ -579,8 +692,9 @@ __global__ void __launch_bounds__(NT, MINB) rows_inv_fast_kernel(RowsParams<T> P
         LaneMidInv<G, T, NL, NT, H / R0, 1, Rs...>::run(s, P.f, tid);
     }
 
-    // ---- last inverse stage fused with the store (crop) and the dot product ----
-    const bool vec = ((n & 1) == 0) && P.vec_ok;
+    // ---- last inverse stage into the side buffer (row-major, SROW reals per row) ----
+    const int SROW = (n + 3) & ~3;
+    T* side = reinterpret_cast<T*>(smem_raw + G::smem_bytes());
     const bool want_dot = P.mode == RI_DOT;
     {
         const bool out_lo = is_pow2(R0) && R0 > 1 && (n + 1) / 2 <= H / 2;
@@ -598,38 +712,75 @@ __global__ void __launch_bounds__(NT, MINB) rows_inv_fast_kernel(RowsParams<T> P
 #pragma unroll
                 for (int r = 1; r < R0; ++r) v[r] = lmulc(v[r], w[r]);
             }
-            double accd[LPT];
-            size_t off[LPT];
-            bool rok[LPT];
-#pragma unroll
-            for (int l = 0; l < LPT; ++l) { const int row = lane * LPT + l; accd[l] = 0.0; rok[l] = row < nl; off[l] = (size_t)(g0 + row) * n + 2 * j; }
-            auto st_elem = [&](int l, int r, cplx<T> val, bool dot) {
+            lbfly<R0, true, T>(v);
+            T* srow0 = side + (size_t)(lane * LPT) * SROW;
+            T* srow1 = side + (size_t)(lane * LPT + LPT - 1) * SROW;
+            auto put = [&](int r) {
                 const int i = 2 * (j + r * S0);
-                const bool ok0 = rok[l] && i < n, ok1 = rok[l] && i + 1 < n;
-                if (ok0) {
-                    const size_t o = off[l] + 2 * r * S0;
-                    st2(P.out + o, vec, val.x, val.y, ok0, ok1);
-                    if (dot) {
-                        T o0, o1; ld2((const T*)P.v0 + o, vec, o0, o1, ok0, ok1);
-                        accd[l] += (double)(val.x * o0) + (ok1 ? (double)(val.y * o1) : 0.0);
-                    }
+                if (i < SROW) {
+                    *reinterpret_cast<cplx<T>*>(srow0 + i) = lane_get(v[r], 0);
+                    if (LPT == 2) *reinterpret_cast<cplx<T>*>(srow1 + i) = lane_get(v[r], LPT - 1);
                 }
             };
-            lbfly<R0, true, T>(v);
-#define HIPGP_DRAIN(RC, DOT)                                                                                \
-            _Pragma("unroll") for (int r = 0; r < (RC); ++r) { _Pragma("unroll") for (int l = 0; l < LPT; ++l) st_elem(l, r, lane_get(v[r], l), DOT); }
-            if (out_lo) { if (want_dot) { HIPGP_DRAIN(R0 / 2, true) } else { HIPGP_DRAIN(R0 / 2, false) } }
-            else { if (want_dot) { HIPGP_DRAIN(R0, true) } else { HIPGP_DRAIN(R0, false) } }
-#undef HIPGP_DRAIN
-            if (want_dot) {
+            if (out_lo) {
 #pragma unroll
-                for (int l = 0; l < LPT; ++l) scratch[(lane * LPT + l) * S0 + j] = accd[l];
+                for (int r = 0; r < R0 / 2; ++r) put(r);
+            } else {
+#pragma unroll
+                for (int r = 0; r < R0; ++r) put(r);
+            }
+        }
+    }
+    __syncthreads();
+    // ---- streaming phase: one warp per row, 16-byte accesses: store (crop) and the fused dot product ----
+    {
+        constexpr int CH = 16 / (int)sizeof(T);
+        constexpr int NW = NT / 32, WPR = NW > NROW ? NW / NROW : 1, TW = 32 * WPR;
+        const int warp = tid >> 5, ln = (tid & 31) + 32 * (warp % WPR);
+        const bool chunked = P.vec16_ok && (n % CH == 0);
+        for (int row = warp / WPR; row < nl; row += NW / WPR) {
+            const T* srow = side + (size_t)row * SROW;
+            const size_t off = (size_t)(g0 + row) * n;
+            double acc = 0.0;
+            if (chunked) {
+                const int nch = n / CH;
+                constexpr int BS = 8;
+                for (int cb = ln; cb < nch; cb += TW * BS) {
+                    Vec16<T> ov[BS];
+                    if (want_dot) {
+#pragma unroll
+                        for (int k = 0; k < BS; ++k) { const int c = cb + TW * k; if (c < nch) ov[k] = ldv_stream((const T*)P.v0 + off + (size_t)c * CH); }
+                    }
+#pragma unroll
+                    for (int k = 0; k < BS; ++k) {
+                        const int c = cb + TW * k;
+                        if (c < nch) {
+                            const Vec16<T> y = *reinterpret_cast<const Vec16<T>*>(srow + c * CH);
+                            if (want_dot) {
+#pragma unroll
+                                for (int e = 0; e < CH; ++e) acc += (double)(y.v[e] * ov[k].v[e]);
+                            }
+                            stv_stream(P.out + off + (size_t)c * CH, y);
+                        }
+                    }
+                }
+            } else {
+                for (int i = ln; i < n; i += TW) {
+                    const T y = srow[i];
+                    if (want_dot) acc += (double)(y * ld_stream((const T*)P.v0 + off + i));
+                    st_stream(P.out + off + i, y);
+                }
+            }
+            if (want_dot) {
+                acc = warp_sum(acc);
+                if ((tid & 31) == 0) s_part[row * WPR + warp % WPR] = acc;
             }
         }
     }
     if (want_dot) {
         __syncthreads();
-        rows_reduce_partials(scratch, S0, nl, g0, P.st.partial, tid, NT);
+        constexpr int WPR2 = (NT / 32) > NROW ? (NT / 32) / NROW : 1;
+        if (tid < nl) { double a = 0.0; for (int k = 0; k < WPR2; ++k) a += s_part[tid * WPR2 + k]; P.st.partial[g0 + tid] = a; }
         pcg_finalize(P.st, P.dot_kind, g0, g1, P.nrows, tid, NT);
     }
 }

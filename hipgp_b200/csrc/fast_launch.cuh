@@ -48,7 +48,9 @@ static void launch_rows_fast_t(hipgp_plan* pl, bool inverse, RowsParams<T>& P, c
         const int want_q = NST > 1 ? (H - G::RLAST) / 4 : 0, want_p = NST > 1 ? G::RLAST / 2 + 1 : H / 2 + 1;
         if (P.nquad != want_q || P.npair0 != want_p) throw Error("internal: unexpected r2c pair structure for H = " + std::to_string(H));
     }
-    const size_t smem = G::smem_bytes() + sizeof(double) * (size_t)C::S0 * NROW;
+    // the tile, then the side buffer: the tile's real rows, row-major
+    const size_t smem = G::smem_bytes() + sizeof(T) * (size_t)((P.n_real + 3) & ~3) * NROW;
+    if (smem > 227 * 1024) throw Error("row pass: rows too long for the shared-memory side buffer");
     dim3 grid((unsigned)((P.total_rows + NROW - 1) / NROW));
     PROF_BEGIN(pl, inverse ? 2 : 0, st);
     if (inverse) {
@@ -65,6 +67,21 @@ static void launch_rows_fast_t(hipgp_plan* pl, bool inverse, RowsParams<T>& P, c
     pl->launches++;
 }
 
+// number of CTAs of `kernel` that fit the device at once (persistent kernels size their grid with this)
+template <class K>
+static int resident_ctas(K kernel, int nthreads, size_t smem) {
+#ifdef HIPGP_EMU
+    (void)kernel; (void)nthreads; (void)smem;
+    return 3;
+#else
+    int dev = 0, sms = 0, per = 0;
+    CK(cudaGetDevice(&dev));
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, kernel, nthreads, smem));
+    return sms * (per > 0 ? per : 1);
+#endif
+}
+
 template <class T, int LEN, int... Rs>
 static void launch_cols_fast_t(hipgp_plan* pl, ColsParams<T>& P, long n_outer, long B, cudaStream_t st) {
     using C = FastCfg<T, Rs...>;
@@ -74,18 +91,20 @@ static void launch_cols_fast_t(hipgp_plan* pl, ColsParams<T>& P, long n_outer, l
     P.TB = TBL; P.TBP = TBL;
     if ((P.in_split_len && (P.mode != CM_INV || P.in_split_len % G::RLAST)) || (P.out_split_len && (P.mode != CM_FWD || P.out_split_len % G::RLAST)))
         throw Error("split row blocks are supported for forward-only outputs / inverse-only inputs, in multiples of the last radix");
-    // real spectrum tile through shared memory (8 bytes per lane and padded position) when two CTAs still fit an SM
-    const size_t spec_bytes = (size_t)(C::Ln + C::Ln / G::RLAST) * C::NL * 8;
-    static const char* env_ns = getenv("HIPGP_NO_SPEC_STAGE");
-    P.spec_stage = (G::NST > 1 && P.mode == CM_FUSED && P.spec_kind == SPEC_REAL && C::MINB * (G::smem_bytes() + spec_bytes + 1024) <= 227 * 1024 && !env_ns) ? 1 : 0;
-    static const char* env_dbg = getenv("HIPGP_DBG");
-    P.dbg = env_dbg ? atoi(env_dbg) : 0;
-    const size_t smem = G::smem_bytes() + (P.spec_stage ? spec_bytes : 0);
-    dim3 grid((unsigned)((P.inner + TBL - 1) / TBL), (unsigned)n_outer, (unsigned)B);
+    // side buffer (8 bytes per lane and padded position): next tile's input rows / this tile's real spectrum
+    const size_t side_bytes = G::NST > 1 ? (size_t)(C::Ln + C::Ln / G::RLAST) * C::NL * 8 : 0;
+    static const char* env_ns = getenv("HIPGP_NO_STAGE");
+    const bool use_side = G::NST > 1 && !env_ns;
+    P.spec_stage = (use_side && P.mode == CM_FUSED && P.spec_kind == SPEC_REAL) ? 1 : 0;
+    P.in_stage = (use_side && P.mode != CM_INV && (size_t)P.n_in * C::NL * 16 <= side_bytes) ? 1 : 0;
+    const size_t smem = G::smem_bytes() + ((P.spec_stage || P.in_stage) ? side_bytes : 0);
+    P.nx = (int)((P.inner + TBL - 1) / TBL); P.ny = (int)n_outer; P.nz = (int)B;
     auto k = cols_fast_kernel<T, C::NL, C::NT, C::MINB, Rs...>;
     if (smem > 48 * 1024) HIPGP_SET_MAX_SMEM(k, smem);
+    const long ntiles = (long)P.nx * P.ny * P.nz;
+    const long grid = std::min<long>(ntiles, resident_ctas(k, C::NT, smem));
     PROF_BEGIN(pl, 1, st);
-    HIPGP_LAUNCH(k, grid, dim3(C::NT), smem, st, P);
+    HIPGP_LAUNCH(k, dim3((unsigned)grid), dim3(C::NT), smem, st, P);
     PROF_END(pl, st);
     CK_LAUNCH();
     pl->launches++;

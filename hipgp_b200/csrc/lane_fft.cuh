@@ -118,6 +118,19 @@ __device__ __forceinline__ void st_stream(double* p, double v) { __stcg(p, v); }
 __device__ __forceinline__ void st_stream(cplx<float>* p, cplx<float> v) { __stcg(reinterpret_cast<float2*>(p), make_float2(v.x, v.y)); }
 __device__ __forceinline__ void st_stream(cplx<double>* p, cplx<double> v) { __stcg(reinterpret_cast<double2*>(p), make_double2(v.x, v.y)); }
 #endif
+// 16 bytes of reals (vector rows are streamed in 16-byte chunks by the row kernels)
+template <class T> struct Vec16;
+template <> struct __align__(16) Vec16<float> { float v[4]; };
+template <> struct __align__(16) Vec16<double> { double v[2]; };
+#ifdef HIPGP_EMU
+template <class T> __device__ __forceinline__ Vec16<T> ldv_stream(const T* p) { return *reinterpret_cast<const Vec16<T>*>(p); }
+template <class T> __device__ __forceinline__ void stv_stream(T* p, Vec16<T> v) { *reinterpret_cast<Vec16<T>*>(p) = v; }
+#else
+__device__ __forceinline__ Vec16<float> ldv_stream(const float* p) { const float4 t = __ldcg(reinterpret_cast<const float4*>(p)); Vec16<float> r; r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w; return r; }
+__device__ __forceinline__ Vec16<double> ldv_stream(const double* p) { const double2 t = __ldcg(reinterpret_cast<const double2*>(p)); Vec16<double> r; r.v[0] = t.x; r.v[1] = t.y; return r; }
+__device__ __forceinline__ void stv_stream(float* p, Vec16<float> v) { __stcg(reinterpret_cast<float4*>(p), make_float4(v.v[0], v.v[1], v.v[2], v.v[3])); }
+__device__ __forceinline__ void stv_stream(double* p, Vec16<double> v) { __stcg(reinterpret_cast<double2*>(p), make_double2(v.v[0], v.v[1])); }
+#endif
 __device__ __forceinline__ Lane<float> lane_from_global(const cplx<float>* p) {
 #ifdef HIPGP_EMU
     return *reinterpret_cast<const Lane<float>*>(p);

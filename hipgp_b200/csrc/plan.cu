@@ -54,6 +54,10 @@ static bool geom_allows_fast(const Geom<T>& g) {
 template <class T>
 static void launch_rows(hipgp_plan* pl, bool inverse, RowsParams<T>& P, cudaStream_t st, bool allow_fast = true) {
     P.vec_ok = (aligned2<T>(P.in) && aligned2<T>(P.out) && aligned2<T>(P.v0) && aligned2<T>(P.v1) && aligned2<T>(P.v2)) ? 1 : 0;
+    {
+        auto a16 = [](const void* q) { return ((uintptr_t)q % 16) == 0; };
+        P.vec16_ok = (a16(P.in) && a16(P.out) && a16(P.v0) && a16(P.v1) && a16(P.v2)) ? 1 : 0;
+    }
     if (allow_fast && P.do_fft && launch_rows_fast<T>(pl, inverse, P, st)) return;
     int nth;
     pick_rows_tiling<T>(P.total_rows, P.H, &P.RB, &P.RBP, &nth);

@@ -14,5 +14,7 @@ nvcc $FLAGS -DHIPGP_INST_GROUP=7 -c fast_inst.cu -o build/v_$SUF/fi_7.o &
 nvcc $FLAGS -DHIPGP_INST_GROUP=8 -c fast_inst.cu -o build/v_$SUF/fi_8.o &
 nvcc $FLAGS -DHIPGP_INST_GROUP=9 -c fast_inst.cu -o build/v_$SUF/fi_9.o &
 wait
+for g in 0 1 2 3 4 5 6 7 8 9; do test -f build/v_$SUF/fi_$g.o || { echo "group $g failed"; exit 1; }; done
+test -f build/v_$SUF/plan.o || { echo plan failed; exit 1; }
 nvcc -gencode arch=compute_100a,code=sm_100a -shared -o variants/lib_$SUF.so build/v_$SUF/*.o
 echo built variants/lib_$SUF.so
