@@ -65,7 +65,7 @@ class ClockSampler(threading.Thread):
              "clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             for line in self.proc.stdout:
                 if self.stop_flag:
@@ -74,10 +74,27 @@ class ClockSampler(threading.Thread):
         except Exception:
             pass
 
-    def finish(self):
+    def mark(self):
+        return len(self.samples)
+
+    def wait_running(self, timeout=5.0):
+        t0 = time.time()
+        while not self.samples and time.time() - t0 < timeout:
+            time.sleep(0.01)
+
+    def finish(self, lo=0, hi=None, lo_fallback=None, hi_fallback=None):
+        """Samples [lo, hi) = the timed region; if that window holds fewer than 3 samples (a very short region) it is
+        widened to [lo_fallback, hi_fallback) -- the same steps repeated under the same load -- and that is reported."""
         self.stop_flag = True
         if self.proc:
             self.proc.terminate()
+        window = "timed region"
+        sel = self.samples[lo:hi]
+        if len(sel) < 3 and lo_fallback is not None:
+            sel = self.samples[lo_fallback:hi_fallback]
+            window = "timed region + the e2e / roofline passes of the same step (timed region shorter than 3 sampling periods)"
+        self.samples = sel
+        self.window = window
         sm = sorted(int(float(s[0])) for s in self.samples if s and s[0].replace(".", "").isdigit())
         mx = [int(float(s[1])) for s in self.samples if len(s) > 1 and s[1].replace(".", "").isdigit()]
         reasons = set()
@@ -86,7 +103,7 @@ class ClockSampler(threading.Thread):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "window": getattr(self, "window", "")}
 
 
 def oracle_step(B, threads=None):
@@ -187,15 +204,17 @@ def run_gpu(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
-    for _ in range(max(args.warmup, 3)):
-        step_dev()
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
+        sampler.wait_running()
+    for _ in range(max(args.warmup, 3)):
+        step_dev()
+    m0 = sampler.mark() if sampler else 0
     l0 = plan.launch_count()
     ms_total = timed(step_dev, args.steps)
     launches = plan.launch_count() - l0
-    clocks = sampler.finish() if sampler else None
+    m1 = sampler.mark() if sampler else 0
 
     for _ in range(2):
         step_e2e()
@@ -208,6 +227,8 @@ def run_gpu(args):
         step_dev()
     prof = plan.profile_read(reset=True)
     plan.profile(False)
+    m2 = sampler.mark() if sampler else 0
+    clocks = sampler.finish(m0, m1, m0, m2) if sampler else None
 
     # fp64 and B=1 companions (not the headline; same step definition)
     extra = {}
@@ -287,7 +308,7 @@ def run_gpu(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--quick", action="store_true", help="skip the companion measurements")
