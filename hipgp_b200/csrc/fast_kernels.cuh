@@ -58,7 +58,10 @@ __device__ __forceinline__ Lane<double> lane_spec(Lane<double> v, const void* sp
     return kind == SPEC_CPLX ? lmul(v, w) : lmulc(v, w);
 }
 // real spectrum factor(s) of one lane staged in shared memory (8 bytes per lane)
-__device__ __forceinline__ Lane<float> lane_spec_smem(Lane<float> v, const void* p) { const cplx<float> sv = *reinterpret_cast<const cplx<float>*>(p); return lmul_real2(v, sv.x, sv.y); }
+__device__ __forceinline__ Lane<float> lane_spec_smem(Lane<float> v, const void* p) {
+    const float2 s2 = *reinterpret_cast<const float2*>(p);      // stays a register pair: the packed multiply takes it as is
+    Lane<float> r; r.re = __fmul2_rn(v.re, s2); r.im = __fmul2_rn(v.im, s2); return r;
+}
 __device__ __forceinline__ Lane<double> lane_spec_smem(Lane<double> v, const void* p) { return lscale(v, *reinterpret_cast<const double*>(p)); }
 
 // =====================================================================================================
@@ -362,7 +365,7 @@ __global__ void __launch_bounds__(NT, MINB) rows_fwd_fast_kernel(RowsParams<T> P
                     *reinterpret_cast<Vec16<T>*>(srow + c * CH) = a;
                 };
                 if (mode == RF_XRUPDATE) {
-                    constexpr int BS = 4;
+                    constexpr int BS = 2;
                     for (int cb = ln; cb < nch; cb += TW * BS) {
                         Vec16<T> a[BS], pv[BS], xv[BS], rv[BS];
 #pragma unroll
@@ -387,7 +390,7 @@ __global__ void __launch_bounds__(NT, MINB) rows_fwd_fast_kernel(RowsParams<T> P
                         }
                     }
                 } else if (mode == RF_PUPDATE && !first_it) {
-                    constexpr int BS = 8;
+                    constexpr int BS = 4;
                     for (int cb = ln; cb < nch; cb += TW * BS) {
                         Vec16<T> a[BS], pv[BS];
 #pragma unroll
@@ -635,37 +638,46 @@ __global__ void __launch_bounds__(NT, MINB) rows_inv_fast_kernel(RowsParams<T> P
             if (q2 != q) s[G::slot(q2) * NL + lane] = lconj(E - iO);
         }
     }
-    // (b) quads: table and workspace loads of all of a thread's quads are issued up front
+    // (b) quads: the table and workspace loads of all of a thread's quads are issued up front, branch-free (rows past
+    //     the end of the batch read the last valid row and are dropped at the very end), so they are all in flight together
     if constexpr (NQUAD > 0) {
         constexpr int QIT = (NQUAD * NL + NT - 1) / NT;
         QuadIdx qq[QIT]; cplx<T> wa[QIT], wa1[QIT];
+        cplx<T> ya[QIT][LPT], ya1[QIT][LPT], yb[QIT][LPT], yb1[QIT][LPT];
 #pragma unroll
         for (int k = 0; k < QIT; ++k) {
-            const int it = tid + k * NT, qi = it / NL;
-            if (it < NQUAD * NL) { qq[k] = reinterpret_cast<const QuadIdx*>(P.quadq)[qi]; wa[k] = ldg_c(P.quadw + 2 * qi); wa1[k] = ldg_c(P.quadw + 2 * qi + 1); }
+            int it = tid + k * NT;
+            it = it < NQUAD * NL ? it : NQUAD * NL - 1;
+            const int qi = it / NL;
+            qq[k] = reinterpret_cast<const QuadIdx*>(P.quadq)[qi]; wa[k] = ldg_c(P.quadw + 2 * qi); wa1[k] = ldg_c(P.quadw + 2 * qi + 1);
+        }
+#pragma unroll
+        for (int k = 0; k < QIT; ++k) {
+            int it = tid + k * NT;
+            it = it < NQUAD * NL ? it : NQUAD * NL - 1;
+            const int lane = it % NL;
+#pragma unroll
+            for (int l = 0; l < LPT; ++l) {
+                const int row = lane * LPT + l;
+                const cplx<T>* src = P.W + s_wbase[row < nl ? row : nl - 1];
+                WRow<T>::load2(src, qq[k].a, ya[k][l], ya1[k][l]);
+                WRow<T>::load2(src, qq[k].b, yb[k][l], yb1[k][l]);
+            }
         }
 #pragma unroll
         for (int k = 0; k < QIT; ++k) {
             const int it = tid + k * NT, lane = it % NL;
             if (it < NQUAD * NL) {
                 const bool self = qq[k].a == qq[k].b;
-                cplx<T> ya[LPT], ya1[LPT], yb[LPT], yb1[LPT];
+                if (spec_kind != SPEC_NONE) {
 #pragma unroll
-                for (int l = 0; l < LPT; ++l) {
-                    const int row = lane * LPT + l;
-                    ya[l] = ya1[l] = yb[l] = yb1[l] = mk<T>(0, 0);
-                    if (row < nl) {
-                        const cplx<T>* src = P.W + s_wbase[row];
-                        WRow<T>::load2(src, qq[k].a, ya[l], ya1[l]);
-                        if (self) { yb[l] = ya[l]; yb1[l] = ya1[l]; } else WRow<T>::load2(src, qq[k].b, yb[l], yb1[l]);
-                        if (spec_kind != SPEC_NONE) {
-                            ya[l] = apply_spec(ya[l], P.spec, spec_kind, (size_t)qq[k].a); ya1[l] = apply_spec(ya1[l], P.spec, spec_kind, (size_t)qq[k].a + 1);
-                            yb[l] = apply_spec(yb[l], P.spec, spec_kind, (size_t)qq[k].b); yb1[l] = apply_spec(yb1[l], P.spec, spec_kind, (size_t)qq[k].b + 1);
-                        }
+                    for (int l = 0; l < LPT; ++l) {
+                        ya[k][l] = apply_spec(ya[k][l], P.spec, spec_kind, (size_t)qq[k].a); ya1[k][l] = apply_spec(ya1[k][l], P.spec, spec_kind, (size_t)qq[k].a + 1);
+                        yb[k][l] = apply_spec(yb[k][l], P.spec, spec_kind, (size_t)qq[k].b); yb1[k][l] = apply_spec(yb1[k][l], P.spec, spec_kind, (size_t)qq[k].b + 1);
                     }
                 }
-                const Lane<T> A = lane_make(ya[0], ya[LPT - 1]), A1 = lane_make(ya1[0], ya1[LPT - 1]);
-                const Lane<T> Bn = lane_make(yb[0], yb[LPT - 1]), B1 = lane_make(yb1[0], yb1[LPT - 1]);
+                const Lane<T> A = lane_make(ya[k][0], ya[k][LPT - 1]), A1 = lane_make(ya1[k][0], ya1[k][LPT - 1]);
+                const Lane<T> Bn = lane_make(yb[k][0], yb[k][LPT - 1]), B1 = lane_make(yb1[k][0], yb1[k][LPT - 1]);
                 Lane<T>* pa = s + (G::slot(qq[k].a) * NL + lane);
                 Lane<T>* pb = s + (G::slot(qq[k].b) * NL + lane);
                 // bin a with mirror b+1

@@ -449,22 +449,6 @@ static void matvec(hipgp_plan* pl, int mode, const void* in, void* out, long B, 
         case HIPGP_MV_R: spec = pl->specW.p; kind = SPEC_CPLX_CONJ; break;
         default: throw Error("unknown matvec mode");
     }
-    {
-        // EXPERIMENT: process the right-hand sides in chunks so that the frequency workspace of a chunk stays in L2
-        static const char* env = getenv("HIPGP_BCHUNK");
-        const long chunk = env ? atol(env) : 0;
-        if (chunk > 0 && chunk < B) {
-            long in_sz = 1, out_sz = 1;
-            for (int d = 0; d < pl->D; ++d) { in_sz *= n_in[d]; out_sz *= n_out[d]; }
-            for (long b0 = 0; b0 < B; b0 += chunk) {
-                const long nb = std::min(chunk, B - b0);
-                RowsFusion f2 = ff, i2 = fi;
-                f2.in = (const T*)in + b0 * in_sz; i2.out = (T*)out + b0 * out_sz;
-                run_pipeline<T>(pl, g, n_in, n_out, spec, kind, nb, f2, i2, null_state(), false, s);
-            }
-            return;
-        }
-    }
     run_pipeline<T>(pl, g, n_in, n_out, spec, kind, B, ff, fi, null_state(), false, s);
 }
 
