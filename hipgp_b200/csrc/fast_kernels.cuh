@@ -364,65 +364,85 @@ __global__ void __launch_bounds__(NT, MINB) rows_fwd_fast_kernel(RowsParams<T> P
                     }
                     *reinterpret_cast<Vec16<T>*>(srow + c * CH) = a;
                 };
-                if (mode == RF_XRUPDATE) {
-                    constexpr int BS = 2;
-                    for (int cb = ln; cb < nch; cb += TW * BS) {
-                        Vec16<T> a[BS], pv[BS], xv[BS], rv[BS];
-#pragma unroll
-                        for (int k = 0; k < BS; ++k) {
-                            const int c = cb + TW * k;
-                            if (c < nch) {
-                                const size_t o = off + (size_t)c * CH;
-                                a[k] = ldv_stream(P.in + o); pv[k] = ldv_stream(P.v2 + o); xv[k] = ldv_stream((const T*)P.v1 + o); rv[k] = ldv_stream((const T*)P.v0 + o);
-                            }
-                        }
-#pragma unroll
-                        for (int k = 0; k < BS; ++k) {
-                            const int c = cb + TW * k;
-                            if (c < nch) {
-                                const size_t o = off + (size_t)c * CH;
-#pragma unroll
-                                for (int e = 0; e < CH; ++e) { xv[k].v[e] = xv[k].v[e] + coef * pv[k].v[e]; a[k].v[e] = rv[k].v[e] - coef * a[k].v[e]; }
-                                stv_stream(P.v1 + o, xv[k]);
-                                stv_stream(P.v0 + o, a[k]);
-                                finish(c, a[k]);
-                            }
-                        }
-                    }
-                } else if (mode == RF_PUPDATE && !first_it) {
-                    constexpr int BS = 4;
-                    for (int cb = ln; cb < nch; cb += TW * BS) {
-                        Vec16<T> a[BS], pv[BS];
-#pragma unroll
-                        for (int k = 0; k < BS; ++k) {
-                            const int c = cb + TW * k;
-                            if (c < nch) { const size_t o = off + (size_t)c * CH; a[k] = ldv_stream(P.in + o); pv[k] = ldv_stream((const T*)P.v0 + o); }
-                        }
-#pragma unroll
-                        for (int k = 0; k < BS; ++k) {
-                            const int c = cb + TW * k;
-                            if (c < nch) {
-#pragma unroll
-                                for (int e = 0; e < CH; ++e) a[k].v[e] = a[k].v[e] + coef * pv[k].v[e];
-                                stv_stream(P.v0 + off + (size_t)c * CH, a[k]);
-                                finish(c, a[k]);
-                            }
-                        }
-                    }
-                } else {
-                    constexpr int BS = 8;
-                    const bool wr = mode == RF_PUPDATE;      // first iteration: p = z
-                    for (int cb = ln; cb < nch; cb += TW * BS) {
-                        Vec16<T> a[BS];
-#pragma unroll
-                        for (int k = 0; k < BS; ++k) { const int c = cb + TW * k; if (c < nch) a[k] = ldv_stream(P.in + off + (size_t)c * CH); }
-#pragma unroll
-                        for (int k = 0; k < BS; ++k) {
-                            const int c = cb + TW * k;
-                            if (c < nch) { if (wr) stv_stream(P.v0 + off + (size_t)c * CH, a[k]); finish(c, a[k]); }
-                        }
-                    }
+                // two register sets, software-pipelined: the loads of batch b+1 are issued before batch b is consumed,
+                // so a full batch of 16-byte loads per lane is always in flight
+#define HIPGP_PIPE(LOAD, PROC)                                                                              \
+                {                                                                                           \
+                    const int step = TW * BS;                                                               \
+                    int cb = ln;                                                                            \
+                    LOAD(0, cb);                                                                            \
+                    for (; cb < nch; cb += 2 * step) {                                                      \
+                        if (cb + step < nch) { LOAD(1, cb + step); }                                        \
+                        PROC(0, cb);                                                                        \
+                        if (cb + 2 * step < nch) { LOAD(0, cb + 2 * step); }                                \
+                        if (cb + step < nch) { PROC(1, cb + step); }                                        \
+                    }                                                                                       \
                 }
+                if (mode == RF_XRUPDATE) {
+                    constexpr int BS = 1;
+                    Vec16<T> a[2][BS], pv[2][BS], xv[2][BS], rv[2][BS];
+#define HIPGP_LD(S, CB)                                                                                     \
+                    _Pragma("unroll") for (int k = 0; k < BS; ++k) {                                        \
+                        const int c = (CB) + TW * k;                                                        \
+                        if (c < nch) {                                                                      \
+                            const size_t o = off + (size_t)c * CH;                                          \
+                            a[S][k] = ldv_stream(P.in + o); pv[S][k] = ldv_stream(P.v2 + o);                \
+                            xv[S][k] = ldv_stream((const T*)P.v1 + o); rv[S][k] = ldv_stream((const T*)P.v0 + o); \
+                        }                                                                                   \
+                    }
+#define HIPGP_PR(S, CB)                                                                                     \
+                    _Pragma("unroll") for (int k = 0; k < BS; ++k) {                                        \
+                        const int c = (CB) + TW * k;                                                        \
+                        if (c < nch) {                                                                      \
+                            const size_t o = off + (size_t)c * CH;                                          \
+                            _Pragma("unroll") for (int e = 0; e < CH; ++e) {                                \
+                                xv[S][k].v[e] = xv[S][k].v[e] + coef * pv[S][k].v[e];                       \
+                                a[S][k].v[e] = rv[S][k].v[e] - coef * a[S][k].v[e];                         \
+                            }                                                                               \
+                            stv_stream(P.v1 + o, xv[S][k]);                                                 \
+                            stv_stream(P.v0 + o, a[S][k]);                                                  \
+                            finish(c, a[S][k]);                                                             \
+                        }                                                                                   \
+                    }
+                    HIPGP_PIPE(HIPGP_LD, HIPGP_PR)
+#undef HIPGP_LD
+#undef HIPGP_PR
+                } else if (mode == RF_PUPDATE && !first_it) {
+                    constexpr int BS = 2;
+                    Vec16<T> a[2][BS], pv[2][BS];
+#define HIPGP_LD(S, CB)                                                                                     \
+                    _Pragma("unroll") for (int k = 0; k < BS; ++k) {                                        \
+                        const int c = (CB) + TW * k;                                                        \
+                        if (c < nch) { const size_t o = off + (size_t)c * CH; a[S][k] = ldv_stream(P.in + o); pv[S][k] = ldv_stream((const T*)P.v0 + o); } \
+                    }
+#define HIPGP_PR(S, CB)                                                                                     \
+                    _Pragma("unroll") for (int k = 0; k < BS; ++k) {                                        \
+                        const int c = (CB) + TW * k;                                                        \
+                        if (c < nch) {                                                                      \
+                            _Pragma("unroll") for (int e = 0; e < CH; ++e) a[S][k].v[e] = a[S][k].v[e] + coef * pv[S][k].v[e]; \
+                            stv_stream(P.v0 + off + (size_t)c * CH, a[S][k]);                               \
+                            finish(c, a[S][k]);                                                             \
+                        }                                                                                   \
+                    }
+                    HIPGP_PIPE(HIPGP_LD, HIPGP_PR)
+#undef HIPGP_LD
+#undef HIPGP_PR
+                } else {
+                    constexpr int BS = 4;
+                    const bool wr = mode == RF_PUPDATE;      // first iteration: p = z
+                    Vec16<T> a[2][BS];
+#define HIPGP_LD(S, CB)                                                                                     \
+                    _Pragma("unroll") for (int k = 0; k < BS; ++k) { const int c = (CB) + TW * k; if (c < nch) a[S][k] = ldv_stream(P.in + off + (size_t)c * CH); }
+#define HIPGP_PR(S, CB)                                                                                     \
+                    _Pragma("unroll") for (int k = 0; k < BS; ++k) {                                        \
+                        const int c = (CB) + TW * k;                                                        \
+                        if (c < nch) { if (wr) stv_stream(P.v0 + off + (size_t)c * CH, a[S][k]); finish(c, a[S][k]); } \
+                    }
+                    HIPGP_PIPE(HIPGP_LD, HIPGP_PR)
+#undef HIPGP_LD
+#undef HIPGP_PR
+                }
+#undef HIPGP_PIPE
             } else {
                 for (int i = ln; i < n; i += TW) {
                     const size_t o = off + i;
