@@ -36,6 +36,13 @@ struct FastCfg {
     static constexpr int S0 = Ln / (RLInfo<List>::count ? RLFirst<List>::value : 1);
 };
 
+static void launch_check(const char* what, int len, int nl, int nt, size_t smem, long grid) {
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess)
+        throw Error(std::string(what) + " launch failed (length " + std::to_string(len) + ", lanes " + std::to_string(nl) + ", threads " + std::to_string(nt) +
+                    ", shared " + std::to_string(smem) + " B, grid " + std::to_string(grid) + "): " + cudaGetErrorString(e));
+}
+
 template <class T, int... Rs>
 static void launch_rows_fast_t(hipgp_plan* pl, bool inverse, RowsParams<T>& P, cudaStream_t st) {
     using C = FastCfg<T, Rs...>;
@@ -55,15 +62,15 @@ static void launch_rows_fast_t(hipgp_plan* pl, bool inverse, RowsParams<T>& P, c
     PROF_BEGIN(pl, inverse ? 2 : 0, st);
     if (inverse) {
         auto k = rows_inv_fast_kernel<T, C::NL, C::NT, C::MINB, Rs...>;
-        if (smem > 48 * 1024) HIPGP_SET_MAX_SMEM(k, smem);
+        if (smem > 40 * 1024) HIPGP_SET_MAX_SMEM(k, smem);   // (static shared memory counts against the 48 KB default too)
         HIPGP_LAUNCH(k, grid, dim3(C::NT), smem, st, P);
     } else {
         auto k = rows_fwd_fast_kernel<T, C::NL, C::NT, C::MINB, Rs...>;
-        if (smem > 48 * 1024) HIPGP_SET_MAX_SMEM(k, smem);
+        if (smem > 40 * 1024) HIPGP_SET_MAX_SMEM(k, smem);   // (static shared memory counts against the 48 KB default too)
         HIPGP_LAUNCH(k, grid, dim3(C::NT), smem, st, P);
     }
     PROF_END(pl, st);
-    CK_LAUNCH();
+    launch_check("row pass", C::Ln, C::NL, C::NT, smem, (long)grid.x);
     pl->launches++;
 }
 
@@ -100,13 +107,13 @@ static void launch_cols_fast_t(hipgp_plan* pl, ColsParams<T>& P, long n_outer, l
     const size_t smem = G::smem_bytes() + ((P.spec_stage || P.in_stage) ? side_bytes : 0);
     P.nx = (int)((P.inner + TBL - 1) / TBL); P.ny = (int)n_outer; P.nz = (int)B;
     auto k = cols_fast_kernel<T, C::NL, C::NT, C::MINB, Rs...>;
-    if (smem > 48 * 1024) HIPGP_SET_MAX_SMEM(k, smem);
+    if (smem > 40 * 1024) HIPGP_SET_MAX_SMEM(k, smem);   // (static shared memory counts against the 48 KB default too)
     const long ntiles = (long)P.nx * P.ny * P.nz;
     const long grid = std::min<long>(ntiles, resident_ctas(k, C::NT, smem));
     PROF_BEGIN(pl, 1, st);
     HIPGP_LAUNCH(k, dim3((unsigned)grid), dim3(C::NT), smem, st, P);
     PROF_END(pl, st);
-    CK_LAUNCH();
+    launch_check("column pass", C::Ln, C::NL, C::NT, smem, grid);
     pl->launches++;
 }
 

@@ -1,0 +1,89 @@
+"""GPU checks at MEDIUM sizes (past what the golden fixtures and the CPU oracle cover in seconds): every embedding
+length family of the specialised kernels (2^k, 3*2^k, 5*2^k; 1-, 2- and 3-D; narrow and wide geometry), checked through
+size-independent properties of the reference operators (toeplitz_tensor.py:70-125):
+  * K v and the C^-1 block against a dense FFT evaluation of the reference formula in numpy fp64 (host side, checker only);
+  * || R^T v ||^2 = v^T K v  and  R R^T v = K v  (R R^T = K is what makes R^T the whitening factor, hipgp.py:139-146);
+  * fp32 against fp64 of the same plan geometry.
+Tolerances: 1e-5 relative in fp32, 1e-10 in fp64 (north star)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+CASES = [((300,), 3), ((1000,), 2), ((150, 130), 3), ((96, 200), 2), ((300, 300), 2), ((48, 40, 36), 2), ((128, 128, 64), 2),
+         ((20, 257, 33), 1)]
+
+
+def relerr(a, b):
+    a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64)
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+
+
+def first_col(dims):
+    g = np.meshgrid(*[np.linspace(0.0, 1.0 + 0.3 * d, m) for d, m in enumerate(dims)], indexing="ij")
+    r = np.sqrt(sum((x - x.flat[0]) ** 2 for x in g))
+    ell = 3.0 / max(dims)
+    col = (1 + np.sqrt(5) * r / ell + 5 * r ** 2 / (3 * ell ** 2)) * np.exp(-np.sqrt(5) * r / ell)
+    col = col.reshape(-1).copy(); col[0] += 1e-3
+    return col
+
+
+def dense_apply(col, dims, v, f):
+    """reference formula: crop IFFT_N( f(max(Re FFT_N C, 1e-6)) * FFT_N pad v ), N = 2m-2 per axis (numpy fp64)"""
+    D = len(dims)
+    Cc = col.reshape(dims)
+    for d in range(D):
+        if dims[d] > 1:
+            sl = [slice(None)] * D; sl[d] = slice(dims[d] - 2, 0, -1)
+            Cc = np.concatenate([Cc, Cc[tuple(sl)]], axis=d)
+    Dg = np.maximum(np.fft.fftn(Cc).real, 1e-6)
+    x = np.zeros((v.shape[0],) + Cc.shape)
+    x[(slice(None),) + tuple(slice(0, k) for k in dims)] = v.reshape((v.shape[0],) + tuple(dims))
+    ax = tuple(range(1, D + 1))
+    y = np.fft.ifftn(f(Dg) * np.fft.fftn(x, axes=ax), axes=ax).real
+    return y[(slice(None),) + tuple(slice(0, k) for k in dims)].reshape(v.shape[0], -1)
+
+
+@pytest.mark.parametrize("dims,B", CASES, ids=lambda c: "x".join(map(str, c)) if isinstance(c, tuple) else str(c))
+def test_medium_sizes_properties(dims, B):
+    from hipgp_b200.plan import Plan
+    from hipgp_b200 import _lib as L
+    col = first_col(dims)
+    M = int(np.prod(dims))
+    rng = np.random.default_rng(1)
+    v64 = rng.standard_normal((B, M))
+    out = {}
+    for dname, dt, tol in (("f64", torch.float64, 1e-10), ("f32", torch.float32, 1e-5)):
+        plan = Plan(list(dims), dt, DEV).set_first_row(torch.from_numpy(col).to(DEV, dt))
+        v = torch.from_numpy(v64).to(DEV, dt)
+        Kv = plan.matvec(L.MV_K, v)
+        Pv = plan.matvec(L.MV_CINV, v)
+        RTv = plan.matvec(L.MV_RT, v)
+        RRTv = plan.matvec(L.MV_R, RTv)
+        vin = v.double().cpu().numpy()
+        assert relerr(Kv.cpu().numpy(), dense_apply(col, dims, vin, lambda d: d)) < tol
+        # the preconditioner amplifies the smallest eigenvalues: compare on the scale the fp32 spectrum can resolve
+        ptol = tol if dname == "f64" else 3e-3
+        assert relerr(Pv.cpu().numpy(), dense_apply(col, dims, vin, lambda d: 1.0 / d)) < ptol
+        vKv = (v.double() * Kv.double()).sum(1)
+        assert float(((RTv.double() ** 2).sum(1) - vKv).abs().max() / vKv.abs().max()) < 10 * tol
+        assert relerr(RRTv.cpu().numpy(), Kv.cpu().numpy()) < 10 * tol
+        out[dname] = (Kv.double().cpu().numpy(), RTv.double().cpu().numpy())
+    assert relerr(out["f32"][0], out["f64"][0]) < 1e-5 and relerr(out["f32"][1], out["f64"][1]) < 1e-5
+
+
+def test_pcg_medium_against_dense_residual():
+    """PCG at a medium size: the returned x must satisfy the reference residual definition ||b - K x|| with the K of
+    the dense formula, and the device-side residual norms must agree with it."""
+    from hipgp_b200.plan import Plan
+    dims = (150, 130)
+    col = first_col(dims)
+    rng = np.random.default_rng(2)
+    b = rng.standard_normal((3, int(np.prod(dims))))
+    plan = Plan(list(dims), torch.float64, DEV).set_first_row(torch.from_numpy(col).to(DEV))
+    x, info = plan.pcg(torch.from_numpy(b).to(DEV), maxiter=200, tol=1e-9, return_info=True)
+    r = b - dense_apply(col, dims, x.cpu().numpy(), lambda d: d)
+    rn = np.linalg.norm(r, axis=1)
+    assert rn.max() < 1e-8
+    assert np.allclose(rn, np.asarray(info["resid"]), rtol=1e-3, atol=1e-12)
