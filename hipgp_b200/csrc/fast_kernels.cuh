@@ -31,6 +31,12 @@ template <class T> __device__ __forceinline__ void st2(T* p, bool vec, T a, T b,
     else { if (ok0) st_stream(p, a); if (ok1) st_stream(p + 1, b); }
 }
 
+// sum over an aligned team of `tw` lanes (tw a power of two <= 32); every lane of the warp takes part
+__device__ __forceinline__ double team_sum(double v, int tw) {
+    for (int o = tw >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
 // deterministic per-row reduction of per-thread partials in smem scratch: warp `row` sums scratch[row*NI .. +NI)
 __device__ __forceinline__ void rows_reduce_partials(const double* scratch, int NI, int nl, long g0, double* partial, int tid, int nthreads) {
     const int warp = tid >> 5, lane = tid & 31, nwarps = nthreads >> 5;
@@ -346,15 +352,26 @@ __global__ void __launch_bounds__(NT, MINB) rows_fwd_fast_kernel(RowsParams<T> P
     {
         constexpr int CH = 16 / (int)sizeof(T);
         // WPR warps share a row when there are more warps than rows; a row's chunks are dealt out over its TW lanes
-        constexpr int NW = NT / 32, WPR = NW > NROW ? NW / NROW : 1, TW = 32 * WPR;
-        const int warp = tid >> 5, ln = (tid & 31) + 32 * (warp % WPR);
+        // Teams: WPR warps share a row when there are more warps than rows; short rows are dealt to sub-warp teams of
+        // `tws` lanes so that all 32 lanes of a warp stream.  TW = lanes per row, `rstep` = rows per sweep of the CTA.
+        constexpr int NW = NT / 32, WPR = NW > NROW ? NW / NROW : 1;
         const bool chunked = P.vec16_ok && (n % CH == 0);
-        for (int row = warp / WPR; row < nl; row += NW / WPR) {
-            T* srow = side + (size_t)row * SROW;
-            const size_t off = (size_t)(g0 + row) * n;
-            const T coef = s_coef[row];
+        // (team width fixed at compile time from the row length the transform was chosen for: n ~ H reals = H / CH chunks)
+        constexpr int tws = WPR > 1 ? 32 : (H / CH >= 32 ? 32 : (H / CH >= 16 ? 16 : (H / CH >= 8 ? 8 : 4)));
+        constexpr int rpw = 32 / tws;                              // rows per warp
+        constexpr int TW = WPR > 1 ? 32 * WPR : tws;
+        const int warp = tid >> 5, l32 = tid & 31;
+        const int ln = WPR > 1 ? l32 + 32 * (warp % WPR) : l32 % tws;
+        constexpr int rstep = WPR > 1 ? NW / WPR : NW * rpw;
+        for (int rbase = WPR > 1 ? warp / WPR : warp * rpw; rbase < nl; rbase += rstep) {
+            const int row = rbase + (WPR > 1 ? 0 : l32 / tws);
+            const bool ractive = row < nl;
+            T* srow = side + (size_t)(ractive ? row : 0) * SROW;
+            const size_t off = (size_t)(g0 + (ractive ? row : 0)) * n;
+            const T coef = s_coef[ractive ? row : 0];
             double acc = 0.0;
-            if (chunked) {
+            if (!ractive) {
+            } else if (chunked) {
                 // batches of BS chunks per lane: all loads of a batch are in flight before the first use
                 const int nch = n / CH;
                 auto finish = [&](int c, Vec16<T> a) {
@@ -460,10 +477,10 @@ __global__ void __launch_bounds__(NT, MINB) rows_fwd_fast_kernel(RowsParams<T> P
                     srow[i] = a;
                 }
             }
-            for (int i = n + ln; i < SROW; i += TW) srow[i] = (T)0;
+            if (ractive) for (int i = n + ln; i < SROW; i += TW) srow[i] = (T)0;
             if (want_dot) {
-                acc = warp_sum(acc);
-                if ((tid & 31) == 0) s_part[row * WPR + warp % WPR] = acc;
+                acc = team_sum(acc, WPR > 1 ? 32 : tws);
+                if (ractive && (WPR > 1 ? l32 == 0 : ln == 0)) s_part[row * WPR + warp % WPR] = acc;
             }
         }
         if (want_dot) {      // fixed-order sum of the WPR partials of a row
@@ -767,14 +784,22 @@ __global__ void __launch_bounds__(NT, MINB) rows_inv_fast_kernel(RowsParams<T> P
     // ---- streaming phase: one warp per row, 16-byte accesses: store (crop) and the fused dot product ----
     {
         constexpr int CH = 16 / (int)sizeof(T);
-        constexpr int NW = NT / 32, WPR = NW > NROW ? NW / NROW : 1, TW = 32 * WPR;
-        const int warp = tid >> 5, ln = (tid & 31) + 32 * (warp % WPR);
+        constexpr int NW = NT / 32, WPR = NW > NROW ? NW / NROW : 1;
         const bool chunked = P.vec16_ok && (n % CH == 0);
-        for (int row = warp / WPR; row < nl; row += NW / WPR) {
-            const T* srow = side + (size_t)row * SROW;
-            const size_t off = (size_t)(g0 + row) * n;
+        constexpr int tws = WPR > 1 ? 32 : (H / CH >= 32 ? 32 : (H / CH >= 16 ? 16 : (H / CH >= 8 ? 8 : 4)));
+        constexpr int rpw = 32 / tws;
+        constexpr int TW = WPR > 1 ? 32 * WPR : tws;
+        const int warp = tid >> 5, l32 = tid & 31;
+        const int ln = WPR > 1 ? l32 + 32 * (warp % WPR) : l32 % tws;
+        constexpr int rstep = WPR > 1 ? NW / WPR : NW * rpw;
+        for (int rbase = WPR > 1 ? warp / WPR : warp * rpw; rbase < nl; rbase += rstep) {
+            const int row = rbase + (WPR > 1 ? 0 : l32 / tws);
+            const bool ractive = row < nl;
+            const T* srow = side + (size_t)(ractive ? row : 0) * SROW;
+            const size_t off = (size_t)(g0 + (ractive ? row : 0)) * n;
             double acc = 0.0;
-            if (chunked) {
+            if (!ractive) {
+            } else if (chunked) {
                 const int nch = n / CH;
                 constexpr int BS = 8;
                 for (int cb = ln; cb < nch; cb += TW * BS) {
@@ -804,8 +829,8 @@ __global__ void __launch_bounds__(NT, MINB) rows_inv_fast_kernel(RowsParams<T> P
                 }
             }
             if (want_dot) {
-                acc = warp_sum(acc);
-                if ((tid & 31) == 0) s_part[row * WPR + warp % WPR] = acc;
+                acc = team_sum(acc, WPR > 1 ? 32 : tws);
+                if (ractive && (WPR > 1 ? l32 == 0 : ln == 0)) s_part[row * WPR + warp % WPR] = acc;
             }
         }
     }
