@@ -97,6 +97,24 @@ class ToeplitzInducingGP(nn.Module):
             return Kmm._matmul_by_RT(d0)
         return Kmm._plan.compute_kn(Knm, maxiter=maxiter_cg, tol=tol)
 
+    @staticmethod
+    def batch_slices(n, batch_size):
+        """The batches of `batch_predict` (svi_gp.py:81-85): ceil(n / batch_size) slices, the last one ragged."""
+        num_batches = int(np.ceil(n / batch_size))
+        return [slice((it % num_batches) * batch_size, min(((it % num_batches) + 1) * batch_size, n)) for it in range(num_batches)]
+
+    def batch_predict(self, x, batch_size, verbose=True, **kwargs):
+        """Wraps predict(...) into smaller batch predictions (svi_gp.py:78-97).  The batches stream through the device:
+        results stay in HBM and come back with ONE device-to-host copy at the end."""
+        batches = self.batch_slices(len(x), batch_size)
+        mus, sigs = [], []
+        for bi, b in enumerate(batches):
+            fmu, fsig = self.predict(x[b], _on_device=True, **kwargs)
+            mus.append(fmu); sigs.append(fsig)
+            if bi % 100 == 0 and verbose:
+                print(" ... batch_predict %d / %d batches" % (bi, len(batches)))
+        return torch.cat(mus, dim=0).cpu(), torch.cat(sigs, dim=0).cpu()
+
     def _make_grams(self, xbatch, integrated_obs=False, semi_integrated_estimator="analytic", semi_integrated_samps=10):
         """gram matrices needed for elbo, predict, etc (svi_gp.py:48-76), evaluated on the fly from the grid."""
         kern_params = self.get_kernel_params()
@@ -206,7 +224,7 @@ class MeanFieldToeplitzGP(ToeplitzInducingGP):
         return elbo_estimate
 
     def predict(self, x, integrated_obs=False, semi_integrated_estimator="analytic", semi_integrated_samps=10,
-                maxiter_cg=50, Kmm=None):
+                maxiter_cg=50, Kmm=None, _on_device=False):
         """E[f(x)] and sd[f(x)] (hipgp.py:416-446)"""
         x = x.to(self.xgrids[0].device)
         with torch.no_grad():
@@ -218,4 +236,6 @@ class MeanFieldToeplitzGP(ToeplitzInducingGP):
             knt_m, knt_kn, knSkn = self._row_stats(kn, qm, qS)
             ktilde_star = (Knn_diag.reshape(-1) - knt_kn).clamp_min(1e-5)
             sig_star = torch.sqrt(ktilde_star + knSkn)[:, None]
+        if _on_device:
+            return knt_m[:, None].detach(), sig_star.detach()
         return knt_m[:, None].cpu().detach(), sig_star.cpu().detach()

@@ -375,3 +375,13 @@ def meanfield_elbo_and_grad(xgrids, kfun, Knm, Knn_diag, ybatch, noise_std_batch
     dS = -.5 * lam_diag[:, None] - theta2
     deta1 = dm + dS * (-2 * qm)
     return elbo, -deta1, -dS
+
+
+def batch_indices(n, batch_size):
+    """svi_gp.py:81-85 (batch_predict): slices of the prediction batches, restated verbatim."""
+    num_batches = int(np.ceil(n / batch_size))
+
+    def one(it):
+        idx = it % num_batches
+        return slice(idx * batch_size, min((idx + 1) * batch_size, n))
+    return [one(i) for i in range(num_batches)]

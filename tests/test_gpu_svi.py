@@ -114,3 +114,39 @@ def test_slab_decomposed_matvec_emulated(dname, nranks):
         got = torch.cat(slab.matvec(mode, slabs)).reshape(1, -1)
         assert relerr(got, full.matvec(mode, v).cpu().numpy()) < tol
         assert relerr(got, ref.numpy()) < (tol if mode == L.MV_K else 50 * tol)
+
+
+def test_batch_predict_streams_the_same_batches(golden_dir):
+    """batch_predict (svi_gp.py:78-97): same batches as the reference's batch_indices (bit-exact slices), each predicted
+    exactly as predict() does, one D2H copy at the end."""
+    from oracle import ziggy_oracle as zo
+    g = np.load(os.path.join(golden_dir, "svi_step_f64.npz"))
+    mod = make_model(g, torch.float64)
+    x = torch.from_numpy(g["x"]).to(DEV)
+    n = x.shape[0]
+    for bs in (7, n, n + 3, 1):
+        if bs == 1 and n > 40:
+            continue
+        mu, sig = mod.batch_predict(x, bs, verbose=False, maxiter_cg=50)
+        assert not mu.is_cuda and mu.shape == (n, 1) and sig.shape == (n, 1)
+        parts = [mod.predict(x[b], maxiter_cg=50) for b in zo.batch_indices(n, bs)]
+        assert torch.equal(mu, torch.cat([p[0] for p in parts])) and torch.equal(sig, torch.cat([p[1] for p in parts]))
+
+
+def test_misaligned_rows_take_the_scalar_path():
+    """Vectors whose rows are not 16-byte aligned (a row-offset view of an odd-length batch) must give the same matvec
+    and PCG results as aligned copies: the row kernels fall back from 16-byte chunks to element accesses."""
+    from hipgp_b200.plan import Plan
+    from hipgp_b200 import _lib as L, kernels as hk
+    for dtype, tol in ((torch.float32, 1e-6), (torch.float64, 1e-13)):
+        dims = (33, 35)
+        xg = [torch.linspace(0, 1, m, dtype=dtype, device=DEV) for m in dims]
+        plan = Plan(list(dims), dtype, DEV).set_first_row(hk.first_row(xg, hk.Matern(nu=2.5, dtype=dtype), (1.0, 0.2), jitter=1e-2))
+        M = dims[0] * dims[1]
+        big = torch.randn(4 * M + 1, dtype=dtype, device=DEV)
+        v_mis = big[1:1 + 3 * M].view(3, M)                 # data_ptr offset by one element
+        assert v_mis.data_ptr() % 16 != 0
+        v_al = v_mis.clone()
+        for mode in (L.MV_K, L.MV_CINV, L.MV_RT):
+            assert relerr(plan.matvec(mode, v_mis), plan.matvec(mode, v_al).cpu().numpy()) < tol
+        assert relerr(plan.pcg(v_mis, maxiter=15, tol=1e-12), plan.pcg(v_al, maxiter=15, tol=1e-12).cpu().numpy()) < 100 * tol

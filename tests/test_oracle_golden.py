@@ -179,3 +179,15 @@ def test_meanfield_step(dname, golden_dir):
     tol = TIGHT[dname] * 50
     assert abs(float(elbo) - float(g["elbo"])) <= tol * abs(float(g["elbo"]))
     assert relerr(g1.numpy(), g["g1"]) < tol and relerr(g2.numpy(), g["g2"]) < tol
+
+
+def test_batch_indices_cover_exactly_once():
+    """svi_gp.py:81-85 restated in the oracle and mirrored by ToeplitzInducingGP.batch_slices: bit-exact slices, every
+    index exactly once, ragged tail, batch larger than the data."""
+    from hipgp_b200.hipgp import ToeplitzInducingGP
+    for n, bs in ((10, 3), (9, 3), (1, 5), (100, 100), (101, 100), (7, 1), (1000, 256)):
+        ref = zo.batch_indices(n, bs)
+        got = ToeplitzInducingGP.batch_slices(n, bs)
+        assert [(s.start, s.stop) for s in ref] == [(s.start, s.stop) for s in got]
+        cover = np.concatenate([np.arange(n)[s] for s in got])
+        assert np.array_equal(cover, np.arange(n))
