@@ -229,7 +229,7 @@ __global__ void __launch_bounds__(NT, MINB) cols_fast_kernel(ColsParams<T> P) {
 
             // ---- last forward stage + spectrum + first inverse stage: RLAST neighbouring positions, in registers ----
             {
-#pragma unroll 1
+#pragma unroll 2
                 for (int it = tid; it < (Ln / RLAST) * NL; it += NT) {
                     const int lane = it % NL, bf = it / NL;
                     const bool ok = (long)lane * LPT < nvalid;
