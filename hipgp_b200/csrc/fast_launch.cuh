@@ -34,6 +34,13 @@ struct FastCfg {
 #endif
     static constexpr int LPT = LaneInfo<T>::LPT;
     static constexpr int S0 = Ln / (RLInfo<List>::count ? RLFirst<List>::value : 1);
+    // column pass: a single lane per tile would mean 16-byte row segments (half of every 32-byte sector wasted); when the
+    // doubled tile and its side buffer still fit one SM, take two lanes and 512 threads (one CTA per SM)
+    static constexpr int RLASTv = RLLast<List>::value;
+    static constexpr bool WIDEN = (NL == 1) && (RLInfo<List>::count > 1) && ((size_t)(Ln + Ln / RLASTv) * 2 * 24 <= 222 * 1024);
+    static constexpr int NLC = WIDEN ? 2 : NL;
+    static constexpr int NTC = WIDEN ? cfg_min(512, cfg_max(32, (BFN * 2 + 31) / 32 * 32)) : NT;
+    static constexpr int MINBC = WIDEN ? 1 : MINB;
 };
 
 static void launch_check(const char* what, int len, int nl, int nt, size_t smem, long grid) {
@@ -92,28 +99,28 @@ static int resident_ctas(K kernel, int nthreads, size_t smem) {
 template <class T, int LEN, int... Rs>
 static void launch_cols_fast_t(hipgp_plan* pl, ColsParams<T>& P, long n_outer, long B, cudaStream_t st) {
     using C = FastCfg<T, Rs...>;
-    using G = TileGeo<T, C::NL, Rs...>;
+    using G = TileGeo<T, C::NLC, Rs...>;
     static_assert(C::Ln == LEN, "radix list does not multiply to the length");
-    constexpr int TBL = C::NL * C::LPT;
+    constexpr int TBL = C::NLC * C::LPT;
     P.TB = TBL; P.TBP = TBL;
     if ((P.in_split_len && (P.mode != CM_INV || P.in_split_len % G::RLAST)) || (P.out_split_len && (P.mode != CM_FWD || P.out_split_len % G::RLAST)))
         throw Error("split row blocks are supported for forward-only outputs / inverse-only inputs, in multiples of the last radix");
     // side buffer (8 bytes per lane and padded position): next tile's input rows / this tile's real spectrum
-    const size_t side_bytes = G::NST > 1 ? (size_t)(C::Ln + C::Ln / G::RLAST) * C::NL * 8 : 0;
+    const size_t side_bytes = G::NST > 1 ? (size_t)(C::Ln + C::Ln / G::RLAST) * C::NLC * 8 : 0;
     static const char* env_ns = getenv("HIPGP_NO_STAGE");
     const bool use_side = G::NST > 1 && !env_ns;
     P.spec_stage = (use_side && P.mode == CM_FUSED && P.spec_kind == SPEC_REAL) ? 1 : 0;
-    P.in_stage = (use_side && P.mode != CM_INV && (size_t)P.n_in * C::NL * 16 <= side_bytes) ? 1 : 0;
+    P.in_stage = (use_side && P.mode != CM_INV && (size_t)P.n_in * C::NLC * 16 <= side_bytes) ? 1 : 0;
     const size_t smem = G::smem_bytes() + ((P.spec_stage || P.in_stage) ? side_bytes : 0);
     P.nx = (int)((P.inner + TBL - 1) / TBL); P.ny = (int)n_outer; P.nz = (int)B;
-    auto k = cols_fast_kernel<T, C::NL, C::NT, C::MINB, Rs...>;
+    auto k = cols_fast_kernel<T, C::NLC, C::NTC, C::MINBC, Rs...>;
     if (smem > 40 * 1024) HIPGP_SET_MAX_SMEM(k, smem);   // (static shared memory counts against the 48 KB default too)
     const long ntiles = (long)P.nx * P.ny * P.nz;
-    const long grid = std::min<long>(ntiles, resident_ctas(k, C::NT, smem));
+    const long grid = std::min<long>(ntiles, resident_ctas(k, C::NTC, smem));
     PROF_BEGIN(pl, 1, st);
-    HIPGP_LAUNCH(k, dim3((unsigned)grid), dim3(C::NT), smem, st, P);
+    HIPGP_LAUNCH(k, dim3((unsigned)grid), dim3(C::NTC), smem, st, P);
     PROF_END(pl, st);
-    launch_check("column pass", C::Ln, C::NL, C::NT, smem, grid);
+    launch_check("column pass", C::Ln, C::NLC, C::NTC, smem, grid);
     pl->launches++;
 }
 

@@ -23,6 +23,15 @@ for dtype in dts:
         for _ in range(10): plan.matvec(L.MV_K, v)
         pr = plan.profile_read(True); plan.profile(False)
         print(str(dtype)[6:], "B=%d" % B, "matvec=%.1fus" % (1e3 * tot_ms), " ".join("%s=%.1fus" % (k, 1e3 * a / max(n, 1)) for k, (a, n) in pr.items() if n), flush=True)
+    if "rt" in sys.argv:
+        v = torch.randn(16, m * m, dtype=dtype, device=dev)
+        for mode, nm in ((L.MV_RT, "RT"), (L.MV_R, "R")):
+            w = v if mode == L.MV_RT else plan.matvec(L.MV_RT, v)
+            for _ in range(2): plan.matvec(mode, w)
+            plan.profile(True); plan.profile_read(True)
+            for _ in range(5): plan.matvec(mode, w)
+            pr = plan.profile_read(True); plan.profile(False)
+            print(str(dtype)[6:], nm, "B=16", " ".join("%s=%.1fus" % (k, 1e3 * a / max(n, 1)) for k, (a, n) in pr.items() if n), "emb", plan.embedding(), flush=True)
     if "pcg" in sys.argv:
         v = torch.randn(16, m * m, dtype=dtype, device=dev)
         for _ in range(2): plan.pcg(v, maxiter=20, tol=1e-8)
