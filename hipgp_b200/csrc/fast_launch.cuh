@@ -34,6 +34,14 @@ struct FastCfg {
 #endif
     static constexpr int LPT = LaneInfo<T>::LPT;
     static constexpr int S0 = Ln / (RLInfo<List>::count ? RLFirst<List>::value : 1);
+    // row passes: their tiles are latency chains (stream in, FFT, split, stream out); smaller tiles = more independent
+    // chains per SM at the same number of warps
+#ifndef HIPGP_ROWS_NL_DIV
+#define HIPGP_ROWS_NL_DIV 4
+#endif
+    static constexpr int NLR = cfg_max(1, NL / HIPGP_ROWS_NL_DIV);
+    static constexpr int NTR = cfg_min(512, cfg_max(32, (BFN * NLR + 31) / 32 * 32));
+    static constexpr int MINBR = cfg_max(1, 512 / NTR);
     // column pass: a single lane per tile would mean 16-byte row segments (half of every 32-byte sector wasted); when the
     // doubled tile and its side buffer still fit one SM, take two lanes and 512 threads (one CTA per SM)
     static constexpr int RLASTv = RLLast<List>::value;
@@ -53,8 +61,8 @@ static void launch_check(const char* what, int len, int nl, int nt, size_t smem,
 template <class T, int... Rs>
 static void launch_rows_fast_t(hipgp_plan* pl, bool inverse, RowsParams<T>& P, cudaStream_t st) {
     using C = FastCfg<T, Rs...>;
-    using G = TileGeo<T, C::NL, Rs...>;
-    constexpr int NROW = C::NL * C::LPT;
+    using G = TileGeo<T, C::NLR, Rs...>;
+    constexpr int NROW = C::NLR * C::LPT;
     static_assert(NROW <= 32, "per-row scalars are held in 32-entry shared arrays");
     P.RB = NROW; P.RBP = NROW;
     {   // the kernels take the pair / quad structure of the digit-reversed order as compile-time facts
@@ -68,16 +76,16 @@ static void launch_rows_fast_t(hipgp_plan* pl, bool inverse, RowsParams<T>& P, c
     dim3 grid((unsigned)((P.total_rows + NROW - 1) / NROW));
     PROF_BEGIN(pl, inverse ? 2 : 0, st);
     if (inverse) {
-        auto k = rows_inv_fast_kernel<T, C::NL, C::NT, C::MINB, Rs...>;
+        auto k = rows_inv_fast_kernel<T, C::NLR, C::NTR, C::MINBR, Rs...>;
         if (smem > 40 * 1024) HIPGP_SET_MAX_SMEM(k, smem);   // (static shared memory counts against the 48 KB default too)
-        HIPGP_LAUNCH(k, grid, dim3(C::NT), smem, st, P);
+        HIPGP_LAUNCH(k, grid, dim3(C::NTR), smem, st, P);
     } else {
-        auto k = rows_fwd_fast_kernel<T, C::NL, C::NT, C::MINB, Rs...>;
+        auto k = rows_fwd_fast_kernel<T, C::NLR, C::NTR, C::MINBR, Rs...>;
         if (smem > 40 * 1024) HIPGP_SET_MAX_SMEM(k, smem);   // (static shared memory counts against the 48 KB default too)
-        HIPGP_LAUNCH(k, grid, dim3(C::NT), smem, st, P);
+        HIPGP_LAUNCH(k, grid, dim3(C::NTR), smem, st, P);
     }
     PROF_END(pl, st);
-    launch_check("row pass", C::Ln, C::NL, C::NT, smem, (long)grid.x);
+    launch_check("row pass", C::Ln, C::NLR, C::NTR, smem, (long)grid.x);
     pl->launches++;
 }
 

@@ -4,7 +4,7 @@ set -e
 SUF=$1; shift
 cd /root/repo/hipgp_b200/csrc
 mkdir -p variants build/v_$SUF
-FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -DHIPGP_DEV_SMALL $@"
+FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC $@"
 nvcc $FLAGS -c plan.cu -o build/v_$SUF/plan.o &
 for g in 0 1 4 5; do nvcc $FLAGS -DHIPGP_INST_GROUP=$g -c fast_inst.cu -o build/v_$SUF/fi_$g.o & done
 nvcc $FLAGS -DHIPGP_INST_GROUP=2 -c fast_inst.cu -o build/v_$SUF/fi_2.o &
