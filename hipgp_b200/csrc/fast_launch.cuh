@@ -46,9 +46,13 @@ struct FastCfg {
     // doubled tile and its side buffer still fit one SM, take two lanes and 512 threads (one CTA per SM)
     static constexpr int RLASTv = RLLast<List>::value;
     static constexpr bool WIDEN = (NL == 1) && (RLInfo<List>::count > 1) && ((size_t)(Ln + Ln / RLASTv) * 2 * 24 <= 222 * 1024);
-    static constexpr int NLC = WIDEN ? 2 : NL;
-    static constexpr int NTC = WIDEN ? cfg_min(512, cfg_max(32, (BFN * 2 + 31) / 32 * 32)) : NT;
-    static constexpr int MINBC = WIDEN ? 1 : MINB;
+    // ... and two-lane tiles are widened to four lanes (512 threads, one CTA per SM): the per-butterfly twiddle loads are
+    // shared by twice as many lines (measured at 2048 points: 183 -> 170 us; wider tiles than that lose again)
+    static constexpr int CMULF = 2;
+    static constexpr bool CMUL = !WIDEN && NL == 2 && ((size_t)(Ln + Ln / RLASTv) * NL * CMULF * 24 <= 222 * 1024) && BFN * NL * CMULF <= 512;
+    static constexpr int NLC = WIDEN ? 2 : (CMUL ? NL * CMULF : NL);
+    static constexpr int NTC = (WIDEN || CMUL) ? cfg_min(512, cfg_max(32, (BFN * NLC + 31) / 32 * 32)) : NT;
+    static constexpr int MINBC = (WIDEN || CMUL) ? cfg_max(1, 512 / NTC) : MINB;
 };
 
 static void launch_check(const char* what, int len, int nl, int nt, size_t smem, long grid) {
