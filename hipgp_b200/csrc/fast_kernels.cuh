@@ -91,8 +91,9 @@ __global__ void __launch_bounds__(NT, MINB) cols_fast_kernel(ColsParams<T> P) {
     const size_t spitch = P.spec_pitch ? (size_t)P.spec_pitch : (size_t)P.pitch;
     const long ntiles = (long)P.nx * P.ny * P.nz;
     auto tile_origin = [&](long t, long& c0, size_t& ioff, size_t& ooff) {
-        const long bx = t % P.nx, r = t / P.nx;
-        const long by = r % P.ny, bz = r / P.ny;
+        long bx, by, bz;
+        if (P.batch_fastest) { bz = t % P.nz; const long r = t / P.nz; bx = r % P.nx; by = r / P.nx; }   // spectrum tile reused by neighbours
+        else { bx = t % P.nx; const long r = t / P.nx; by = r % P.ny; bz = r / P.ny; }
         c0 = bx * TBL;
         ioff = (size_t)by * P.in_ostride + (size_t)bz * P.in_bstride + c0;
         ooff = (size_t)by * P.out_ostride + (size_t)bz * P.out_bstride + c0;
@@ -820,6 +821,16 @@ __global__ void __launch_bounds__(NT, MINB) rows_inv_fast_kernel(RowsParams<T> P
                             stv_stream(P.out + off + (size_t)c * CH, y);
                         }
                     }
+                }
+            } else if (sizeof(T) == 4 && (n & 1) == 0 && P.vec_ok) {
+                // 8-byte chunks: rows of even length that are not a multiple of 4 (N = 2m - 2 outputs of R^T)
+                for (int c = ln; c < n / 2; c += TW) {
+                    const cplx<T> y = *reinterpret_cast<const cplx<T>*>(srow + 2 * c);
+                    if (want_dot) {
+                        const cplx<T> ov = ld_stream(reinterpret_cast<const cplx<T>*>((const T*)P.v0 + off + 2 * c));
+                        acc += (double)(y.x * ov.x) + (double)(y.y * ov.y);
+                    }
+                    st_stream(reinterpret_cast<cplx<T>*>(P.out + off + 2 * c), y);
                 }
             } else {
                 for (int i = ln; i < n; i += TW) {

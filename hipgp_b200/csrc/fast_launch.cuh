@@ -125,6 +125,13 @@ static void launch_cols_fast_t(hipgp_plan* pl, ColsParams<T>& P, long n_outer, l
     P.in_stage = (use_side && P.mode != CM_INV && (size_t)P.n_in * C::NLC * 16 <= side_bytes) ? 1 : 0;
     const size_t smem = G::smem_bytes() + ((P.spec_stage || P.in_stage) ? side_bytes : 0);
     P.nx = (int)((P.inner + TBL - 1) / TBL); P.ny = (int)n_outer; P.nz = (int)B;
+    // tile order: lines fastest keeps neighbouring CTAs on neighbouring 32/64-byte row segments (shared DRAM bursts); but a
+    // spectrum that does not stay in L2 would then be re-read from DRAM for every right-hand side, so for big spectra and
+    // tiles that are a full 128-byte segment wide the batch index runs fastest instead
+    {
+        const size_t spec_bytes = (size_t)G::Ln * (size_t)P.inner * (P.spec_kind == SPEC_REAL ? sizeof(T) : 2 * sizeof(T));
+        P.batch_fastest = (P.mode == CM_FUSED && B > 1 && spec_bytes > ((size_t)48 << 20) && (size_t)TBL * sizeof(cplx<T>) >= 128) ? 1 : 0;
+    }
     auto k = cols_fast_kernel<T, C::NLC, C::NTC, C::MINBC, Rs...>;
     if (smem > 40 * 1024) HIPGP_SET_MAX_SMEM(k, smem);   // (static shared memory counts against the 48 KB default too)
     const long ntiles = (long)P.nx * P.ny * P.nz;
