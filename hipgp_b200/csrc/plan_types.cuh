@@ -56,9 +56,9 @@ struct DevBuf {
 #else
 #define HIPGP_FAST_LIST_G0(X) X(2048, 16, 8, 16) X(8192, 16, 8, 8, 8)
 #define HIPGP_FAST_LIST_G1(X) X(4096, 16, 16, 16) X(16, 16) X(8, 8) X(4, 4)
-#define HIPGP_FAST_LIST_G2(X) X(1024, 8, 8, 16) X(512, 8, 8, 8) X(256, 16, 16) X(128, 16, 8)
-#define HIPGP_FAST_LIST_G3(X) X(3072, 3, 16, 8, 8) X(1536, 3, 8, 8, 8) X(768, 3, 16, 16) X(64, 8, 8) X(32, 8, 4)
-#define HIPGP_FAST_LIST_G4(X) X(640, 5, 16, 8) X(320, 5, 8, 8) X(384, 3, 16, 8) X(192, 3, 8, 8) X(96, 3, 8, 4)
+#define HIPGP_FAST_LIST_G2(X) X(1024, 8, 8, 16) X(512, 4, 8, 16) X(256, 16, 16) X(128, 8, 16)
+#define HIPGP_FAST_LIST_G3(X) X(3072, 3, 16, 8, 8) X(1536, 3, 8, 8, 8) X(768, 3, 16, 16) X(64, 4, 16) X(32, 8, 4)
+#define HIPGP_FAST_LIST_G4(X) X(640, 5, 8, 16) X(320, 5, 4, 16) X(384, 3, 8, 16) X(192, 3, 4, 16) X(96, 3, 8, 4)
 #endif
 #define HIPGP_FAST_LIST(X) HIPGP_FAST_LIST_G0(X) HIPGP_FAST_LIST_G1(X) HIPGP_FAST_LIST_G2(X) HIPGP_FAST_LIST_G3(X) HIPGP_FAST_LIST_G4(X)
 
