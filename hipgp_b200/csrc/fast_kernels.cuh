@@ -350,9 +350,21 @@ __global__ void __launch_bounds__(NT, MINB) rows_fwd_fast_kernel(RowsParams<T> P
     //      row goes to the side buffer (row-major, SROW reals per row, zero-filled behind n); deterministic row sums ----
     const int SROW = (n + 3) & ~3;
     T* side = reinterpret_cast<T*>(smem_raw + G::smem_bytes());
-    {
+    bool streamed = false;
+#ifndef HIPGP_EMU
+    // plain rows: the tile's rows are one contiguous block of global memory -> a single bulk-asynchronous (TMA) copy
+    if (mode == RF_PLAIN && P.tma_ok && P.vec16_ok && SROW == n) {
+        __shared__ __align__(8) unsigned long long s_mbar;
+        const unsigned bytes = (unsigned)((size_t)nl * n * sizeof(T));
+        if (tid == 0) { mbar_init(&s_mbar, 1); fence_proxy_async(); }
+        __syncthreads();
+        if (tid == 0) { mbar_arrive_expect_tx(&s_mbar, bytes); bulk_g2s(side, P.in + (size_t)g0 * n, bytes, &s_mbar); }
+        mbar_wait(&s_mbar, 0);
+        streamed = true;
+    }
+#endif
+    if (!streamed) {
         constexpr int CH = 16 / (int)sizeof(T);
-        // WPR warps share a row when there are more warps than rows; a row's chunks are dealt out over its TW lanes
         // Teams: WPR warps share a row when there are more warps than rows; short rows are dealt to sub-warp teams of
         // `tws` lanes so that all 32 lanes of a warp stream.  TW = lanes per row, `rstep` = rows per sweep of the CTA.
         constexpr int NW = NT / 32, WPR = NW > NROW ? NW / NROW : 1;
@@ -781,7 +793,19 @@ __global__ void __launch_bounds__(NT, MINB) rows_inv_fast_kernel(RowsParams<T> P
             }
         }
     }
+#ifndef HIPGP_EMU
+    const bool tma_out = !want_dot && P.tma_ok && P.vec16_ok && SROW == n;
+    if (tma_out) fence_proxy_async();        // this thread's shared-memory writes become visible to the async proxy
+#else
+    const bool tma_out = false;
+#endif
     __syncthreads();
+#ifndef HIPGP_EMU
+    if (tma_out) {      // plain rows: the tile's output rows are one contiguous block -> a single bulk-asynchronous store
+        if (tid == 0) bulk_s2g(P.out + (size_t)g0 * n, side, (unsigned)((size_t)nl * n * sizeof(T)));
+        return;
+    }
+#endif
     // ---- streaming phase: one warp per row, 16-byte accesses: store (crop) and the fused dot product ----
     {
         constexpr int CH = 16 / (int)sizeof(T);

@@ -77,6 +77,8 @@ static void launch_rows_fast_t(hipgp_plan* pl, bool inverse, RowsParams<T>& P, c
     // the tile, then the side buffer: the tile's real rows, row-major
     const size_t smem = G::smem_bytes() + sizeof(T) * (size_t)((P.n_real + 3) & ~3) * NROW;
     if (smem > 227 * 1024) throw Error("row pass: rows too long for the shared-memory side buffer");
+    static const char* env_nt = getenv("HIPGP_NO_TMA");
+    P.tma_ok = env_nt ? 0 : 1;
     dim3 grid((unsigned)((P.total_rows + NROW - 1) / NROW));
     PROF_BEGIN(pl, inverse ? 2 : 0, st);
     if (inverse) {

@@ -225,6 +225,37 @@ __device__ __forceinline__ void cp_async_wait_all() {
 #endif
 }
 
+// ---- bulk asynchronous copies (TMA, 1-D): one instruction moves a whole contiguous block of rows between global and
+// shared memory; completion of a load is signalled on an mbarrier (transaction bytes), of a store by its bulk group ----
+#ifndef HIPGP_EMU
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\t"
+        "HIPGP_MBAR_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, 0x989680;\n\t"
+        "@P1 bra HIPGP_MBAR_DONE;\n\t"
+        "bra HIPGP_MBAR_WAIT;\n\t"
+        "HIPGP_MBAR_DONE:\n\t}" ::"r"(a), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* gmem_dst, const void* smem_src, unsigned bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"((unsigned)__cvta_generic_to_shared(smem_src)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+#endif
+
 // ---------------------------------------------------------------------------------------------------------
 // butterflies on lanes:  v[q] = sum_r v[r] w_R^{qr},  w_R = exp(-+ 2 pi i / R)
 template <bool INV, class E> __device__ __forceinline__ void lb2(E* v) { const E a = v[0], b = v[1]; v[0] = a + b; v[1] = a - b; }
