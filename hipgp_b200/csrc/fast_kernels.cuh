@@ -6,17 +6,18 @@
 //     f32x2 arithmetic across the two lines of a lane, all butterfly legs at [base + immediate];
 //   * the frequency workspace is kept in LANE layout (lane_fft.cuh), so the column pass moves lanes between global
 //     memory and registers with plain 16-byte accesses;
-//   * the first forward stage reads its operands straight from global memory (zero padding = skipped loads and a
-//     pruned butterfly when the upper half of the inputs is padding; PCG vector updates fused into the row loads) and
-//     the last inverse stage writes straight to global memory (crop = skipped stores, dot products fused);
-//   * column pass: last forward stage, spectrum multiply and first inverse stage run back to back in registers; the
-//     spectrum tile is fetched with cp.async into shared memory at kernel start, so its latency hides behind the
-//     forward stages;
-//   * row passes: the r2c split / c2r merge works on QUADS -- two neighbouring bins and their two mirror bins -- so
-//     one thread turns four shared-memory lanes into 16-byte global accesses (the few bins of digit group 0, whose
-//     mirrors are irregular, go through a scalar path);
-//   * tiles are small (64-110 KB) so that two CTAs are resident per SM and one CTA's global traffic overlaps the
-//     other's butterflies.
+//   * COLUMN pass: persistent CTAs; the first forward stage reads its operands from a shared-memory SIDE buffer that was
+//     filled with cp.async while the previous tile was in its inverse stages (zero padding = skipped reads and a pruned
+//     butterfly); the same buffer then receives the tile's real spectrum behind the forward stages; last forward stage,
+//     spectrum multiply and first inverse stage run back to back in registers; the last inverse stage writes straight
+//     to global memory (crop = skipped stores).  Tiles are wide (4 lanes, 512 threads at 2048 points) because the
+//     per-butterfly twiddle loads are shared by all lanes of a tile;
+//   * ROW passes: small tiles on purpose (2 fp32 rows, 8 CTAs per SM at 1024 points): a row tile is a latency chain.
+//     Vectors stream in 16-byte chunks, one row per (sub-)warp team, with the PCG vector updates fused and deterministic
+//     row sums; PLAIN row blocks move with one bulk-asynchronous TMA copy (cp.async.bulk + mbarrier); the r2c split /
+//     c2r merge works on QUADS -- two neighbouring bins and their two mirror bins -- so one thread turns four
+//     shared-memory lanes into 16-byte global accesses, all loads of a thread issued up front and branch-free (the few
+//     bins of digit group 0, whose mirrors are irregular, go through a scalar path).
 #pragma once
 #include "lane_fft.cuh"
 
@@ -35,17 +36,6 @@ template <class T> __device__ __forceinline__ void st2(T* p, bool vec, T a, T b,
 __device__ __forceinline__ double team_sum(double v, int tw) {
     for (int o = tw >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
-}
-
-// deterministic per-row reduction of per-thread partials in smem scratch: warp `row` sums scratch[row*NI .. +NI)
-__device__ __forceinline__ void rows_reduce_partials(const double* scratch, int NI, int nl, long g0, double* partial, int tid, int nthreads) {
-    const int warp = tid >> 5, lane = tid & 31, nwarps = nthreads >> 5;
-    for (int row = warp; row < nl; row += nwarps) {
-        double a = 0.0;
-        for (int i = lane; i < NI; i += 32) a += scratch[row * NI + i];
-        a = warp_sum(a);
-        if (lane == 0) partial[g0 + row] = a;
-    }
 }
 
 // spectrum factor(s) of one lane, read from global memory: `idx` = index of the lane's first line in the spectrum
@@ -320,7 +310,6 @@ __global__ void __launch_bounds__(NT, MINB) rows_fwd_fast_kernel(RowsParams<T> P
     constexpr int LEG0 = G::leg(NST > 1 ? S0 : 1);
     HIPGP_DYN_SMEM(smem_raw);
     Lane<T>* s = reinterpret_cast<Lane<T>*>(smem_raw);
-    double* scratch = reinterpret_cast<double*>(smem_raw + G::smem_bytes());
     const int tid = threadIdx.x;
     if (P.mode != RF_PLAIN && P.st.flags[0]) return;
     const long g0 = (long)blockIdx.x * NROW;
@@ -634,7 +623,6 @@ __global__ void __launch_bounds__(NT, MINB) rows_inv_fast_kernel(RowsParams<T> P
     constexpr int LEG0 = G::leg(NST > 1 ? S0 : 1);
     HIPGP_DYN_SMEM(smem_raw);
     Lane<T>* s = reinterpret_cast<Lane<T>*>(smem_raw);
-    double* scratch = reinterpret_cast<double*>(smem_raw + G::smem_bytes());
     const int tid = threadIdx.x;
     if (P.mode != RI_PLAIN && P.st.flags[0]) return;
     const long g0 = (long)blockIdx.x * NROW;

@@ -5,19 +5,14 @@
 
 namespace hipgp {
 
-#ifndef HIPGP_NL_MUL      /* developer knobs: scale the lanes per CTA (and the threads with them) */
-#define HIPGP_NL_MUL 1
-#endif
-#ifndef HIPGP_NL_DIV
-#define HIPGP_NL_DIV 1
-#endif
-
 constexpr int cfg_min(int a, int b) { return a < b ? a : b; }
 constexpr int cfg_max(int a, int b) { return a > b ? a : b; }
 constexpr int pow2_floor(int x) { return x <= 1 ? 1 : 2 * pow2_floor(x / 2); }
 
-// Tile configuration of one (dtype, radix list): NL lanes per CTA so that the widest stage gives every one of ~256
-// threads one butterfly and the tile stays near 64 KB (two to three CTAs per SM); NT threads; register cap 128.
+// Tile configuration of one (dtype, radix list).  Base rule: NL lanes per CTA so that the widest stage gives every one of
+// ~256 threads one butterfly and the tile stays near 64 KB; register cap 128 (MINB = CTAs per SM by threads).  The row
+// passes then take a QUARTER of that (NLR: many small latency chains per SM), the column pass widens one- and two-lane
+// tiles (NLC: wider global segments, shared twiddle loads).  All of it is measured, see profiles/README.md.
 template <class T, int... Rs>
 struct FastCfg {
     using List = RL<Rs...>;
@@ -25,21 +20,14 @@ struct FastCfg {
     static constexpr int RMAX = RLMax<List>::value;
     static constexpr int BFN = Ln / RMAX;                       // butterflies per line in the widest stage
     static constexpr int NL0 = pow2_floor(cfg_max(1, cfg_min(256 / cfg_max(BFN, 1), 4096 / Ln)));
-    static constexpr int NL = cfg_max(1, cfg_min(16, NL0 * HIPGP_NL_MUL / HIPGP_NL_DIV));
+    static constexpr int NL = cfg_max(1, cfg_min(16, NL0));
     static constexpr int NT = cfg_min(512, cfg_max(32, (BFN * NL + 31) / 32 * 32));
-#ifdef HIPGP_MINB
-    static constexpr int MINB = HIPGP_MINB;
-#else
     static constexpr int MINB = cfg_max(1, 512 / NT);
-#endif
     static constexpr int LPT = LaneInfo<T>::LPT;
     static constexpr int S0 = Ln / (RLInfo<List>::count ? RLFirst<List>::value : 1);
     // row passes: their tiles are latency chains (stream in, FFT, split, stream out); smaller tiles = more independent
     // chains per SM at the same number of warps
-#ifndef HIPGP_ROWS_NL_DIV
-#define HIPGP_ROWS_NL_DIV 4
-#endif
-    static constexpr int NLR = cfg_max(1, NL / HIPGP_ROWS_NL_DIV);
+    static constexpr int NLR = cfg_max(1, NL / 4);
     static constexpr int NTR = cfg_min(512, cfg_max(32, (BFN * NLR + 31) / 32 * 32));
     static constexpr int MINBR = cfg_max(1, 512 / NTR);
     // column pass: a single lane per tile would mean 16-byte row segments (half of every 32-byte sector wasted); when the
