@@ -126,7 +126,8 @@ struct RowsParams {
     int mode, dot_kind, do_fft;
     int vec_ok;           // all row pointers are aligned for 2-element vector access
     int vec16_ok;         // ... and for 16-byte access (specialised kernels stream rows in 16-byte chunks)
-    int tma_ok;           // specialised kernels: plain row blocks move with 1-D bulk-asynchronous (TMA) copies
+    int tma_ok;           // specialised kernels: row blocks move with 1-D bulk-asynchronous (TMA) copies
+    int tma_op;           // ... including the operands of a fused PCG update (they land in the idle tile buffer, which is big enough)
     const void* spec; int spec_kind;   // rows_inv only (1-D grids)
     PcgDev st;
 };

@@ -341,14 +341,101 @@ __global__ void __launch_bounds__(NT, MINB) rows_fwd_fast_kernel(RowsParams<T> P
     T* side = reinterpret_cast<T*>(smem_raw + G::smem_bytes());
     bool streamed = false;
 #ifndef HIPGP_EMU
-    // plain rows: the tile's rows are one contiguous block of global memory -> a single bulk-asynchronous (TMA) copy
-    if (mode == RF_PLAIN && P.tma_ok && P.vec16_ok && SROW == n) {
+    // Bulk-asynchronous (TMA) streaming: the tile's rows are one contiguous block of every vector.  The FFT input lands in
+    // the side buffer and the other operands of a fused PCG update in the (still idle) tile buffer -- one instruction per
+    // vector, no register staging; the update then runs shared memory -> shared memory and the updated vector leaves with
+    // one bulk store.  Only x of the x/r update (read AND written) goes through ordinary 16-byte accesses.
+    bool bulk_store_pending = false;
+    if (P.tma_ok && P.vec16_ok && SROW == n && (mode == RF_PLAIN || mode == RF_SELFDOT || P.tma_op)) {
+        constexpr int CH = 16 / (int)sizeof(T);
         __shared__ __align__(8) unsigned long long s_mbar;
         const unsigned bytes = (unsigned)((size_t)nl * n * sizeof(T));
+        const size_t goff = (size_t)g0 * n;
+        T* bufA = reinterpret_cast<T*>(smem_raw);                  // operand landing zones inside the tile buffer
+        T* bufB = bufA + (size_t)NROW * SROW;
+        const bool two = mode == RF_PUPDATE && !first_it, three = mode == RF_XRUPDATE;
         if (tid == 0) { mbar_init(&s_mbar, 1); fence_proxy_async(); }
         __syncthreads();
-        if (tid == 0) { mbar_arrive_expect_tx(&s_mbar, bytes); bulk_g2s(side, P.in + (size_t)g0 * n, bytes, &s_mbar); }
+        if (tid == 0) {
+            mbar_arrive_expect_tx(&s_mbar, bytes * (three ? 3u : (two ? 2u : 1u)));
+            bulk_g2s(side, P.in + goff, bytes, &s_mbar);                                   // in / z / Ap
+            if (two) bulk_g2s(bufA, (const T*)P.v0 + goff, bytes, &s_mbar);                // p
+            if (three) { bulk_g2s(bufA, (const T*)P.v0 + goff, bytes, &s_mbar); bulk_g2s(bufB, P.v2 + goff, bytes, &s_mbar); }   // r, p
+        }
+        // row teams (same dealing as the register path below)
+        constexpr int NW = NT / 32, WPR = NW > NROW ? NW / NROW : 1;
+        constexpr int tws = WPR > 1 ? 32 : (H / CH >= 32 ? 32 : (H / CH >= 16 ? 16 : (H / CH >= 8 ? 8 : 4)));
+        constexpr int rpw = 32 / tws, TW = WPR > 1 ? 32 * WPR : tws, rstep = WPR > 1 ? NW / WPR : NW * rpw;
+        const int warp = tid >> 5, l32 = tid & 31;
+        const int ln = WPR > 1 ? l32 + 32 * (warp % WPR) : l32 % tws;
+        const int nch = n / CH;
         mbar_wait(&s_mbar, 0);
+        if (mode != RF_PLAIN && !(mode == RF_PUPDATE && first_it)) {
+            for (int rbase = WPR > 1 ? warp / WPR : warp * rpw; rbase < nl; rbase += rstep) {
+                const int row = rbase + (WPR > 1 ? 0 : l32 / tws);
+                const bool ractive = row < nl;
+                double acc = 0.0;
+                if (ractive) {
+                    T* srow = side + (size_t)row * SROW;
+                    const T* arow = bufA + (size_t)row * SROW;
+                    const T* brow = bufB + (size_t)row * SROW;
+                    const size_t off = goff + (size_t)row * n;
+                    const T coef = s_coef[row];
+                    if (three) {
+                        constexpr int BS = 4;                   // x: ordinary loads, a batch in flight
+                        for (int cb = ln; cb < nch; cb += TW * BS) {
+                            Vec16<T> xv[BS];
+#pragma unroll
+                            for (int k = 0; k < BS; ++k) { const int c = cb + TW * k; if (c < nch) xv[k] = ldv_stream((const T*)P.v1 + off + (size_t)c * CH); }
+#pragma unroll
+                            for (int k = 0; k < BS; ++k) {
+                                const int c = cb + TW * k;
+                                if (c < nch) {
+                                    Vec16<T> q = *reinterpret_cast<const Vec16<T>*>(srow + c * CH);          // Ap
+                                    const Vec16<T> rv = *reinterpret_cast<const Vec16<T>*>(arow + c * CH);   // r
+                                    const Vec16<T> pv = *reinterpret_cast<const Vec16<T>*>(brow + c * CH);   // p
+#pragma unroll
+                                    for (int e = 0; e < CH; ++e) { xv[k].v[e] = xv[k].v[e] + coef * pv.v[e]; q.v[e] = rv.v[e] - coef * q.v[e]; acc += (double)(q.v[e] * q.v[e]); }
+                                    stv_stream(P.v1 + off + (size_t)c * CH, xv[k]);
+                                    *reinterpret_cast<Vec16<T>*>(srow + c * CH) = q;                          // r_new = FFT input
+                                }
+                            }
+                        }
+                    } else if (two) {
+                        for (int c = ln; c < nch; c += TW) {
+                            Vec16<T> z = *reinterpret_cast<const Vec16<T>*>(srow + c * CH);
+                            const Vec16<T> pv = *reinterpret_cast<const Vec16<T>*>(arow + c * CH);
+#pragma unroll
+                            for (int e = 0; e < CH; ++e) z.v[e] = z.v[e] + coef * pv.v[e];
+                            *reinterpret_cast<Vec16<T>*>(srow + c * CH) = z;                                  // p_new = FFT input
+                        }
+                    } else {        // RF_SELFDOT
+                        for (int c = ln; c < nch; c += TW) {
+                            const Vec16<T> z = *reinterpret_cast<const Vec16<T>*>(srow + c * CH);
+#pragma unroll
+                            for (int e = 0; e < CH; ++e) acc += (double)(z.v[e] * z.v[e]);
+                        }
+                    }
+                }
+                if (want_dot) {
+                    acc = team_sum(acc, WPR > 1 ? 32 : tws);
+                    if (ractive && (WPR > 1 ? l32 == 0 : ln == 0)) s_part[row * WPR + warp % WPR] = acc;
+                }
+            }
+        }
+        if (mode == RF_PUPDATE || mode == RF_XRUPDATE) {       // the updated vector (p or r) = the side buffer -> global
+            fence_proxy_async();
+            __syncthreads();
+            if (tid == 0) {
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(P.v0 + goff), "r"((unsigned)__cvta_generic_to_shared(side)), "r"(bytes) : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+            bulk_store_pending = true;
+        }
+        if (want_dot) {
+            __syncthreads();
+            if (tid < nl) { double a = 0.0; for (int k = 0; k < WPR; ++k) a += s_part[tid * WPR + k]; P.st.partial[g0 + tid] = a; }
+        }
         streamed = true;
     }
 #endif
@@ -614,6 +701,9 @@ __global__ void __launch_bounds__(NT, MINB) rows_fwd_fast_kernel(RowsParams<T> P
             }
         }
     }
+#ifndef HIPGP_EMU
+    if (bulk_store_pending && tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the side buffer has been read
+#endif
 }
 
 template <class T, int NL, int NT, int MINB, int R0, int... Rs>

@@ -66,7 +66,10 @@ static void launch_rows_fast_t(hipgp_plan* pl, bool inverse, RowsParams<T>& P, c
     const size_t smem = G::smem_bytes() + sizeof(T) * (size_t)((P.n_real + 3) & ~3) * NROW;
     if (smem > 227 * 1024) throw Error("row pass: rows too long for the shared-memory side buffer");
     static const char* env_nt = getenv("HIPGP_NO_TMA");
+    static const char* env_nf = getenv("HIPGP_NO_TMA_FUSED");
     P.tma_ok = env_nt ? 0 : 1;
+    // operands of a fused update land in the tile buffer: two row blocks must fit in it
+    P.tma_op = (!env_nf && !inverse && 2 * sizeof(T) * (size_t)((P.n_real + 3) & ~3) * NROW <= G::smem_bytes()) ? 1 : 0;
     dim3 grid((unsigned)((P.total_rows + NROW - 1) / NROW));
     PROF_BEGIN(pl, inverse ? 2 : 0, st);
     if (inverse) {
