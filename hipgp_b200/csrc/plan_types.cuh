@@ -50,8 +50,8 @@ struct DevBuf {
 #endif
 #define HIPGP_FAST_LIST_G0(X) X(2048, HIPGP_EXP_R2048)
 #define HIPGP_FAST_LIST_G1(X) X(16, 16)
-#define HIPGP_FAST_LIST_G2(X) X(1024, HIPGP_EXP_R1024) X(128, 16, 8)
-#define HIPGP_FAST_LIST_G3(X) X(64, 8, 8) X(32, 8, 4)
+#define HIPGP_FAST_LIST_G2(X) X(1024, HIPGP_EXP_R1024) X(128, 8, 16)
+#define HIPGP_FAST_LIST_G3(X) X(64, 4, 16) X(32, 8, 4)
 #define HIPGP_FAST_LIST_G4(X)
 #else
 #define HIPGP_FAST_LIST_G0(X) X(2048, 16, 8, 16) X(8192, 16, 8, 8, 8)
