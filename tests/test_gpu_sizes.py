@@ -12,7 +12,7 @@ import torch
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 CASES = [((300,), 3), ((1000,), 2), ((150, 130), 3), ((96, 200), 2), ((300, 300), 2), ((48, 40, 36), 2), ((128, 128, 64), 2),
-         ((20, 257, 33), 1)]
+         ((20, 257, 33), 1), ((1000, 1000), 2)]       # the last one is BASELINE config 2 at full size
 
 
 def relerr(a, b):
