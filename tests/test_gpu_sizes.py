@@ -88,3 +88,25 @@ def test_pcg_medium_against_dense_residual():
     assert rn.max() < 1e-8
     # (the solver reports the RECURRENCE residual, cg.py:67-69; it drifts from the true one by rounding only)
     assert np.allclose(rn, np.asarray(info["resid"]), rtol=5e-2, atol=1e-12)
+
+
+def test_pcg_iterates_at_full_size_vs_oracle():
+    """BASELINE config 2 at FULL size (10^6-point grid, fp64): after the same number of PCG iterations (8; the case does
+    not converge within any affordable count on the CPU) the device iterate must equal the CPU oracle's, the callback
+    counts must agree (cg.py:70-78) and so must the recurrence residual."""
+    from hipgp_b200.plan import Plan
+    from oracle import ziggy_oracle as zo
+    m = 1000
+    g1 = torch.linspace(0, 4, m, dtype=torch.float64); g2 = torch.linspace(-2, 2, m, dtype=torch.float64)
+    ora = zo.OracleToeplitz([g1, g2], lambda x, y: zo.matern(x, y, 1.0, 0.01, 2.5), jitter_val=1e-3)
+    torch.manual_seed(42)
+    v = torch.randn(1, m * m, dtype=torch.float64)
+    n_ref = [0]
+    x_ref = ora.solve(v, do_precond=True, maxiter=8, tol=1e-12, callback=lambda n, x: n_ref.__setitem__(0, n_ref[0] + 1))
+    plan = Plan([m, m], torch.float64, DEV).set_first_row(ora.column.to(DEV))
+    n_dev = [0]
+    x, info = plan.pcg(v.to(DEV), maxiter=8, tol=1e-12, callback=lambda n, xx: n_dev.__setitem__(0, n_dev[0] + 1), return_info=True)
+    assert n_dev[0] == n_ref[0] == 8
+    assert relerr(x.cpu().numpy(), x_ref.numpy()) < 1e-9
+    r = v - ora.matmul_K(x_ref)
+    assert abs(float(info["resid"][0]) - float(r.norm())) <= 1e-6 * float(r.norm())
