@@ -430,7 +430,9 @@ static void slab_stage3(hipgp_plan* pl, const void* recv_buf, void* out_slab, cu
 template <class T>
 static void matvec(hipgp_plan* pl, int mode, const void* in, void* out, long B, cudaStream_t s) {
     if (!pl->have_spec) throw Error("plan has no spectrum: call hipgp_plan_set_first_row first");
-    if (B <= 0) return;
+    if (B < 0) throw Error("negative number of right-hand sides");
+    if (B == 0) return;
+    if (!in || !out) throw Error("null vector pointer");
     RowsFusion ff, fi;
     ff.mode = RF_PLAIN; ff.in = in; fi.mode = RI_PLAIN; fi.out = out;
     const bool wide = (mode == HIPGP_MV_RT || mode == HIPGP_MV_R);
@@ -498,6 +500,7 @@ template <class T>
 static void pcg_begin(hipgp_plan* pl, const void* b, void* x, long B, double tol, bool precond, cudaStream_t s) {
     if (!pl->have_spec) throw Error("plan has no spectrum: call hipgp_plan_set_first_row first");
     if (B <= 0) throw Error("pcg needs at least one right-hand side");
+    if (!b || !x) throw Error("null vector pointer");
     const long M = pl->M;
     PcgDev st = pcg_state<T>(pl, B, tol, !precond);
     if (!pl->pinned) CK(cudaMallocHost(&pl->pinned, 64));
@@ -575,7 +578,8 @@ static void pcg(hipgp_plan* pl, const void* b, void* x, long B, int maxiter, dou
                 int* callbacks_out, double* resid_out, hipgp_iter_cb cb, void* user, cudaStream_t s) {
     if (iters_out) *iters_out = 0;
     if (callbacks_out) *callbacks_out = 0;
-    if (B <= 0) return;
+    if (B < 0) throw Error("negative number of right-hand sides");
+    if (B == 0) return;
     pcg_begin<T>(pl, b, x, B, tol, precond, s);
     const int check_every = cb ? 1 : 8;
     int done = 0, iters = 0, n = 0;
@@ -604,7 +608,8 @@ static void pcg(hipgp_plan* pl, const void* b, void* x, long B, int maxiter, dou
 
 #define DISPATCH(pl, call_f32, call_f64) do { if ((pl)->dtype == HIPGP_F32) { call_f32; } else { call_f64; } } while (0)
 
-static void set_device(const hipgp_plan* pl) { CK(cudaSetDevice(pl->device)); }
+static void need_plan(const hipgp_plan* pl) { if (!pl) throw Error("null plan handle"); }
+static void set_device(const hipgp_plan* pl) { need_plan(pl); CK(cudaSetDevice(pl->device)); }
 
 extern "C" {
 
@@ -658,6 +663,7 @@ int hipgp_plan_destroy(hipgp_plan* pl) {
 
 int hipgp_plan_sizes(const hipgp_plan* pl, int64_t* M, int64_t* Mprime) {
     API_BEGIN
+    need_plan(pl);
     if (M) *M = pl->M;
     if (Mprime) *Mprime = pl->E;
     API_END
@@ -665,6 +671,7 @@ int hipgp_plan_sizes(const hipgp_plan* pl, int64_t* M, int64_t* Mprime) {
 
 int hipgp_plan_embedding(const hipgp_plan* pl, int64_t* Ln, int64_t* Lw) {
     API_BEGIN
+    need_plan(pl);
     int a = 0;
     for (int d = 0; d < pl->ndim_user; ++d) {
         const bool active = pl->m_user[d] > 1 || (pl->D == 1 && pl->M == 1 && d == 0);
@@ -779,6 +786,7 @@ int hipgp_compute_kn(hipgp_plan* pl, const void* Knm, void* kn, int64_t B, int m
 
 int hipgp_plan_set_slab(hipgp_plan* pl, int rank, int nranks) {
     API_BEGIN
+    need_plan(pl);
     if (pl->D != 3) throw Error("slab decomposition needs a 3-D grid");
     if (nranks < 1 || rank < 0 || rank >= nranks) throw Error("bad rank / nranks");
     if (pl->m[0] % nranks) throw Error("grid extent of axis 0 must be divisible by the number of ranks");
@@ -788,6 +796,7 @@ int hipgp_plan_set_slab(hipgp_plan* pl, int rank, int nranks) {
 }
 int hipgp_slab_sizes(const hipgp_plan* pl, int64_t* slab_reals, int64_t* exchange_complex) {
     API_BEGIN
+    need_plan(pl);
     const long n0 = pl->m[0] / pl->slab_nranks;
     if (slab_reals) *slab_reals = n0 * pl->m[1] * pl->m[2];
     const long P3 = ((long)pl->Ln[2] / 2 + 1 + 7) / 8 * 8;
@@ -816,11 +825,13 @@ int hipgp_slab_stage3(hipgp_plan* pl, const void* recv_buf, void* out_slab, void
 }
 int hipgp_plan_profile(hipgp_plan* pl, int enable) {
     API_BEGIN
+    need_plan(pl);
     pl->profiling = enable != 0;
     API_END
 }
 int hipgp_plan_profile_read(hipgp_plan* pl, int kernel_class, double* ms_total, int64_t* launches, int reset) {
     API_BEGIN
+    need_plan(pl);
     if (kernel_class < 0 || kernel_class > 3) throw Error("kernel_class must be 0..3");
 #ifndef HIPGP_EMU
     set_device(pl);
@@ -838,8 +849,8 @@ int hipgp_plan_profile_read(hipgp_plan* pl, int kernel_class, double* ms_total, 
     if (reset) for (int i = 0; i < 4; ++i) { pl->prof_ms[i] = 0; pl->prof_n[i] = 0; }
     API_END
 }
-int hipgp_plan_device_bytes(const hipgp_plan* pl, size_t* bytes) { API_BEGIN if (bytes) *bytes = pl->dev_bytes; API_END }
-int hipgp_plan_launch_count(const hipgp_plan* pl, int64_t* launches) { API_BEGIN if (launches) *launches = pl->launches; API_END }
+int hipgp_plan_device_bytes(const hipgp_plan* pl, size_t* bytes) { API_BEGIN need_plan(pl); if (bytes) *bytes = pl->dev_bytes; API_END }
+int hipgp_plan_launch_count(const hipgp_plan* pl, int64_t* launches) { API_BEGIN need_plan(pl); if (launches) *launches = pl->launches; API_END }
 
 }  // extern "C"
 

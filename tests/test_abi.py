@@ -51,3 +51,68 @@ def test_product_never_imports_oracle():
                 src = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in src.replace("no CPU fallback", ""), f
                 assert "emu_build" not in src and "libhipgp_emu" not in src, f
+
+
+def _lib():
+    from hipgp_b200 import _lib as L
+    if not os.path.exists(L.LIB_PATH):
+        import __graft_entry__ as g
+        g.build()
+    return L, L.declare(ctypes.CDLL(L.LIB_PATH))
+
+
+def _create(lib, dims, dtype=0):
+    h = ctypes.c_void_p()
+    arr = (ctypes.c_int64 * len(dims))(*dims)
+    rc = lib.hipgp_plan_create(len(dims), arr, dtype, 0, ctypes.byref(h))
+    return rc, h
+
+
+def test_plan_create_validates_arguments_without_a_gpu():
+    """hipgp_plan_create / _sizes / _embedding are host-only: argument errors come back as a negative status with a
+    message (never an abort), and a null handle is refused by every query."""
+    L, lib = _lib()
+    for dims, dtype, what in (([0, 4], 0, "extents"), ([4, -1], 0, "extents"), ([4, 4], 7, "dtype"), ([3, 3, 3, 3], 0, "at most 3")):
+        rc, h = _create(lib, dims, dtype)
+        assert rc != 0 and what in lib.hipgp_last_error().decode(), (dims, lib.hipgp_last_error())
+    h = ctypes.c_void_p()
+    assert lib.hipgp_plan_create(0, (ctypes.c_int64 * 1)(4), 0, 0, ctypes.byref(h)) != 0
+    assert lib.hipgp_plan_create(1, None, 0, 0, ctypes.byref(h)) != 0
+    M = ctypes.c_int64(); E = ctypes.c_int64()
+    assert lib.hipgp_plan_sizes(None, ctypes.byref(M), ctypes.byref(E)) != 0
+    assert "null plan" in lib.hipgp_last_error().decode()
+    assert lib.hipgp_plan_embedding(None, None, None) != 0
+    assert lib.hipgp_plan_launch_count(None, None) != 0
+    assert lib.hipgp_plan_set_slab(None, 0, 1) != 0
+    assert lib.hipgp_plan_destroy(None) == 0               # destroying nothing is not an error
+
+
+@pytest.mark.parametrize("dims", [(2,), (100,), (1000, 1000), (300, 300), (128, 128, 64), (1, 50, 1), (17, 1, 40), (512, 512, 512)])
+def test_embedding_lengths(dims):
+    """M = prod m, M' = prod (2m-2) as in the reference (toeplitz_tensor.py:17-40, unit axes dropped); the embedding
+    lengths the transforms run at are 5-smooth, >= 2m-1 (narrow: K, C^-1) and >= (2m-2)+m-1 (wide: R^T, R)."""
+    L, lib = _lib()
+    rc, h = _create(lib, list(dims))
+    assert rc == 0, lib.hipgp_last_error()
+    M = ctypes.c_int64(); E = ctypes.c_int64()
+    assert lib.hipgp_plan_sizes(h, ctypes.byref(M), ctypes.byref(E)) == 0
+    act = [m for m in dims if m > 1]
+    expM = 1; expE = 1
+    for m in act:
+        expM *= m; expE *= 2 * m - 2
+    assert (M.value, E.value) == (expM, expE)
+    n = len(dims)
+    Ln = (ctypes.c_int64 * n)(); Lw = (ctypes.c_int64 * n)()
+    assert lib.hipgp_plan_embedding(h, Ln, Lw) == 0
+    for d, m in enumerate(dims):
+        if m == 1:
+            assert (Ln[d], Lw[d]) == (1, 1)
+            continue
+        for Lv, need in ((Ln[d], 2 * m - 1), (Lw[d], 3 * m - 3)):
+            assert Lv >= need and Lv < 2 * need + 8, (Lv, need)
+            r = Lv
+            for p in (2, 3, 5):
+                while r % p == 0:
+                    r //= p
+            assert r == 1, Lv
+    assert lib.hipgp_plan_destroy(h) == 0

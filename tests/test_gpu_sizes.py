@@ -110,3 +110,45 @@ def test_pcg_iterates_at_full_size_vs_oracle():
     assert relerr(x.cpu().numpy(), x_ref.numpy()) < 1e-9
     r = v - ora.matmul_K(x_ref)
     assert abs(float(info["resid"][0]) - float(r.norm())) <= 1e-6 * float(r.norm())
+
+
+def _free():
+    import gc
+    gc.collect(); torch.cuda.empty_cache()
+
+
+def test_more_than_2_31_elements_in_a_batch():
+    """Maximum sizes: batches whose vectors, workspace and outputs exceed 2^31 elements (64-bit offsets everywhere).
+    (a) BASELINE config 2 grid, 2200 right-hand sides: 2.2e9 input/output reals, 4.6e9 workspace bins;
+    (b) BASELINE config 4 grid, R^T of 272 right-hand sides: 2.21e9 output reals (the (B, M') matrix k_n of hipgp.py:139-146).
+    A right-hand side's result does not depend on what else is in the batch, so rows first / middle / last must equal a
+    one-row call bit for bit; plus ||R^T v||^2 = v^T K v on the last row."""
+    from hipgp_b200.plan import Plan
+    from hipgp_b200 import _lib as L
+    dt = torch.float32
+    # (a)
+    dims = (1000, 1000); B = 2200
+    plan = Plan(list(dims), dt, DEV).set_first_row(torch.from_numpy(first_col(dims)).to(DEV, dt))
+    g = torch.Generator(device=DEV); g.manual_seed(5)
+    v = torch.randn(B, plan.M, device=DEV, dtype=dt, generator=g)
+    assert v.numel() > 2 ** 31
+    out = plan.matvec(L.MV_K, v)
+    for i in (0, 1, B // 2, B - 2, B - 1):
+        one = plan.matvec(L.MV_K, v[i:i + 1].contiguous())
+        assert torch.equal(out[i], one[0]), i
+    del out, v, plan, one
+    _free()
+    # (b)
+    dims = (128, 128, 64); B = 272
+    plan = Plan(list(dims), dt, DEV).set_first_row(torch.from_numpy(first_col(dims)).to(DEV, dt))
+    v = torch.randn(B, plan.M, device=DEV, dtype=dt, generator=g)
+    kn = plan.matvec(L.MV_RT, v)
+    assert kn.numel() > 2 ** 31 and kn.shape == (B, plan.Mprime)
+    for i in (0, B // 2, B - 1):
+        one = plan.matvec(L.MV_RT, v[i:i + 1].contiguous())
+        assert torch.equal(kn[i], one[0]), i
+    Kv = plan.matvec(L.MV_K, v[B - 1:B].contiguous())
+    lhs = float((kn[B - 1].double() ** 2).sum()); rhs = float((v[B - 1].double() * Kv[0].double()).sum())
+    assert abs(lhs - rhs) / abs(rhs) < 1e-4
+    del kn, v, plan, one, Kv
+    _free()
