@@ -1,9 +1,11 @@
 """Drop-in for `ziggy/misc/_inv_matmul.py` : autograd Function for K^{-1} R.
 
 forward  = fused PCG (hipgp_pcg) under no_grad, as `_inv_matmul.py:10-25`.
-backward = a second PCG on grad_output for the right-hand-side gradient (`_inv_matmul.py:35-37,58-60`).
-The gradient with respect to the Toeplitz column (kernel hyper-parameter learning, `_inv_matmul.py:39-55`, via the
-vendored GPyTorch `sym_toeplitz_derivative_quadratic_form`) is a "next" row of SURVEY.md 8f and raises for now.
+backward = a second PCG on grad_output (the "left solves", `_inv_matmul.py:35-37`), returned as the right-hand-side
+gradient (`:58-60`), and -- when the Toeplitz column needs a gradient (learn_kernel=True) -- the quadratic form
+`sym_toeplitz_derivative_quadratic_form([L; R], -1/2 [R; L])` of `_inv_matmul.py:39-55`.  That form is bilinear and
+symmetric in its two arguments, so it equals `-1 * form(L, R)`; `hipgp_toeplitz_quadform` evaluates it with the plan's
+own row / column transform passes (see csrc/corr_api.inl) instead of the reference's 1-D FFTs of length 2M - 1.
 """
 import torch
 from torch.autograd import Function
@@ -22,12 +24,15 @@ class InvMatmul(Function):
 
     @staticmethod
     def backward(ctx, grad_output):
+        right_solves, = ctx.saved_tensors
+        left_solves = None
+        if any(ctx.needs_input_grad):
+            left_solves = InvMatmul.apply(ctx.toeplitz_tensor, ctx.toeplitz_tensor.column, grad_output.contiguous(), True,
+                                          ctx.maxiter, ctx.tol)
+        column_grad = None
         if ctx.needs_input_grad[1]:
-            raise NotImplementedError(
-                "hipgp_b200: gradient w.r.t. the Toeplitz column (learn_kernel=True) is not built yet "
-                "(reference: ziggy/misc/_inv_matmul.py:39-55); SURVEY.md 8f rank 2")
-        right_grad = None
-        if ctx.needs_input_grad[2]:
-            right_grad = InvMatmul.apply(ctx.toeplitz_tensor, ctx.toeplitz_tensor.column, grad_output, True,
-                                         ctx.maxiter, ctx.tol)
-        return None, None, right_grad, None, None, None
+            with torch.no_grad():
+                column_grad = ctx.toeplitz_tensor._plan.toeplitz_quadform(left_solves, right_solves, scale=-1.0)
+            column_grad = column_grad.view(ctx.toeplitz_tensor.column.shape)
+        right_grad = left_solves if ctx.needs_input_grad[2] else None
+        return None, column_grad, right_grad, None, None, None

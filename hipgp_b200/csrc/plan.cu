@@ -654,7 +654,8 @@ int hipgp_plan_destroy(hipgp_plan* pl) {
     pl->gn32.release(t); pl->gw32.release(t); pl->gn64.release(t); pl->gw64.release(t);
     for (DevBuf* b : {&pl->specK, &pl->specCinv, &pl->specW, &pl->Dm, &pl->Dinv, &pl->Dsqrt, &pl->colK, &pl->colG, &pl->colS,
                       &pl->tmpA, &pl->tmpB, &pl->costab, &pl->counts, &pl->W1, &pl->W2, &pl->vr, &pl->vp, &pl->vz, &pl->vAp,
-                      &pl->partial, &pl->scal, &pl->cnt, &pl->flags, &pl->stage_in, &pl->stage_out})
+                      &pl->partial, &pl->scal, &pl->cnt, &pl->flags, &pl->stage_in, &pl->stage_out, &pl->corrU, &pl->corrV, &pl->corrS,
+                      &pl->corrLag})
         b->release(t);
     if (pl->pinned) cudaFreeHost(pl->pinned);
     delete pl;
@@ -856,6 +857,7 @@ int hipgp_plan_launch_count(const hipgp_plan* pl, int64_t* launches) { API_BEGIN
 
 #include "vec_api.inl"
 #include "kxu_api.inl"
+#include "corr_api.inl"
 
 #ifdef HIPGP_EMU
 namespace emu {

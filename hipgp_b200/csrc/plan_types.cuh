@@ -273,6 +273,7 @@ struct hipgp_plan {
     DevBuf W1, W2;                         // frequency-domain workspace
     DevBuf vr, vp, vz, vAp, partial, scal, cnt, flags;   // PCG state
     DevBuf stage_in, stage_out;            // device staging for the *_host entry points
+    DevBuf corrU, corrV, corrS, corrLag;   // Toeplitz-column quadratic form (corr_api.inl): spectra of a chunk of pairs, their sum, lags
     void* pinned = nullptr;                // host flags mirror
     long pcg_B = 0;
     int slab_rank = 0, slab_nranks = 1;      // slab-decomposed grid (axis 0 split over ranks); 1 = not decomposed

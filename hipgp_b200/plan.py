@@ -130,6 +130,20 @@ class Plan:
                                                          _stream_ptr(self.device)))
         return out
 
+    def toeplitz_quadform(self, left, right, scale=1.0):
+        """sum_j u_j^T (dT/dc_i) v_j over the FLATTENED M-vectors (gpt_toeplitz.py:169-209
+        `sym_toeplitz_derivative_quadratic_form`); left / right are (S, M).  Returns (M,)."""
+        u = self._vec(left, self.M, "left")
+        v = self._vec(right, self.M, "right")
+        if u.shape != v.shape:
+            raise ValueError("left and right must have the same shape")
+        out = torch.empty(self.M, dtype=self.dtype, device=self.device)
+        with torch.cuda.device(self.device):
+            L.check(self.lib, self.lib.hipgp_toeplitz_quadform(self._h, C.c_void_p(u.data_ptr()), C.c_void_p(v.data_ptr()),
+                                                                u.shape[0], float(scale), C.c_void_p(out.data_ptr()),
+                                                                _stream_ptr(self.device)))
+        return out
+
     # host-buffer entry points (H2D / D2H inside the call) -- used for the end-to-end benchmark figure
     def matvec_host(self, mode, vec_host, out_host):
         assert not vec_host.is_cuda and not out_host.is_cuda and vec_host.is_contiguous() and out_host.is_contiguous()

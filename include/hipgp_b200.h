@@ -122,6 +122,14 @@ int hipgp_meanfield_rowstats(int dtype, const void* kn_dev, const void* qm_dev, 
 int hipgp_meanfield_colstats(int dtype, const void* kn_dev, const void* w1_dev, const void* w2_dev, int64_t B, int64_t E,
                              void* dm_dev, void* lam_dev, void* stream);
 
+/* ---- Toeplitz-column quadratic form: the kernel-hyper-parameter gradient of InvMatmul.backward
+ * (ziggy/misc/_inv_matmul.py:39-55 -> gpt_toeplitz.py:169-209 sym_toeplitz_derivative_quadratic_form, evaluated there on
+ * the FLATTENED M-vectors with 1-D FFTs of length 2M-1).  left/right: S pairs of M-vectors (device, row-major S x M);
+ *   out[i] = scale * sum_j sum_k ( u_j[k+i] v_j[k] + v_j[k+i] u_j[k] )   (1 <= i < M),   out[0] = scale * sum_j u_j . v_j
+ * over the flattened index.  InvMatmul.backward is this with S = B, u = left solves, v = right solves, scale = -1. */
+int hipgp_toeplitz_quadform(hipgp_plan* plan, const void* left_dev, const void* right_dev, int64_t S, double scale,
+                            void* out_dev, void* stream);
+
 /* ---- slab-decomposed 3-D grids (axis 0 split over `nranks` GPUs; K and C^-1 matvecs; one right-hand side).
  * The reference has no multi-GPU path; this is the grid-sharded route of SURVEY.md 8e.  A matvec is
  *   stage1(in_slab -> send) ; all-to-all(send -> buf) ; stage2(mode, buf in place) ; all-to-all(buf -> recv) ;

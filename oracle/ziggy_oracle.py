@@ -385,3 +385,40 @@ def batch_indices(n, batch_size):
         idx = it % num_batches
         return slice(idx * batch_size, min((idx + 1) * batch_size, n))
     return [one(i) for i in range(num_batches)]
+
+
+def toeplitz_matmul_1d(column, row, vec):
+    """T v for the Toeplitz matrix with first column `column` and first row `row` (gpt_toeplitz.py:96-154): circulant
+    embedding of size 2n-1 = [column, reversed(row[1:])], product in the Fourier domain, first n outputs."""
+    n = column.shape[-1]
+    c = np.concatenate([column, row[1:][::-1]])
+    vp = np.zeros(2 * n - 1, dtype=np.float64); vp[:n] = vec
+    return np.real(np.fft.ifft(np.fft.fft(c) * np.fft.fft(vp)))[:n]
+
+
+def sym_toeplitz_derivative_quadratic_form(left_vectors, right_vectors):
+    """sum_j u_j^T (dT/dc_i) v_j for all i (gpt_toeplitz.py:169-209); inputs (M, S) like the reference (columns are the
+    vectors), fp64 numpy.  Two Toeplitz products per pair -- an upper-triangular one built from u and one from its
+    reversal -- and the diagonal correction of element 0, exactly in the reference's order."""
+    L = np.asarray(left_vectors, dtype=np.float64); R = np.asarray(right_vectors, dtype=np.float64)
+    if L.ndim == 1:
+        L = L[:, None]; R = R[:, None]
+    M, S = L.shape
+    res = np.zeros(M)
+    for j in range(S):
+        u, v = L[:, j], R[:, j]
+        col = np.zeros(M); col[0] = u[0]
+        res += toeplitz_matmul_1d(col, u, v)                      # gpt_toeplitz.py:199-201
+        ur = u[::-1]
+        col = np.zeros(M); col[0] = ur[0]
+        res += toeplitz_matmul_1d(col, ur, v[::-1])               # :202-204
+    res[0] -= np.sum(L * R)                                       # :207
+    return res
+
+
+def inv_matmul_backward(left_solves, right_solves):
+    """column gradient of InvMatmul.backward (_inv_matmul.py:39-55); left/right solves are (B, M)."""
+    Ls = np.asarray(left_solves, dtype=np.float64); Rs = np.asarray(right_solves, dtype=np.float64)
+    left_vecs = np.concatenate([Ls, Rs], 0).T
+    right_vecs = np.concatenate([Rs, Ls], 0).T * (-0.5)
+    return sym_toeplitz_derivative_quadratic_form(left_vecs, right_vecs)

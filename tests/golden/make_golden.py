@@ -10,6 +10,8 @@ own implementation.  Files:
   kernels_<dtype>.npz          kernels.py forward/diag/k_semi/k_semi_mc/k_doubly_diag,
                                exact_gp_1d_derivatives.py:9-38
   compute_kn_<dtype>.npz       hipgp.py:117-146 + svi_gp.py:48-76 through MeanFieldToeplitzGP
+  quadform_<dtype>.npz         gpt_toeplitz.py:169-209 on flattened 1-/2-/3-D grid vectors, and the column / right-hand-side
+                               gradients of InvMatmul.backward (_inv_matmul.py:28-64) through ToeplitzTensor.inv_matmul
   notebook_counts.npz          preconditioner-analysis.ipynb saved outputs (raw lines 101-103,142-144,183-185,224-226)
 """
 import os
@@ -238,6 +240,34 @@ def make_svi_step():
         print("svi_step", dname, float(elbo))
 
 
+def make_quadform():
+    """sym_toeplitz_derivative_quadratic_form on seeded vectors, and autograd through the reference's InvMatmul."""
+    from ziggy.misc.gpt_toeplitz import sym_toeplitz_derivative_quadratic_form as quad
+    for dname, dtype in DT.items():
+        torch.manual_seed(99)
+        out = {}
+        for tag, dims, S in (("1d", (100,), 3), ("2d", (17, 40), 3), ("3d", (6, 9, 12), 2), ("2d_odd", (5, 3), 4)):
+            M = int(np.prod(dims))
+            u = torch.randn(S, M, dtype=dtype); v = torch.randn(S, M, dtype=dtype)
+            out[tag + "_dims"] = np.array(dims); out[tag + "_u"] = u.numpy(); out[tag + "_v"] = v.numpy()
+            out[tag + "_quad"] = quad(u.t().contiguous(), v.t().contiguous()).numpy()
+        # InvMatmul.backward on the 2d_17x40_matern32 Toeplitz case
+        grids, kname, sig2, ell, jitter, B = TOEPLITZ_CASES["2d_17x40_matern32"]
+        xgrids = [torch.linspace(lo, hi, m, dtype=dtype) for lo, hi, m in grids]
+        kern = get_kernel(kname, dtype)
+        tt = ToeplitzTensor(xgrids, lambda x, y: kern.forward(x, y, params=(sig2, ell)), batch_shape=None, jitter_val=jitter)
+        tt.column.requires_grad_(True)
+        Rt = torch.randn(B, int(tt.M), dtype=dtype, requires_grad=True)
+        wts = torch.randn(B, int(tt.M), dtype=dtype)
+        maxiter, tol = 60, (1e-12 if dname == "f64" else 1e-6)
+        sol = tt.inv_matmul(Rt, do_precond=True, maxiter=maxiter, tol=tol)
+        (sol * wts).sum().backward()
+        out.update(bw_R=Rt.detach().numpy(), bw_w=wts.numpy(), bw_solves=sol.detach().numpy(),
+                   bw_column_grad=tt.column.grad.numpy(), bw_right_grad=Rt.grad.numpy(), bw_maxiter=maxiter, bw_tol=tol)
+        np.savez_compressed(os.path.join(HERE, "quadform_%s.npz" % dname), **out)
+        print("quadform", dname, {k: np.asarray(v).shape for k, v in out.items() if k.endswith("quad") or k.startswith("bw_c")})
+
+
 def make_notebook_counts():
     """Saved cell outputs of experiments-hip-gp/preconditioner-analysis.ipynb -- the only numbers the
     reference repo pins (unseeded RNG there => reproducible to a few iterations only)."""
@@ -253,9 +283,13 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "svi":
         make_svi_step()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "quadform":
+        make_quadform()
+        sys.exit(0)
     make_notebook_counts()
     make_svi_step()
     make_toeplitz()
     make_kernels()
     make_compute_kn()
     make_cfg1()
+    make_quadform()

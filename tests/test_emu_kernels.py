@@ -131,3 +131,31 @@ def test_vec_kernels(lib):
     p0 = p.copy()
     assert lib.hipgp_vec_p_update(L.F64, ptr(p), ptr(x), ptr(rs), ptr(pAp), B, M, None) == 0
     assert np.allclose(p, x + al * p0)
+
+
+@pytest.mark.parametrize("tag,dname", [("1d", "f64"), ("2d", "f64"), ("2d", "f32"), ("3d", "f64"), ("2d_odd", "f64")])
+def test_toeplitz_quadform(lib, tag, dname):
+    """hipgp_toeplitz_quadform (forward passes, real spectrum product, one inverse, carry-pattern gather) against the
+    reference's sym_toeplitz_derivative_quadratic_form on flattened 1-/2-/3-D grid vectors (golden, gpt_toeplitz.py:169-209)."""
+    g = np.load(os.path.join(GOLD, "quadform_%s.npz" % dname))
+    dt = np.float32 if dname == "f32" else np.float64
+    dims = np.array(g[tag + "_dims"], dtype=np.int64)
+    M = int(np.prod(dims))
+    plan = C.c_void_p()
+    assert lib.hipgp_plan_create(len(dims), dims.ctypes.data_as(L._pi64), L.F32 if dt == np.float32 else L.F64, 0, C.byref(plan)) == 0
+    col = np.zeros(M, dtype=dt); col[0] = 1.0              # any first row: the form does not depend on it
+    ncl = C.c_int64()
+    assert lib.hipgp_plan_set_first_row(plan, ptr(col), 1e-6, C.byref(ncl), None) == 0, lib.hipgp_last_error()
+    u = np.ascontiguousarray(g[tag + "_u"].astype(dt)); v = np.ascontiguousarray(g[tag + "_v"].astype(dt))
+    out = np.zeros(M, dtype=dt)
+    assert lib.hipgp_toeplitz_quadform(plan, ptr(u), ptr(v), u.shape[0], 1.0, ptr(out), None) == 0, lib.hipgp_last_error()
+    assert rel(out, g[tag + "_quad"]) < (1e-5 if dname == "f32" else 1e-10), rel(out, g[tag + "_quad"])
+    # scale and the empty sum
+    assert lib.hipgp_toeplitz_quadform(plan, ptr(u), ptr(v), 1, -2.0, ptr(out), None) == 0
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+    from oracle import ziggy_oracle as zo
+    ref1 = -2.0 * zo.sym_toeplitz_derivative_quadratic_form(u[0].astype(np.float64), v[0].astype(np.float64))
+    assert rel(out, ref1) < (1e-5 if dname == "f32" else 1e-10)
+    assert lib.hipgp_toeplitz_quadform(plan, None, None, 0, 1.0, ptr(out), None) == 0 and not out.any()
+    lib.hipgp_plan_destroy(plan)

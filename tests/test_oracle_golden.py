@@ -191,3 +191,16 @@ def test_batch_indices_cover_exactly_once():
         assert [(s.start, s.stop) for s in ref] == [(s.start, s.stop) for s in got]
         cover = np.concatenate([np.arange(n)[s] for s in got])
         assert np.array_equal(cover, np.arange(n))
+
+
+@pytest.mark.parametrize("dname", ["f32", "f64"])
+def test_toeplitz_quadform_and_inv_matmul_backward(dname, golden_dir):
+    """gpt_toeplitz.py:169-209 and the column gradient of _inv_matmul.py:39-55: oracle restatement vs the reference."""
+    g = np.load(os.path.join(golden_dir, "quadform_%s.npz" % dname))
+    tol = TIGHT[dname] * 20
+    for tag in ("1d", "2d", "3d", "2d_odd"):
+        got = zo.sym_toeplitz_derivative_quadratic_form(g[tag + "_u"].T, g[tag + "_v"].T)
+        assert relerr(got, g[tag + "_quad"]) < tol, tag
+    # InvMatmul.backward: left solves = K^-1 (dL/dsolves) are the reference's own right-hand-side gradient
+    got = zo.inv_matmul_backward(g["bw_right_grad"], g["bw_solves"])
+    assert relerr(got, g["bw_column_grad"]) < tol
