@@ -858,6 +858,7 @@ int hipgp_plan_launch_count(const hipgp_plan* pl, int64_t* launches) { API_BEGIN
 #include "vec_api.inl"
 #include "kxu_api.inl"
 #include "corr_api.inl"
+#include "block_api.inl"
 
 #ifdef HIPGP_EMU
 namespace emu {

@@ -14,7 +14,8 @@ from torch import nn
 from .toeplitz_tensor import ToeplitzTensor
 from . import kernels as hk
 from . import dist as hdist
-from .plan import meanfield_rowstats, meanfield_colstats
+from .plan import meanfield_rowstats, meanfield_colstats, block_lam, block_diag_multiply, row_dot
+from . import util as hutil
 
 
 class _GridKernelFn:
@@ -173,6 +174,16 @@ class MeanFieldToeplitzGP(ToeplitzInducingGP):
     def _row_stats(self, kn, qm, qS):
         return meanfield_rowstats(kn, qm, qS)      # knt_m, knt_kn, knSkn
 
+    def _batch_stats(self, kn, bdiff, ivar_noise):
+        """sums over the (local) minibatch that the natural gradient needs: sum_n bdiff_n k_n and sum_n w_n k_n^2"""
+        return meanfield_colstats(kn, bdiff, ivar_noise)
+
+    def _natural_gradient(self, dm, lam_sum, qm, bscale):
+        """hipgp.py:247-250"""
+        lam_diag = bscale * lam_sum + 1
+        dS = -.5 * lam_diag[:, None] - self.global_theta2.data
+        return dm + dS * (-2 * qm), dS
+
     def elbo_and_grad(self, xbatch, ybatch, noise_std_batch=None, maxiter_cg=10, integrated_obs=False,
                       semi_integrated_estimator="analytic", semi_integrated_samps=10, print_debug_info=False, Kmm=None,
                       shard=True):
@@ -206,17 +217,14 @@ class MeanFieldToeplitzGP(ToeplitzInducingGP):
             batch_an = -0.5 * ivar_noise * (mse + variance) - log_noise_std - 0.5 * np.log(2 * np.pi)
             # natural-gradient statistics, hipgp.py:241-250
             bdiff = ivar_noise * (knt_m - y)
-            dm_sum, lam_sum = meanfield_colstats(kn, bdiff, ivar_noise)
+            dm_sum, lam_sum = self._batch_stats(kn, bdiff, ivar_noise)
             an_sum = batch_an.sum().reshape(1)
             if sharded:
                 hdist.allreduce_packed([dm_sum, lam_sum, an_sum])      # the one data-path collective of the step
             bscale = self.N / bsz
             data_dm = -dm_sum[:, None]
             dm = bscale * data_dm - qm
-            lam_diag = bscale * lam_sum + 1
-            dS = -.5 * lam_diag[:, None] - self.global_theta2.data
-            deta1 = dm + dS * (-2 * qm)
-            deta2 = dS
+            deta1, deta2 = self._natural_gradient(dm, lam_sum, qm, bscale)
             self.global_theta1.grad = -deta1
             self.global_theta2.grad = -deta2
             kl_to_prior = self.get_kl_to_prior(qm, qS)
@@ -239,3 +247,99 @@ class MeanFieldToeplitzGP(ToeplitzInducingGP):
         if _on_device:
             return knt_m[:, None].detach(), sig_star.detach()
         return knt_m[:, None].cpu().detach(), sig_star.cpu().detach()
+
+
+class BlockToeplitzGP(MeanFieldToeplitzGP):
+    """Block-diagonal variational family (ziggy/hipgp.py:527-690): q(u) = N(m, blockdiag(S_k)) with the blocks being
+    neighbouring chunks of the WHITENED (2m-2)-grid.  `qm` is kept in Toeplitz ordering, the blocks in block ordering;
+    the two contractions over k_n run through `hipgp_block_lam` / `hipgp_block_diag_multiply`, which read k_n through the
+    index map (no permuted copies, no (bsz, num_blocks, bs, bs) outer products as in hipgp.py:252-255).  The ELBO /
+    natural-gradient step and `predict` are the shared code of the mean-field class with this family's statistics."""
+
+    def __init__(self, kernel, xgrids, num_obs, xblock_size=10, block_sizes=None, sig2_init=1., ell_init=.05, noise2_init=1.,
+                 init_Svar=.1, learn_kernel=False, learn_noise=False, dtype=torch.float, whitened_type='ziggy',
+                 parameterization='expectation-family', jitter_val=1e-3):
+        ToeplitzInducingGP.__init__(self, kernel, xgrids, num_obs, sig2_init=sig2_init, ell_init=ell_init,
+                                    noise2_init=noise2_init, learn_kernel=learn_kernel, learn_noise=learn_noise, dtype=dtype,
+                                    whitened_type=whitened_type, parameterization=parameterization, jitter_val=jitter_val)
+        input_dim = len(xgrids)
+        if block_sizes is not None:
+            assert input_dim == len(block_sizes), "xgrids ndim = {}, block ndim = {}".format(input_dim, len(block_sizes))
+        else:
+            block_sizes = [xblock_size for _ in range(input_dim)]
+        expanded_xgrids = self.get_expanded_xgrids(xgrids)
+        self.block_idx, self.to_blocks, self.from_blocks = hutil.define_block_chunks(expanded_xgrids, block_sizes)
+        self.num_blocks, self.block_size = self.block_idx.shape
+        self._block_idx_dev = None
+        eye = torch.eye(self.block_size, dtype=self.dtype)
+        if self.parameterization == 'standard':
+            self.global_m = nn.Parameter(torch.nn.init.xavier_normal_(torch.zeros(self.Mprime, 1, dtype=self.dtype)))
+            self.global_S = nn.Parameter(torch.stack([init_Svar * eye for _ in range(self.num_blocks)]))
+        else:
+            self.global_theta1 = nn.Parameter(torch.nn.init.xavier_normal_(torch.zeros(self.Mprime, 1, dtype=self.dtype)))
+            self.global_theta2 = nn.Parameter(torch.stack([(-.5 / init_Svar) * eye for _ in range(self.num_blocks)]))
+
+    @property
+    def name(self):
+        return 'block'
+
+    def get_expanded_xgrids(self, xgrids):
+        return [torch.arange(2 * len(x) - 2) for x in xgrids]
+
+    def _idx(self, device):
+        if self._block_idx_dev is None or self._block_idx_dev.device != device:
+            self._block_idx_dev = self.block_idx.to(device)
+        return self._block_idx_dev
+
+    def standard_variational_params(self):
+        if self.parameterization == 'standard':
+            return self.global_m, self.global_S
+        S = torch.inverse(-2 * self.global_theta2.data)                 # batched small inverses (library call)
+        m = self.block_diag_multiply(S, self.global_theta1.data.t()).t()
+        return m, S
+
+    def block_diag_multiply(self, S_block, v):
+        """S_block (num_blocks, bs, bs) times v (bsz, M') in Toeplitz ordering (hipgp.py:640-652)"""
+        bsz, _ = v.shape
+        Sv = block_diag_multiply(S_block, v, self._idx(v.device))
+        assert Sv.shape == (bsz, self.num_blocks * self.block_size), Sv.shape
+        return Sv
+
+    def get_S_from_lam(self, lam):
+        return torch.inverse(lam)
+
+    def compute_knSkn(self, kn, qS):
+        return row_dot(kn, self.block_diag_multiply(qS, kn))
+
+    def get_identity_for_lam(self):
+        return torch.eye(self.block_size, device=self.xgrids[0].device, dtype=self.dtype)
+
+    def get_lam(self, ivar_noise, kn, bscale=1, add_identity=True):
+        """Lambda = bscale * sum_n 1/sigma_n^2 kn kn^T (+ I), (num_blocks, bs, bs)  (hipgp.py:666-685)"""
+        return block_lam(kn, ivar_noise, self._idx(kn.device), scale=bscale, diag=1.0 if add_identity else 0.0)
+
+    def get_kl_to_prior(self, qm=None, qS=None):
+        """stats.py:15-29 block_kl_to_standard (Cholesky log-determinants of the jittered blocks)"""
+        if qm is None or qS is None:
+            qm, qS = self.standard_variational_params()
+        I = torch.eye(qS.shape[1], dtype=qS.dtype, device=qS.device)
+        Schol = torch.linalg.cholesky(qS + 1e-4 * I)
+        lndet = 2.0 * torch.sum(torch.log(torch.diagonal(Schol, dim1=-2, dim2=-1)))
+        D = qS.shape[0] * qS.shape[1]
+        Strace = torch.sum(torch.diagonal(qS, dim1=-2, dim2=-1))
+        return .5 * (Strace + torch.sum(qm * qm) - lndet - D)
+
+    def _row_stats(self, kn, qm, qS):
+        st = meanfield_rowstats(kn, qm, torch.zeros_like(qm))
+        return st[0], st[1], self.compute_knSkn(kn, qS)
+
+    def _batch_stats(self, kn, bdiff, ivar_noise):
+        dm_sum, _ = meanfield_colstats(kn, bdiff, ivar_noise)
+        return dm_sum, block_lam(kn, ivar_noise, self._idx(kn.device), scale=1.0, diag=0.0)
+
+    def _natural_gradient(self, dm, lam_sum, qm, bscale):
+        """hipgp.py:251-261"""
+        lam_block = bscale * lam_sum + self.get_identity_for_lam().to(lam_sum.device)[None]
+        dS = -.5 * lam_block - self.global_theta2.data
+        dSdeta1 = self.block_diag_multiply(dS, -2 * qm[None, :, 0])
+        return dm + dSdeta1.squeeze().unsqueeze(-1), dS

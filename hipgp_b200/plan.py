@@ -234,3 +234,58 @@ def meanfield_colstats(kn, w1, w2):
                                                   C.c_void_p(w2.data_ptr()), B, E, C.c_void_p(dm.data_ptr()),
                                                   C.c_void_p(lam.data_ptr()), _stream_ptr(kn.device)))
     return dm, lam
+
+
+def _blk_idx(blk_idx, device):
+    idx = blk_idx.to(device=device, dtype=torch.int64).contiguous()
+    if idx.dim() != 2:
+        raise ValueError("block index must be (num_blocks, block_size)")
+    return idx
+
+
+def block_lam(kn, w, blk_idx, scale=1.0, diag=1.0):
+    """lam[k] = scale * sum_n w_n kn_blk[n,k] kn_blk[n,k]^T + diag * I  (get_lam, hipgp.py:666-685) without the permuted
+    copy of kn or the (B, num_blocks, bs, bs) outer products of hipgp.py:252-255.  Returns (num_blocks, bs, bs)."""
+    _require_cuda(kn, "kn")
+    lib = L.load()
+    kn = kn.contiguous(); w = w.reshape(-1).to(kn.dtype).contiguous()
+    idx = _blk_idx(blk_idx, kn.device)
+    B, E = kn.shape
+    nblk, bs = idx.shape
+    out = torch.empty((nblk, bs, bs), dtype=kn.dtype, device=kn.device)
+    with torch.cuda.device(kn.device):
+        L.check(lib, lib.hipgp_block_lam(_DT[kn.dtype], C.c_void_p(kn.data_ptr()), C.c_void_p(w.data_ptr()),
+                                         C.c_void_p(idx.data_ptr()), B, E, nblk, bs, float(scale), float(diag),
+                                         C.c_void_p(out.data_ptr()), _stream_ptr(kn.device)))
+    return out
+
+
+def block_diag_multiply(S_block, v, blk_idx):
+    """from_blocks(S_block @ to_blocks(v)) for v (B, M')  (hipgp.py:640-652).  Returns (B, M')."""
+    _require_cuda(v, "v")
+    lib = L.load()
+    v = v.contiguous(); S = S_block.to(v.dtype).contiguous()
+    idx = _blk_idx(blk_idx, v.device)
+    B, E = v.shape
+    nblk, bs = idx.shape
+    if tuple(S.shape) != (nblk, bs, bs):
+        raise ValueError("S_block must be (num_blocks, block_size, block_size)")
+    out = torch.empty_like(v)
+    with torch.cuda.device(v.device):
+        L.check(lib, lib.hipgp_block_diag_multiply(_DT[v.dtype], C.c_void_p(S.data_ptr()), C.c_void_p(v.data_ptr()),
+                                                   C.c_void_p(idx.data_ptr()), B, E, nblk, bs, C.c_void_p(out.data_ptr()),
+                                                   _stream_ptr(v.device)))
+    return out
+
+
+def row_dot(a, b):
+    """per-row dot products of two (B, M) tensors, deterministic fixed-order reduction (hipgp_vec_dot).  Returns (B,)."""
+    _require_cuda(a, "a")
+    lib = L.load()
+    a = a.contiguous(); b = b.to(a.dtype).contiguous()
+    B, M = a.shape
+    out = torch.empty(B, dtype=torch.float64, device=a.device)
+    with torch.cuda.device(a.device):
+        L.check(lib, lib.hipgp_vec_dot(_DT[a.dtype], C.c_void_p(a.data_ptr()), C.c_void_p(b.data_ptr()),
+                                       C.c_void_p(out.data_ptr()), B, M, _stream_ptr(a.device)))
+    return out.to(a.dtype)

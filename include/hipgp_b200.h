@@ -122,6 +122,17 @@ int hipgp_meanfield_rowstats(int dtype, const void* kn_dev, const void* qm_dev, 
 int hipgp_meanfield_colstats(int dtype, const void* kn_dev, const void* w1_dev, const void* w2_dev, int64_t B, int64_t E,
                              void* dm_dev, void* lam_dev, void* stream);
 
+/* ---- block-diagonal variational family (ziggy/hipgp.py:527-690; index maps of ziggy/misc/util.py:79-126).
+ * blk_idx (num_blocks x block_size, int64, device) is the permutation `define_block_chunks` returns; nblk * bs = M'.
+ * block_lam:            lam[k][i][j] = scale * sum_n w[n] kn[n, idx[k,i]] kn[n, idx[k,j]] + diag * (i == j)
+ *                       (get_lam, hipgp.py:666-685; the natural-gradient branch :251-257 with scale = N / bsz, diag = 1)
+ * block_diag_multiply:  out[b, idx[k,i]] = sum_j S[k][i][j] v[b, idx[k,j]]   (= from_blocks(S to_blocks(v)), hipgp.py:640-652)
+ * kn, v, out: (B, M'); w: (B); S, lam: (nblk, bs, bs); all in `dtype`. */
+int hipgp_block_lam(int dtype, const void* kn_dev, const void* w_dev, const int64_t* blk_idx_dev, int64_t B, int64_t E,
+                    int64_t nblk, int64_t bs, double scale, double diag, void* lam_dev, void* stream);
+int hipgp_block_diag_multiply(int dtype, const void* S_dev, const void* v_dev, const int64_t* blk_idx_dev, int64_t B,
+                              int64_t E, int64_t nblk, int64_t bs, void* out_dev, void* stream);
+
 /* ---- Toeplitz-column quadratic form: the kernel-hyper-parameter gradient of InvMatmul.backward
  * (ziggy/misc/_inv_matmul.py:39-55 -> gpt_toeplitz.py:169-209 sym_toeplitz_derivative_quadratic_form, evaluated there on
  * the FLATTENED M-vectors with 1-D FFTs of length 2M-1).  left/right: S pairs of M-vectors (device, row-major S x M);

@@ -422,3 +422,73 @@ def inv_matmul_backward(left_solves, right_solves):
     left_vecs = np.concatenate([Ls, Rs], 0).T
     right_vecs = np.concatenate([Rs, Ls], 0).T * (-0.5)
     return sym_toeplitz_derivative_quadratic_form(left_vecs, right_vecs)
+
+
+# ---- block-diagonal variational family (hipgp.py:527-690, util.py:79-126, stats.py:15-29) --------------------------
+def define_block_chunks(lens, chunk_sizes):
+    """util.py:79-117: (num_blocks, block_size) flat indices; blocks enumerated with axis 0 outermost, points inside a
+    block in row-major order of the chunk."""
+    chunks = [np.split(np.arange(n), n // c) for n, c in zip(lens, chunk_sizes)]
+    out = []
+    if len(lens) == 2:
+        for bx in chunks[0]:
+            for by in chunks[1]:
+                xx, yy = np.meshgrid(bx, by, indexing="ij")
+                out.append((xx * lens[1] + yy).reshape(-1))
+    else:
+        for bx in chunks[0]:
+            for by in chunks[1]:
+                for bz in chunks[2]:
+                    xx, yy, zz = np.meshgrid(bx, by, bz, indexing="ij")
+                    out.append((xx * (lens[1] * lens[2]) + yy * lens[2] + zz).reshape(-1))
+    return np.stack(out, 0)
+
+
+def block_get_lam(blk_idx, ivar_noise, kn, bscale=1.0, add_identity=True):
+    """hipgp.py:666-685"""
+    blk_kn = kn[..., torch.as_tensor(blk_idx)].transpose(0, 1)                  # (num_blocks, bsz, block_size)
+    lam = bscale * torch.matmul(blk_kn.transpose(1, 2), ivar_noise * blk_kn)
+    if add_identity:
+        lam = lam + torch.eye(blk_idx.shape[1], dtype=kn.dtype)
+    return lam
+
+
+def block_diag_multiply(blk_idx, S_block, v):
+    """hipgp.py:640-652: from_blocks(S_block @ to_blocks(v))"""
+    idx = torch.as_tensor(blk_idx)
+    Sv_block = S_block.matmul(v[..., idx][..., None])
+    rev = torch.argsort(idx.flatten())
+    return Sv_block.flatten(start_dim=1)[..., rev]
+
+
+def block_kl_to_standard(blk_m, blk_S):
+    """stats.py:15-29"""
+    I = torch.eye(blk_S.shape[1], dtype=blk_S.dtype)
+    Schol = torch.linalg.cholesky(blk_S + 1e-4 * I)
+    lndet = 2.0 * torch.sum(torch.sum(torch.log(torch.diagonal(Schol, dim1=-2, dim2=-1)), dim=-1))
+    n_blk, blk_size, _ = blk_S.shape
+    return .5 * (torch.sum(torch.diagonal(blk_S, dim1=-2, dim2=-1)) + torch.sum(blk_m * blk_m) - lndet - n_blk * blk_size)
+
+
+def block_elbo_and_grad(xgrids, kfun, blk_idx, Knm, Knn_diag, ybatch, noise_std_batch, theta1, theta2, num_obs, maxiter_cg=10,
+                        jitter_val=1e-3):
+    """hipgp.py:194-276 (block branch :251-261) + compute_batch_an (:370-414) + standard_variational_params (:631-638).
+    Returns (elbo_estimate, theta1.grad, theta2.grad, kn, qm, qS)."""
+    kn = compute_kn(xgrids, kfun, Knm, maxiter_cg=maxiter_cg, jitter_val=jitter_val)
+    qS = torch.inverse(-2 * theta2)
+    qm = block_diag_multiply(blk_idx, qS, theta1.t()).t()
+    y = ybatch.squeeze(); Knn = Knn_diag.squeeze()
+    knt_kn = torch.sum(kn * kn, dim=-1).squeeze()
+    knt_m = kn.matmul(qm).squeeze()
+    knSkn = torch.sum(kn * block_diag_multiply(blk_idx, qS, kn), dim=-1).squeeze()
+    ivar = (1 / (noise_std_batch ** 2)).squeeze()
+    batch_an = -0.5 * ivar * ((knt_m - y) ** 2 + Knn - knt_kn + knSkn) - torch.log(noise_std_batch).squeeze() - 0.5 * np.log(2 * np.pi)
+    elbo = torch.mean(batch_an) - block_kl_to_standard(qm, qS) / num_obs
+    bscale = num_obs / Knm.shape[0]
+    ivar_noise = 1 / (noise_std_batch ** 2)
+    bdiff = ivar_noise * (kn.matmul(qm) - ybatch)
+    dm = bscale * (-torch.matmul(bdiff.t(), kn).t()) - qm
+    lam_block = block_get_lam(blk_idx, ivar_noise, kn, bscale=bscale, add_identity=True)
+    dS = -.5 * lam_block - theta2
+    deta1 = dm + block_diag_multiply(blk_idx, dS, -2 * qm[None, :, 0]).squeeze().unsqueeze(-1)
+    return elbo, -deta1, -dS, kn, qm, qS

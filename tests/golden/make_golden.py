@@ -12,6 +12,8 @@ own implementation.  Files:
   compute_kn_<dtype>.npz       hipgp.py:117-146 + svi_gp.py:48-76 through MeanFieldToeplitzGP
   quadform_<dtype>.npz         gpt_toeplitz.py:169-209 on flattened 1-/2-/3-D grid vectors, and the column / right-hand-side
                                gradients of InvMatmul.backward (_inv_matmul.py:28-64) through ToeplitzTensor.inv_matmul
+  block_step_<dtype>.npz       BlockToeplitzGP (hipgp.py:527-690): define_block_chunks (util.py:79-126) index maps in 2-D and 3-D,
+                               get_lam, block_diag_multiply, compute_knSkn, elbo_and_grad (block branch :251-261), predict
   notebook_counts.npz          preconditioner-analysis.ipynb saved outputs (raw lines 101-103,142-144,183-185,224-226)
 """
 import os
@@ -268,6 +270,44 @@ def make_quadform():
         print("quadform", dname, {k: np.asarray(v).shape for k, v in out.items() if k.endswith("quad") or k.startswith("bw_c")})
 
 
+def make_block_step():
+    """BlockToeplitzGP natural-gradient step / predict and its block helpers on a small 2-D problem; index maps in 3-D."""
+    from ziggy.misc import util as zutil
+    for dname, dtype in DT.items():
+        torch.manual_seed(21)
+        grids = [(-5.7, 1.8, 14), (50., 55.5, 11)]
+        xgrids = [torch.linspace(lo, hi, m, dtype=dtype) for lo, hi, m in grids]
+        kern = get_kernel("matern32", dtype)
+        mod = zh.BlockToeplitzGP(kern, xgrids, num_obs=500, block_sizes=[13, 5], sig2_init=0.9, ell_init=0.7, dtype=dtype,
+                                 jitter_val=1e-3)
+        # a non-trivial (symmetric negative definite) theta2 so that the block algebra is exercised
+        A = 0.05 * torch.randn(mod.num_blocks, mod.block_size, mod.block_size, dtype=dtype)
+        mod.global_theta2.data = mod.global_theta2.data - A.matmul(A.transpose(-1, -2))
+        lo = torch.tensor([g[0] for g in grids], dtype=dtype); hi = torch.tensor([g[1] for g in grids], dtype=dtype)
+        xb = lo + (hi - lo) * torch.rand(8, 2, dtype=dtype)
+        yb = torch.randn(8, 1, dtype=dtype)
+        nb = 0.3 + 0.1 * torch.rand(8, 1, dtype=dtype)
+        th1 = mod.global_theta1.data.clone(); th2 = mod.global_theta2.data.clone()
+        elbo = mod.elbo_and_grad(xb, yb, nb, maxiter_cg=20)
+        mu, sig = mod.predict(xb, maxiter_cg=50)
+        with torch.no_grad():
+            Knm, _ = mod._make_grams(xb)
+            kn = mod.compute_kn(Knm, maxiter_cg=20)
+            qm, qS = mod.standard_variational_params()
+            lam = mod.get_lam(1 / nb ** 2, kn, bscale=500 / 8)
+            Sv = mod.block_diag_multiply(qS, kn)
+            knSkn = mod.compute_knSkn(kn, qS)
+            kl = mod.get_kl_to_prior(qm, qS)
+        idx3, _, _ = zutil.define_block_chunks([torch.arange(6), torch.arange(10), torch.arange(14)], [3, 5, 7])
+        np.savez_compressed(os.path.join(HERE, "block_step_%s.npz" % dname), grids=np.array(grids), x=xb.numpy(), y=yb.numpy(),
+                            noise_std=nb.numpy(), theta1=th1.numpy(), theta2=th2.numpy(), elbo=float(elbo),
+                            g1=mod.global_theta1.grad.numpy(), g2=mod.global_theta2.grad.numpy(), mu=mu.numpy(), sig=sig.numpy(),
+                            params=np.array([0.9, 0.7, 1e-3, 500]), block_sizes=np.array([13, 5]),
+                            block_idx=mod.block_idx.numpy(), kn=kn.numpy(), qm=qm.numpy(), qS=qS.numpy(), lam=lam.numpy(),
+                            Sv=Sv.numpy(), knSkn=knSkn.numpy(), kl=float(kl), block_idx_3d=idx3.numpy())
+        print("block_step", dname, float(elbo), mod.block_idx.shape)
+
+
 def make_notebook_counts():
     """Saved cell outputs of experiments-hip-gp/preconditioner-analysis.ipynb -- the only numbers the
     reference repo pins (unseeded RNG there => reproducible to a few iterations only)."""
@@ -283,6 +323,9 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "svi":
         make_svi_step()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "block":
+        make_block_step()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "quadform":
         make_quadform()
         sys.exit(0)
@@ -293,3 +336,4 @@ if __name__ == "__main__":
     make_compute_kn()
     make_cfg1()
     make_quadform()
+    make_block_step()

@@ -204,3 +204,39 @@ def test_toeplitz_quadform_and_inv_matmul_backward(dname, golden_dir):
     # InvMatmul.backward: left solves = K^-1 (dL/dsolves) are the reference's own right-hand-side gradient
     got = zo.inv_matmul_backward(g["bw_right_grad"], g["bw_solves"])
     assert relerr(got, g["bw_column_grad"]) < tol
+
+
+@pytest.mark.parametrize("dname", ["f32", "f64"])
+def test_block_family(dname, golden_dir):
+    """BlockToeplitzGP (hipgp.py:527-690): index maps bit-exact (util.py:79-117, also the host-side drop-in
+    hipgp_b200.util.define_block_chunks), get_lam / block_diag_multiply / KL / natural-gradient step vs the reference."""
+    from hipgp_b200.util import define_block_chunks
+    g = np.load(os.path.join(golden_dir, "block_step_%s.npz" % dname))
+    dtype = DT[dname]
+    assert np.array_equal(zo.define_block_chunks([26, 20], [13, 5]), g["block_idx"])
+    assert np.array_equal(zo.define_block_chunks([6, 10, 14], [3, 5, 7]), g["block_idx_3d"])
+    i2, to_b, from_b = define_block_chunks([torch.arange(26), torch.arange(20)], [13, 5])
+    i3, _, _ = define_block_chunks([torch.arange(6), torch.arange(10), torch.arange(14)], [3, 5, 7])
+    assert i2.dtype == torch.int64 and np.array_equal(i2.numpy(), g["block_idx"]) and np.array_equal(i3.numpy(), g["block_idx_3d"])
+    v = torch.randn(3, 520)
+    assert torch.equal(from_b(to_b(v)), v) and torch.equal(to_b(v), v[..., torch.from_numpy(g["block_idx"])])
+    with pytest.raises(AssertionError):
+        define_block_chunks([torch.arange(26), torch.arange(20)], [12, 5])
+    idx = g["block_idx"]
+    kn = torch.from_numpy(g["kn"]); qS = torch.from_numpy(g["qS"]); qm = torch.from_numpy(g["qm"])
+    nb = torch.from_numpy(g["noise_std"])
+    tol = TIGHT[dname] * 50
+    assert relerr(zo.block_get_lam(idx, 1 / nb ** 2, kn, bscale=500 / 8).numpy(), g["lam"]) < tol
+    assert relerr(zo.block_diag_multiply(idx, qS, kn).numpy(), g["Sv"]) < tol
+    assert abs(float(zo.block_kl_to_standard(qm, qS)) - float(g["kl"])) <= tol * abs(float(g["kl"]))
+    xgrids = [torch.linspace(lo, hi, int(m), dtype=dtype) for lo, hi, m in g["grids"]]
+    sig2 = torch.tensor(float(g["params"][0]), dtype=dtype); ell = torch.tensor(float(g["params"][1]), dtype=dtype)
+    kfun = kernel_fn("matern32", sig2, ell)
+    x = torch.from_numpy(g["x"])
+    Knm = kfun(x, zo.meshgrid_points(xgrids))
+    elbo, g1, g2, kn2, qm2, qS2 = zo.block_elbo_and_grad(xgrids, kfun, idx, Knm, sig2 * x.new_ones(x.shape[0]), torch.from_numpy(g["y"]),
+                                                         nb, torch.from_numpy(g["theta1"]), torch.from_numpy(g["theta2"]),
+                                                         num_obs=int(g["params"][3]), maxiter_cg=20, jitter_val=float(g["params"][2]))
+    assert relerr(kn2.numpy(), g["kn"]) < tol and relerr(qm2.numpy(), g["qm"]) < tol * 10
+    assert abs(float(elbo) - float(g["elbo"])) <= tol * 10 * abs(float(g["elbo"]))
+    assert relerr(g1.numpy(), g["g1"]) < tol * 10 and relerr(g2.numpy(), g["g2"]) < tol * 10
