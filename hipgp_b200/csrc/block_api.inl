@@ -6,78 +6,124 @@
 //   out[b, idx[k,i]] = sum_j S[k][i][j] v[b, idx[k,j]]                                          (block_diag_multiply, :640-652)
 namespace hipgp {
 
-// one CTA per block; rows of k_n stream through shared memory in chunks of `rchunk`, partial sums live in `out`
+// ---- shared 64 x 64 register-tiled contraction:  C[m][n] += sum_k X[k][m] * Y[k][n]  with both operands k-major in
+// shared memory (16 x 16 threads, 4 x 4 outputs each: two 16-byte shared loads per 16 FMAs)
+constexpr int BK_TILE = 64, BK_KT = 16, BK_LD = 68;
 template <class T>
-__global__ void __launch_bounds__(256) block_lam_kernel(const T* __restrict__ kn, const T* __restrict__ w,
-                                                        const long long* __restrict__ idx, long B, long E, int bs, int rchunk,
-                                                        T scale, T diag, T* __restrict__ out) {
-    HIPGP_DYN_SMEM(smem_raw);
-    long long* sidx = reinterpret_cast<long long*>(smem_raw);
-    T* A = reinterpret_cast<T*>(sidx + bs);              // [rchunk][bs]
-    T* ws = A + (size_t)rchunk * bs;                      // [rchunk]
-    const long k = blockIdx.x;
-    const int tid = threadIdx.x, nt = blockDim.x;
-    for (int i = tid; i < bs; i += nt) sidx[i] = idx[k * bs + i];
-    __syncthreads();
-    T* o = out + (size_t)k * bs * bs;
-    for (long r0 = 0; r0 < B; r0 += rchunk) {
-        const int nr = (int)((B - r0) < rchunk ? (B - r0) : rchunk);
-        for (int t = tid; t < nr * bs; t += nt) {
-            const int n = t / bs, i = t - n * bs;
-            A[(size_t)n * bs + i] = kn[(size_t)(r0 + n) * E + sidx[i]];
-        }
-        for (int n = tid; n < nr; n += nt) ws[n] = w[r0 + n];
-        __syncthreads();
-        const bool last = r0 + nr >= B;
-        for (int t = tid; t < bs * bs; t += nt) {
-            const int i = t / bs, j = t - i * bs;
-            T acc = r0 == 0 ? (T)0 : o[t];
-            for (int n = 0; n < nr; ++n) acc += (ws[n] * A[(size_t)n * bs + i]) * A[(size_t)n * bs + j];
-            if (last) acc = scale * acc + (i == j ? diag : (T)0);
-            o[t] = acc;
-        }
-        __syncthreads();
+__device__ __forceinline__ void block_tile_fma(const T* __restrict__ Xs, const T* __restrict__ Ys, int kt, int m0, int n0,
+                                               T (&acc)[4][4]) {
+    for (int kk = 0; kk < kt; ++kk) {
+        T xa[4], yb[4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) { xa[a] = Xs[kk * BK_LD + m0 + a]; yb[a] = Ys[kk * BK_LD + n0 + a]; }
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) acc[a][b] += xa[a] * yb[b];
     }
 }
 
-// grid (num_blocks, ceil(B / 8)); a warp owns output row i of the block, its lanes stride over j (coalesced S reads)
+// grid (num_blocks, tile pairs ti <= tj): lam tile = sum_n (w_n kn[n, idx[i]]) kn[n, idx[j]], rows gathered through the
+// index map 16 at a time; accumulators stay in registers over the whole minibatch; the mirror tile is written too
+template <class T>
+__global__ void __launch_bounds__(256) block_lam_kernel(const T* __restrict__ kn, const T* __restrict__ w,
+                                                        const long long* __restrict__ idx, long B, long E, int bs, int ntile,
+                                                        T scale, T diag, T* __restrict__ out) {
+    __align__(16) __shared__ T Xs[BK_KT * BK_LD];
+    __align__(16) __shared__ T Ys[BK_KT * BK_LD];
+    __shared__ long long si[BK_TILE], sj[BK_TILE];
+    const long k = blockIdx.x;
+    int ti = 0, tj = 0;
+    {   // pair index -> (ti <= tj)
+        int p = blockIdx.y;
+        while (p >= ntile - ti) { p -= ntile - ti; ++ti; }
+        tj = ti + p;
+    }
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4, m0 = ty * 4, n0 = tx * 4;
+    const int i0 = ti * BK_TILE, j0 = tj * BK_TILE;
+    if (tid < BK_TILE) si[tid] = i0 + tid < bs ? idx[k * bs + i0 + tid] : -1;
+    else if (tid < 2 * BK_TILE) sj[tid - BK_TILE] = j0 + tid - BK_TILE < bs ? idx[k * bs + j0 + tid - BK_TILE] : -1;
+    __syncthreads();
+    T acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = (T)0;
+    for (long r0 = 0; r0 < B; r0 += BK_KT) {
+        const int kt = (int)((B - r0) < BK_KT ? (B - r0) : BK_KT);
+        for (int t = tid; t < BK_KT * BK_TILE; t += 256) {
+            const int n = t / BK_TILE, m = t - n * BK_TILE;
+            T x = (T)0, y = (T)0;
+            if (n < kt) {
+                const T* row = kn + (size_t)(r0 + n) * E;
+                if (si[m] >= 0) x = w[r0 + n] * row[si[m]];
+                if (sj[m] >= 0) y = row[sj[m]];
+            }
+            Xs[n * BK_LD + m] = x; Ys[n * BK_LD + m] = y;
+        }
+        __syncthreads();
+        block_tile_fma<T>(Xs, Ys, kt, m0, n0, acc);
+        __syncthreads();
+    }
+    T* o = out + (size_t)k * bs * bs;
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const int i = i0 + m0 + a, j = j0 + n0 + b;
+            if (i < bs && j < bs) {
+                const T v = scale * acc[a][b] + (i == j ? diag : (T)0);
+                o[(size_t)i * bs + j] = v;
+                if (ti != tj) o[(size_t)j * bs + i] = v;
+            }
+        }
+}
+
+// grid (num_blocks, row tiles of the block, tiles of 64 right-hand sides): out[b, idx[i]] = sum_j S[k][i][j] v[b, idx[j]]
 template <class T>
 __global__ void __launch_bounds__(256) block_diag_multiply_kernel(const T* __restrict__ S, const T* __restrict__ v,
                                                                   const long long* __restrict__ idx, long B, long E, int bs,
                                                                   T* __restrict__ out) {
-    constexpr int BCH = 8;
-    HIPGP_DYN_SMEM(smem_raw);
-    long long* sidx = reinterpret_cast<long long*>(smem_raw);
-    T* vs = reinterpret_cast<T*>(sidx + bs);             // [BCH][bs]
+    __align__(16) __shared__ T Xs[BK_KT * BK_LD];       // X[jj][m] = S[k][i0 + m][j0 + jj]
+    __align__(16) __shared__ T Ys[BK_KT * BK_LD];       // Y[jj][n] = v[b0 + n][idx[j0 + jj]]
+    __shared__ long long sj[BK_KT];
     const long k = blockIdx.x;
-    const long b0 = (long)blockIdx.y * BCH;
-    const int nb = (int)((B - b0) < BCH ? (B - b0) : BCH);
-    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = nt >> 5;
-    for (int i = tid; i < bs; i += nt) sidx[i] = idx[k * bs + i];
-    __syncthreads();
-    for (int t = tid; t < BCH * bs; t += nt) {
-        const int b = t / bs, j = t - b * bs;
-        vs[t] = b < nb ? v[(size_t)(b0 + b) * E + sidx[j]] : (T)0;
-    }
-    __syncthreads();
+    const int i0 = blockIdx.y * BK_TILE;
+    const long b0 = (long)blockIdx.z * BK_TILE;
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4, m0 = ty * 4, n0 = tx * 4;
     const T* Sk = S + (size_t)k * bs * bs;
-    for (int i = warp; i < bs; i += nwarp) {
-        T acc[BCH];
+    T acc[4][4];
 #pragma unroll
-        for (int b = 0; b < BCH; ++b) acc[b] = (T)0;
-        for (int j = lane; j < bs; j += 32) {
-            const T s = Sk[(size_t)i * bs + j];
+    for (int a = 0; a < 4; ++a)
 #pragma unroll
-            for (int b = 0; b < BCH; ++b) acc[b] += s * vs[b * bs + j];
+        for (int b = 0; b < 4; ++b) acc[a][b] = (T)0;
+    for (int j0 = 0; j0 < bs; j0 += BK_KT) {
+        const int kt = bs - j0 < BK_KT ? bs - j0 : BK_KT;
+        if (tid < BK_KT) sj[tid] = tid < kt ? idx[k * bs + j0 + tid] : -1;
+        __syncthreads();
+        for (int t = tid; t < BK_KT * BK_TILE; t += 256) {
+            const int jj = t & (BK_KT - 1), m = t >> 4;          // jj fastest: coalesced along a row of S / the gathered v
+            T x = (T)0, y = (T)0;
+            if (jj < kt) {
+                if (i0 + m < bs) x = Sk[(size_t)(i0 + m) * bs + j0 + jj];
+                if (b0 + m < B) y = v[(size_t)(b0 + m) * E + sj[jj]];
+            }
+            Xs[jj * BK_LD + m] = x; Ys[jj * BK_LD + m] = y;
         }
+        __syncthreads();
+        block_tile_fma<T>(Xs, Ys, kt, m0, n0, acc);
+        __syncthreads();
+    }
 #pragma unroll
-        for (int b = 0; b < BCH; ++b) {
-            T a = acc[b];
-            for (int m = 16; m >= 1; m >>= 1) a += __shfl_xor_sync(0xffffffffu, a, m);
-            acc[b] = a;
+    for (int a = 0; a < 4; ++a) {
+        const int i = i0 + m0 + a;
+        if (i >= bs) continue;
+        const long long col = idx[k * bs + i];
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const long bb = b0 + n0 + b;
+            if (bb < B) out[(size_t)bb * E + col] = acc[a][b];
         }
-        if (lane == 0)
-            for (int b = 0; b < nb; ++b) out[(size_t)(b0 + b) * E + sidx[i]] = acc[b];
     }
 }
 
@@ -93,11 +139,8 @@ static void block_lam(const void* kn, const void* w, const void* idx, long B, lo
                       double diag, void* out, cudaStream_t s) {
     block_check(idx, B, E, nblk, bs);
     if (!out || (B > 0 && (!kn || !w))) throw Error("null pointer");
-    long rchunk = (long)(64 * 1024 / (sizeof(T) * (size_t)bs));
-    rchunk = std::max<long>(1, std::min<long>(rchunk, std::max<long>(B, 1)));
-    const size_t smem = sizeof(long long) * (size_t)bs + sizeof(T) * (size_t)(rchunk * bs + rchunk);
     auto k = block_lam_kernel<T>;
-    if (smem > 40 * 1024) HIPGP_SET_MAX_SMEM(k, smem);
+    const int ntile = (int)((bs + BK_TILE - 1) / BK_TILE);
     if (B == 0) {                                          // empty minibatch: lam = diag * I
         std::vector<T> h((size_t)nblk * bs * bs, (T)0);
         for (long q = 0; q < nblk; ++q) for (long i = 0; i < bs; ++i) h[(size_t)q * bs * bs + i * bs + i] = (T)diag;
@@ -105,9 +148,14 @@ static void block_lam(const void* kn, const void* w, const void* idx, long B, lo
         CK(cudaStreamSynchronize(s));
         return;
     }
-    HIPGP_LAUNCH(k, dim3((unsigned)nblk), dim3(256), smem, s, (const T*)kn, (const T*)w, (const long long*)idx, B, E, (int)bs,
-                 (int)rchunk, (T)scale, (T)diag, (T*)out);
-    CK_LAUNCH();
+    const long npair = (long)ntile * (ntile + 1) / 2;
+    for (long k0 = 0; k0 < nblk; k0 += 1L << 30) {
+        const long nk = std::min<long>(nblk - k0, 1L << 30);
+        HIPGP_LAUNCH(k, dim3((unsigned)nk, (unsigned)npair), dim3(256), 0, s, (const T*)kn, (const T*)w,
+                     (const long long*)idx + (size_t)k0 * bs, B, E, (int)bs, ntile, (T)scale, (T)diag,
+                     (T*)out + (size_t)k0 * bs * bs);
+        CK_LAUNCH();
+    }
 }
 
 template <class T>
@@ -116,12 +164,11 @@ static void block_diag_multiply(const void* S, const void* v, const void* idx, l
     block_check(idx, B, E, nblk, bs);
     if (B == 0) return;
     if (!S || !v || !out) throw Error("null pointer");
-    const size_t smem = sizeof(long long) * (size_t)bs + sizeof(T) * (size_t)(8 * bs);
     auto k = block_diag_multiply_kernel<T>;
-    if (smem > 40 * 1024) HIPGP_SET_MAX_SMEM(k, smem);
-    for (long b0 = 0; b0 < B; b0 += 8 * 65535L) {          // grid.y limit
-        const long nb = std::min<long>(B - b0, 8 * 65535L);
-        HIPGP_LAUNCH(k, dim3((unsigned)nblk, (unsigned)((nb + 7) / 8)), dim3(256), smem, s, (const T*)S,
+    const unsigned nti = (unsigned)((bs + BK_TILE - 1) / BK_TILE);
+    for (long b0 = 0; b0 < B; b0 += BK_TILE * 65535L) {    // grid.z limit
+        const long nb = std::min<long>(B - b0, BK_TILE * 65535L);
+        HIPGP_LAUNCH(k, dim3((unsigned)nblk, nti, (unsigned)((nb + BK_TILE - 1) / BK_TILE)), dim3(256), 0, s, (const T*)S,
                      (const T*)v + (size_t)b0 * E, (const long long*)idx, nb, E, (int)bs, (T*)out + (size_t)b0 * E);
         CK_LAUNCH();
     }

@@ -294,7 +294,7 @@ class BlockToeplitzGP(MeanFieldToeplitzGP):
     def standard_variational_params(self):
         if self.parameterization == 'standard':
             return self.global_m, self.global_S
-        S = torch.inverse(-2 * self.global_theta2.data)                 # batched small inverses (library call)
+        S = self._spd_inverse(-2 * self.global_theta2.data)
         m = self.block_diag_multiply(S, self.global_theta1.data.t()).t()
         return m, S
 
@@ -305,8 +305,20 @@ class BlockToeplitzGP(MeanFieldToeplitzGP):
         assert Sv.shape == (bsz, self.num_blocks * self.block_size), Sv.shape
         return Sv
 
+    @staticmethod
+    def _spd_inverse(A):
+        """batched inverse of the (num_blocks, bs, bs) precision blocks (library calls on small dense matrices).  The
+        blocks are symmetric positive definite whenever q(u) is a proper Gaussian, so A^-1 = L^-T L^-1 from one batched
+        Cholesky (5x faster than the LU route of `torch.inverse`, hipgp.py:634); anything else falls back to LU."""
+        Lc, info = torch.linalg.cholesky_ex(A)
+        if bool((info != 0).any()):
+            return torch.inverse(A)
+        eye = torch.eye(A.shape[-1], dtype=A.dtype, device=A.device).expand_as(A)
+        Li = torch.linalg.solve_triangular(Lc, eye, upper=False)
+        return Li.transpose(-1, -2) @ Li
+
     def get_S_from_lam(self, lam):
-        return torch.inverse(lam)
+        return self._spd_inverse(lam)
 
     def compute_knSkn(self, kn, qS):
         return row_dot(kn, self.block_diag_multiply(qS, kn))
