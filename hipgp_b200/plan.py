@@ -289,3 +289,32 @@ def row_dot(a, b):
         L.check(lib, lib.hipgp_vec_dot(_DT[a.dtype], C.c_void_p(a.data_ptr()), C.c_void_p(b.data_ptr()),
                                        C.c_void_p(out.data_ptr()), B, M, _stream_ptr(a.device)))
     return out.to(a.dtype)
+
+
+class _ToeplitzMatvec(torch.autograd.Function):
+    """The four structured matvecs as differentiable LINEAR maps of their vector argument, like the torch ops of the
+    reference (toeplitz_tensor.py:70-125): K and the C^-1 block are symmetric, R^T and R are each other's transpose.
+    The dependence on the Toeplitz column (through the spectrum) is NOT differentiated here -- a graph that asks for it
+    fails loudly instead of returning a gradient with that term missing (InvMatmul handles the column for the solve)."""
+    _ADJOINT = {L.MV_K: L.MV_K, L.MV_CINV: L.MV_CINV, L.MV_RT: L.MV_R, L.MV_R: L.MV_RT}
+
+    @staticmethod
+    def forward(ctx, plan, column, vec, mode):
+        ctx.plan, ctx.mode = plan, mode
+        return plan.matvec(mode, vec)
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        if ctx.needs_input_grad[1]:
+            raise NotImplementedError("hipgp_b200: gradient of a structured matvec with respect to the Toeplitz column "
+                                      "(kernel hyper-parameters through the spectrum, toeplitz_tensor.py:70-125) is not built; "
+                                      "InvMatmul.backward covers the column gradient of the solve")
+        gv = ctx.plan.matvec(_ToeplitzMatvec._ADJOINT[ctx.mode], grad_output.contiguous()) if ctx.needs_input_grad[2] else None
+        return None, None, gv, None
+
+
+def matvec_autograd(plan, mode, vec, column=None):
+    """plan.matvec that takes part in autograd when the vector (or the column) requires a gradient"""
+    if torch.is_grad_enabled() and (vec.requires_grad or (column is not None and column.requires_grad)):
+        return _ToeplitzMatvec.apply(plan, column, vec, mode)
+    return plan.matvec(mode, vec)

@@ -4,7 +4,7 @@ import torch
 from torch import nn
 
 from . import _lib as L
-from .plan import Plan
+from .plan import Plan, matvec_autograd
 from .cg import conj_grad
 
 _MODES = {"gram": L.MV_K, "RTv": L.MV_RT, "Rv": L.MV_R, "circ_inv": L.MV_CINV}
@@ -58,7 +58,7 @@ class ToeplitzMatmul(nn.Module):
         """vec: bsz x M (bsz x M' for "Rv"); multiply_type in gram | RTv | Rv | circ_inv (toeplitz_expanded.py:139-189)"""
         if multiply_type not in _MODES:
             raise NotImplementedError("gram|RTv|Rv|circ_inv")
-        return self._plan.matvec(_MODES[multiply_type], vec.reshape(vec.shape[0], -1))
+        return matvec_autograd(self._plan, _MODES[multiply_type], vec.reshape(vec.shape[0], -1))
 
     # methods the fused CG path recognises
     def _matmul_by_K(self, vec):

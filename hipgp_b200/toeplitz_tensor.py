@@ -10,7 +10,7 @@ import numpy as np
 import torch
 
 from . import _lib as L
-from .plan import Plan
+from .plan import Plan, matvec_autograd
 from ._inv_matmul import InvMatmul
 from .cg import conj_grad2
 
@@ -80,16 +80,16 @@ class ToeplitzTensor:
 
     # ---- matvecs -----------------------------------------------------------------------------------
     def _matmul_by_K(self, vec):
-        return self._plan.matvec(L.MV_K, vec)
+        return matvec_autograd(self._plan, L.MV_K, vec, self.column)
 
     def _matmul_by_RT(self, vec):
-        return self._plan.matvec(L.MV_RT, vec)
+        return matvec_autograd(self._plan, L.MV_RT, vec, self.column)
 
     def _matmul_by_R(self, vec):
-        return self._plan.matvec(L.MV_R, vec.reshape(vec.shape[0], -1))
+        return matvec_autograd(self._plan, L.MV_R, vec.reshape(vec.shape[0], -1), self.column)
 
     def _matmul_by_Cinv(self, vec):
-        return self._plan.matvec(L.MV_CINV, vec)
+        return matvec_autograd(self._plan, L.MV_CINV, vec, self.column)
 
     # ---- construction helpers (same names as the reference) ------------------------------------
     def toeplitz_gram(self, xgrids, kernel, jitter_val):

@@ -217,3 +217,37 @@ def test_batched_pcg_nan_row_is_isolated():
     assert info["iters"] == 15                                  # NaN < tol is False: never "converged"
     x1 = plan.pcg(b[[0, 2]], maxiter=15, tol=1e-8)
     assert relerr(x[[0, 2]], x1.cpu().numpy()) < 1e-12
+
+
+def test_matvecs_are_differentiable_linear_maps(golden_dir):
+    """The reference's matvecs are torch ops, hence differentiable in their vector argument (toeplitz_tensor.py:70-125);
+    the drop-in matches: K and C^-1 are their own adjoints, R^T and R each other's; compute_kn with a differentiable
+    K_nm back-propagates through R^T and the PCG solve; a graph that needs the COLUMN gradient of a matvec fails loudly."""
+    from hipgp_b200.toeplitz_tensor import ToeplitzTensor
+    g = np.load(os.path.join(golden_dir, "toeplitz_2d_25x25_matern52_f64.npz"), allow_pickle=True)
+    dtype = torch.float64
+    xgrids = [torch.linspace(lo, hi, int(m), dtype=dtype, device=DEV) for lo, hi, m in g["grids"]]
+    kern = make_kernel("matern52", dtype)
+    tt = ToeplitzTensor(xgrids, lambda x, y: kern.forward(x, y, params=(float(g["sig2"]), float(g["ell"]))),
+                        batch_shape=None, jitter_val=float(g["jitter"]))
+    v = torch.from_numpy(g["v"]).to(DEV); w = torch.from_numpy(g["w"]).to(DEV)
+    for fwd, adj, x, ct in ((tt._matmul_by_K, tt._matmul_by_K, v, v.flip(0)), (tt._matmul_by_Cinv, tt._matmul_by_Cinv, v, v.flip(0)),
+                            (tt._matmul_by_RT, tt._matmul_by_R, v, w), (tt._matmul_by_R, tt._matmul_by_RT, w, v)):
+        xr = x.clone().requires_grad_(True)
+        out = fwd(xr)
+        assert out.requires_grad
+        (out * ct).sum().backward()
+        assert relerr(xr.grad, adj(ct).cpu().numpy()) < 1e-12
+    assert not tt._matmul_by_K(v).requires_grad                    # plain calls stay outside autograd
+    # d/dKnm sum(W * R^T K^-1 Knm) = K^-1 (R W)
+    Knm = v[:2].clone().requires_grad_(True)
+    d0 = tt.inv_matmul(Knm, do_precond=True, maxiter=80, tol=1e-13)
+    kn = tt._matmul_by_RT(d0)
+    (kn * w[:2]).sum().backward()
+    want = tt._solve(tt._matmul_by_R(w[:2]), maxiter=80, tol=1e-13)
+    assert relerr(Knm.grad, want.cpu().numpy()) < 1e-8
+    # the column gradient of a matvec is not built: loud failure, not a silently incomplete gradient
+    tt.column.requires_grad_(True)
+    out = tt._matmul_by_RT(v)
+    with pytest.raises(NotImplementedError, match="Toeplitz column"):
+        out.sum().backward()
