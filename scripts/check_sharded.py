@@ -1,4 +1,4 @@
-"""Run under torchrun with N >= 2 GPUs: the sharded mean-field step (packed all-reduce) must give every rank the same
+"""Run under torchrun with N >= 2 GPUs (optional argument: block): the sharded natural-gradient step (packed all-reduce) must give every rank the same
 gradients as the unsharded step computed locally on rank 0's GPU."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -11,7 +11,12 @@ dist.init_process_group("nccl", device_id=dev)
 dtype = torch.float64
 xg = [torch.linspace(-5.7, 1.8, 60, dtype=dtype), torch.linspace(50, 55.5, 44, dtype=dtype)]
 torch.manual_seed(1)
-mod = hh.MeanFieldToeplitzGP(hk.Matern(nu=1.5, dtype=dtype), xg, num_obs=10000, sig2_init=1.0, ell_init=0.4, dtype=dtype).cuda_params(local)
+family = sys.argv[1] if len(sys.argv) > 1 else "mean-field"
+if family == "block":      # M' = 118 x 86 -> 59 x 43-point blocks
+    mod = hh.BlockToeplitzGP(hk.Matern(nu=1.5, dtype=dtype), xg, num_obs=10000, block_sizes=[59, 43], sig2_init=1.0, ell_init=0.4,
+                             dtype=dtype).cuda_params(local)
+else:
+    mod = hh.MeanFieldToeplitzGP(hk.Matern(nu=1.5, dtype=dtype), xg, num_obs=10000, sig2_init=1.0, ell_init=0.4, dtype=dtype).cuda_params(local)
 rs = np.random.RandomState(0)
 x = torch.tensor(np.stack([rs.uniform(-5.7, 1.8, 37), rs.uniform(50, 55.5, 37)], 1), dtype=dtype, device=dev)
 y = torch.tensor(rs.randn(37, 1), dtype=dtype, device=dev); nb = torch.full((37, 1), 0.3, dtype=dtype, device=dev)
@@ -22,6 +27,6 @@ err = max(float((g1s - mod.global_theta1.grad).abs().max() / mod.global_theta1.g
           float((g2s - mod.global_theta2.grad).abs().max() / mod.global_theta2.grad.abs().max()), abs(float(e_sh - e_full)))
 t = torch.tensor([err], device=dev, dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX)
 if rank == 0:
-    print("sharded vs unsharded max rel diff over ranks: %.3e (world %d)" % (t.item(), world))
+    print("%s family: sharded vs unsharded max rel diff over ranks: %.3e (world %d)" % (family, t.item(), world))
     assert t.item() < 1e-9
 dist.destroy_process_group()
