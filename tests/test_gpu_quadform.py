@@ -94,3 +94,20 @@ def test_quadform_medium_and_full_sizes(dims, S):
         got = plan.toeplitz_quadform(torch.from_numpy(u).to(DEV, DT[dname]), torch.from_numpy(v).to(DEV, DT[dname]))
         assert relerr(got, want) < TOL[dname], (dname, relerr(got, want))
         del plan
+
+
+def test_quadform_random_small_shapes():
+    """carry-pattern gather on many small grids (extents down to 2, odd / prime extents, embeddings with L = 2m - 1 where a
+    skipped out-of-range lag would alias onto a valid one), fp64 against the flattened correlation."""
+    rng = np.random.default_rng(7)
+    shapes = [(2,), (3,), (2, 2), (2, 3), (3, 2), (2, 2, 2), (5, 2, 3), (2, 7, 2), (3, 3, 3), (13, 2), (2, 13)]
+    for _ in range(14):
+        D = int(rng.integers(1, 4))
+        shapes.append(tuple(int(rng.integers(2, 24)) for _ in range(D)))
+    for dims in shapes:
+        M = int(np.prod(dims))
+        S = int(rng.integers(1, 4))
+        u = rng.standard_normal((S, M)); v = rng.standard_normal((S, M))
+        plan = unit_plan(dims, torch.float64)
+        got = plan.toeplitz_quadform(torch.from_numpy(u).to(DEV), torch.from_numpy(v).to(DEV))
+        assert relerr(got, flat_quadform(u, v)) < 1e-11, dims
