@@ -106,6 +106,20 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(reasons), "samples": len(sm), "window": getattr(self, "window", "")}
 
 
+def host_threads():
+    """threads for the CPU arm: the box's physical cores (what torch picks by default), within this process's affinity"""
+    try:
+        import psutil
+        phys = psutil.cpu_count(logical=False) or os.cpu_count() or 1
+    except Exception:
+        phys = os.cpu_count() or 1
+    try:
+        phys = min(phys, len(os.sched_getaffinity(0)))
+    except Exception:
+        pass
+    return max(1, int(phys))
+
+
 def oracle_step(B, threads=None):
     """One bounded CPU step: oracle PCG (20 iterations) on B right-hand sides of the 10^6-point grid."""
     import torch
@@ -133,8 +147,9 @@ def run_reference(args):
     if rank != 0:
         return
     B = 1
-    cores = torch.get_num_threads()
-    step, t_setup = oracle_step(B)
+    cores = host_threads()
+    torch.set_num_threads(cores)               # torchrun exports OMP_NUM_THREADS=1: the CPU arm still uses every core
+    step, t_setup = oracle_step(B, threads=cores)
     for _ in range(min(args.warmup, 1)):
         step()
     ts = [step() for _ in range(args.steps)]
@@ -232,7 +247,7 @@ def run_gpu(args):
 
     # fp64 and B=1 companions (not the headline; same step definition)
     extra = {}
-    if rank == 0 and not args.quick:
+    if world == 1 and not args.quick:          # single-GPU run only: `timed` synchronises all ranks
         b1 = b[:1].contiguous()
         for _ in range(3):
             plan.pcg(b1, maxiter=MAXITER, tol=TOL)
