@@ -12,27 +12,32 @@ from torch.autograd import Function
 
 
 class InvMatmul(Function):
+    """K^-1 R as an autograd node; argument order and meaning as in the reference (`_inv_matmul.py:10`)."""
+
     @staticmethod
     def forward(ctx, toeplitz_tensor, column, right_tensor, do_precond, maxiter, tol):
-        assert right_tensor.ndimension() == 2, right_tensor.ndimension()
-        ctx.toeplitz_tensor = toeplitz_tensor
+        if right_tensor.ndimension() != 2:
+            raise AssertionError(right_tensor.ndimension())
+        ctx.op = toeplitz_tensor
+        ctx.cg_args = (int(maxiter), float(tol))
         with torch.no_grad():
-            solves = toeplitz_tensor._solve(right_tensor, do_precond=do_precond, maxiter=maxiter, tol=tol, callback=None)
-        ctx.maxiter, ctx.tol = int(maxiter), float(tol)
-        ctx.save_for_backward(solves)
-        return solves
+            x = toeplitz_tensor._solve(right_tensor, do_precond=do_precond, maxiter=ctx.cg_args[0], tol=ctx.cg_args[1],
+                                       callback=None)
+        ctx.save_for_backward(x)
+        return x
 
     @staticmethod
     def backward(ctx, grad_output):
-        right_solves, = ctx.saved_tensors
-        left_solves = None
-        if any(ctx.needs_input_grad):
-            left_solves = InvMatmul.apply(ctx.toeplitz_tensor, ctx.toeplitz_tensor.column, grad_output.contiguous(), True,
-                                          ctx.maxiter, ctx.tol)
-        column_grad = None
-        if ctx.needs_input_grad[1]:
+        (x,) = ctx.saved_tensors
+        want_column, want_rhs = ctx.needs_input_grad[1], ctx.needs_input_grad[2]
+        if not (want_column or want_rhs):
+            return None, None, None, None, None, None
+        op = ctx.op
+        maxiter, tol = ctx.cg_args
+        # left solves K^-1 g, always preconditioned (`_inv_matmul.py:35-37`); differentiable again for double backward
+        lhs = InvMatmul.apply(op, op.column, grad_output.contiguous(), True, maxiter, tol)
+        g_column = None
+        if want_column:
             with torch.no_grad():
-                column_grad = ctx.toeplitz_tensor._plan.toeplitz_quadform(left_solves, right_solves, scale=-1.0)
-            column_grad = column_grad.view(ctx.toeplitz_tensor.column.shape)
-        right_grad = left_solves if ctx.needs_input_grad[2] else None
-        return None, column_grad, right_grad, None, None, None
+                g_column = op._plan.toeplitz_quadform(lhs, x, scale=-1.0).view(op.column.shape)
+        return None, g_column, (lhs if want_rhs else None), None, None, None
