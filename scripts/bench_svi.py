@@ -1,6 +1,6 @@
 """BASELINE config 3/4 shaped SVI benchmark: mean-field natural-gradient minibatch steps with the observations of each
 minibatch sharded over the ranks (one packed all-reduce per step).  Run under torchrun for N > 1:
-    python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 scripts/bench_svi.py [cfg3|cfg4] [steps]
+    python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 scripts/bench_svi.py [cfg3|cfg4] [steps] [mean-field|block]
 Prints one JSON line from rank 0.  cfg3: 300x300 grid, Matern-3/2, point observations (UK-housing shape);
 cfg4: 128x128x64 grid, SqExp analytic line integrals from the origin (dust-map shape)."""
 import json, os, sys, time
@@ -12,6 +12,7 @@ from hipgp_b200 import hipgp as hh, kernels as hk
 
 cfg = sys.argv[1] if len(sys.argv) > 1 else "cfg3"
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 20
+family = sys.argv[3] if len(sys.argv) > 3 else "mean-field"
 world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
 torch.cuda.set_device(local); dev = torch.device("cuda", local)
 if world > 1:
@@ -36,7 +37,12 @@ else:
     # about the hot path
     tab = np.stack([np.linspace(0, 5, 50), np.zeros(50), np.linspace(1, 0.1, 50)])
     kern._diag_interp = hk.KernelDoublyDiagInterpolator(kern, table=tab)
-mod = hh.MeanFieldToeplitzGP(kern, xgrids, num_obs=nobs, sig2_init=sig2, ell_init=ell, dtype=dtype, jitter_val=1e-3).cuda_params(local)
+if family == "block":      # neighbouring chunks of the whitened grid: 13x13 of 598x598 (cfg3), 2x2x2 of 254x254x126 (cfg4)
+    blocks = [13, 13] if cfg == "cfg3" else [2, 2, 2]
+    mod = hh.BlockToeplitzGP(kern, xgrids, num_obs=nobs, block_sizes=blocks, sig2_init=sig2, ell_init=ell, dtype=dtype,
+                             jitter_val=1e-3).cuda_params(local)
+else:
+    mod = hh.MeanFieldToeplitzGP(kern, xgrids, num_obs=nobs, sig2_init=sig2, ell_init=ell, dtype=dtype, jitter_val=1e-3).cuda_params(local)
 opt = torch.optim.SGD([mod.global_theta1, mod.global_theta2], lr=1e-4)   # random synthetic targets: keep the iteration tame
 Xh = torch.from_numpy(X).to(dtype).pin_memory(); Yh = torch.from_numpy(Y).to(dtype).pin_memory(); Nh = torch.from_numpy(NS).to(dtype).pin_memory()
 
@@ -61,7 +67,7 @@ if world > 1:
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
 if rank == 0:
     t = ms.item() / steps / 1e3
-    print(json.dumps({"bench": "svi_minibatch_step", "config": cfg, "n_gpus": world, "batch_size": bsz, "maxiter_cg": 20, "dtype": "f32",
+    print(json.dumps({"bench": "svi_minibatch_step", "config": cfg, "family": family, "n_gpus": world, "batch_size": bsz, "maxiter_cg": 20, "dtype": "f32",
                       "s_per_step": t, "obs_per_s": bsz / t, "epoch_s_extrapolated": nobs / bsz * t, "elbo_last": float(el),
                       "M": mod.M, "Mprime": mod.Mprime, "embedding": list(mod.make_Kmm()._plan.embedding()[0])}))
 if world > 1:
