@@ -35,9 +35,16 @@ def _worker(rank, world, port, out):
         w1 = torch.randn(B, dtype=torch.float64); w2 = torch.rand(B, dtype=torch.float64)
         sl = hdist.shard_slice(B)
         dm = (w1[sl, None] * kn[sl]).sum(0); lam = (w2[sl, None] * kn[sl] ** 2).sum(0); an = kn[sl].sum().reshape(1)
-        hdist.allreduce_packed([dm, lam, an])
+        # block family: the per-block statistic sum_n w_n k k^T is a (num_blocks, bs, bs) tensor in the same packed reduction
+        from hipgp_b200.util import define_block_chunks
+        idx, _, _ = define_block_chunks([torch.arange(6), torch.arange(6)], [3, 2])          # 6 blocks of 6 (E = 36 of the 37 columns)
+        kb = kn[sl][:, :36][:, idx].transpose(0, 1)                                               # (num_blocks, rows, bs)
+        lam_blk = torch.matmul(kb.transpose(1, 2), w2[sl][None, :, None] * kb)
+        hdist.allreduce_packed([dm, lam, an, lam_blk])
+        kb_all = kn[:, :36][:, idx].transpose(0, 1)
         ok = torch.allclose(dm, (w1[:, None] * kn).sum(0)) and torch.allclose(lam, (w2[:, None] * kn ** 2).sum(0)) \
-            and torch.allclose(an, kn.sum().reshape(1))
+            and torch.allclose(an, kn.sum().reshape(1)) \
+            and torch.allclose(lam_blk, torch.matmul(kb_all.transpose(1, 2), w2[None, :, None] * kb_all))
         # global stop: converged only when EVERY rank is below tol; NaN on one rank never converges
         c1 = hdist.global_converged(1e-9 if rank == 0 else 1e-3, 1e-8, "cpu")
         c2 = hdist.global_converged(1e-9, 1e-8, "cpu")
