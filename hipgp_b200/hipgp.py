@@ -355,3 +355,13 @@ class BlockToeplitzGP(MeanFieldToeplitzGP):
         dS = -.5 * lam_block - self.global_theta2.data
         dSdeta1 = self.block_diag_multiply(dS, -2 * qm[None, :, 0])
         return dm + dSdeta1.squeeze().unsqueeze(-1), dS
+
+
+class FullRankToeplitzGP(ToeplitzInducingGP):
+    """The reference's full-rank family (ziggy/hipgp.py:693-797) stores a dense (M', M') variational covariance -- 2.6 TB at
+    BASELINE config 3 -- and is the reference's own small-problem baseline, outside the structured hot path (SURVEY.md 8,
+    DESIGN.md 0).  The name exists so that a switch-over fails with a pointer instead of an AttributeError."""
+
+    def __init__(self, *args, **kwargs):
+        raise NotImplementedError("hipgp_b200 implements the mean-field and block-diagonal families (MeanFieldToeplitzGP, "
+                                  "BlockToeplitzGP); the dense full-rank family of ziggy/hipgp.py:693-797 is out of scope")
