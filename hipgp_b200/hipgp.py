@@ -358,7 +358,7 @@ class BlockToeplitzGP(MeanFieldToeplitzGP):
 
 
 class FullRankToeplitzGP(ToeplitzInducingGP):
-    """The reference's full-rank family (ziggy/hipgp.py:693-797) stores a dense (M', M') variational covariance -- 2.6 TB at
+    """The reference's full-rank family (ziggy/hipgp.py:693-797) stores a dense (M', M') variational covariance -- 0.5 TB in fp32 at
     BASELINE config 3 -- and is the reference's own small-problem baseline, outside the structured hot path (SURVEY.md 8,
     DESIGN.md 0).  The name exists so that a switch-over fails with a pointer instead of an AttributeError."""
 
