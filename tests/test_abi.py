@@ -116,3 +116,18 @@ def test_embedding_lengths(dims):
                     r //= p
             assert r == 1, Lv
     assert lib.hipgp_plan_destroy(h) == 0
+
+
+def test_new_entry_points_validate_before_touching_the_device():
+    """hipgp_toeplitz_quadform / hipgp_block_* reject a null plan and an index that does not tile M' without any CUDA call."""
+    L, lib = _lib()
+    buf = (ctypes.c_float * 8)()
+    idx = (ctypes.c_int64 * 8)(*range(8))
+    assert lib.hipgp_toeplitz_quadform(None, buf, buf, 1, 1.0, buf, None) != 0
+    assert "null plan" in lib.hipgp_last_error().decode()
+    assert lib.hipgp_block_lam(0, buf, buf, idx, 1, 8, 2, 3, 1.0, 1.0, buf, None) != 0          # 2 x 3 != 8
+    assert "num_blocks * block_size" in lib.hipgp_last_error().decode()
+    assert lib.hipgp_block_diag_multiply(0, buf, buf, None, 1, 8, 2, 4, buf, None) != 0
+    assert "null block index" in lib.hipgp_last_error().decode()
+    assert lib.hipgp_block_lam(5, buf, buf, idx, 1, 8, 2, 4, 1.0, 1.0, buf, None) != 0 and "dtype" in lib.hipgp_last_error().decode()
+    assert lib.hipgp_block_diag_multiply(0, buf, buf, idx, 0, 8, 2, 4, buf, None) == 0          # empty batch: no-op
