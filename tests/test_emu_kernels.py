@@ -186,3 +186,25 @@ def test_block_kernels(lib, dname):
     # empty minibatch: lam = diag * I, multiply is a no-op
     assert lib.hipgp_block_lam(code, None, None, ptr(idx), 0, E, nblk, bs, 3.0, 2.0, ptr(lam), None) == 0
     assert np.array_equal(lam, np.broadcast_to(2.0 * np.eye(bs, dtype=dt), lam.shape))
+
+
+def test_toeplitz_quadform_lane_layout(lib):
+    """fp32 on a 30x60 grid: both embedding lengths (64, 128) are in the emulation build's specialised list, so the
+    forward spectra are in the fp32 LANE layout (re0, re1, im0, im1) and corr_accumulate_kernel's layout switch is taken."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+    from oracle import ziggy_oracle as zo
+    dims = np.array([30, 60], dtype=np.int64); M = 1800
+    plan = C.c_void_p()
+    assert lib.hipgp_plan_create(2, dims.ctypes.data_as(L._pi64), L.F32, 0, C.byref(plan)) == 0
+    Ln = (C.c_int64 * 2)(); Lw = (C.c_int64 * 2)()
+    assert lib.hipgp_plan_embedding(plan, Ln, Lw) == 0 and list(Ln) == [64, 128]
+    col = np.zeros(M, dtype=np.float32); col[0] = 1.0
+    assert lib.hipgp_plan_set_first_row(plan, ptr(col), 1e-6, None, None) == 0, lib.hipgp_last_error()
+    rng = np.random.default_rng(4)
+    u = rng.standard_normal((2, M)).astype(np.float32); v = rng.standard_normal((2, M)).astype(np.float32)
+    out = np.zeros(M, dtype=np.float32)
+    assert lib.hipgp_toeplitz_quadform(plan, ptr(u), ptr(v), 2, 1.0, ptr(out), None) == 0, lib.hipgp_last_error()
+    want = zo.sym_toeplitz_derivative_quadratic_form(u.T.astype(np.float64), v.T.astype(np.float64))
+    assert rel(out, want) < 1e-5, rel(out, want)
+    lib.hipgp_plan_destroy(plan)
