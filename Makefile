@@ -1,11 +1,11 @@
-# Developer convenience; __graft_entry__.build() is the contract entry point and does the same compile.
-NVCC ?= /usr/local/cuda/bin/nvcc
-FLAGS = -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -shared
+# Developer convenience.  `lib` runs the contract entry point (__graft_entry__.build(): plan.cu + the per-length-group
+# fast_inst.cu units, compiled in parallel and linked into hipgp_b200/csrc/libhipgp_b200.so); `dev` is the same build with
+# the reduced length list (HIPGP_DEV_SMALL); `emu` builds the test-only CPU emulation.
 SRC = hipgp_b200/csrc
-lib: $(SRC)/libhipgp_b200.so
-$(SRC)/libhipgp_b200.so: $(SRC)/*.cu $(SRC)/*.cuh $(SRC)/*.inl $(SRC)/*.h include/hipgp_b200.h
-	$(NVCC) $(FLAGS) $(SRC)/plan.cu -o $@
+lib:
+	python -c "import __graft_entry__ as g; g._compile_lib()"
 dev:
-	$(NVCC) $(FLAGS) -DHIPGP_DEV_SMALL $(SRC)/plan.cu -o $(SRC)/libhipgp_b200.so
+	HIPGP_DEV_SMALL=1 python -c "import __graft_entry__ as g; g._compile_lib()"
 emu:
 	python -c "import sys; sys.path.insert(0,'tests'); import emu_build; print(emu_build.build())"
+.PHONY: lib dev emu

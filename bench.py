@@ -4,22 +4,27 @@
 Workload (BASELINE.json configs[1]): 2-D inducing grid 1000 x 1000 (M = 10^6), Matern-5/2, ell = 0.01,
 jitter 1e-3, fp32; one STEP = one PCG solve K_uu^-1 b with the HIP-GP preconditioner exactly as the SVI
 loop issues it (maxiter 20, tol 1e-8 -- it does not converge, so 20 iterations = 20 K-matvecs + 21
-preconditioner matvecs + the fused vector updates) on B = 16 right-hand sides per GPU.
+preconditioner matvecs + the fused vector updates) on B = 64 right-hand sides per GPU.
 
 metric  : Toeplitz matvec GB/s = algorithmic bytes of the step's 41 structured matvecs,
           w (2 M B + E_h) each (SURVEY.md 8d contract figure, E_h = 1998*1000), divided by the step time.
           `pcg_solve_s` (the other half of BASELINE.json's metric) is reported beside it.
 value   : inputs resident in HBM (plan.pcg on device tensors).
-e2e     : the same step through the C-ABI host entry point (hipgp_pcg_host): pinned host b -> H2D -> solve ->
-          D2H x, every step.
+e2e     : the same step through the C-ABI host entry point (hipgp_pcg_host_pipelined): pinned host b -> H2D -> solve
+          -> D2H x, every step; the right-hand sides travel in groups of 16 so that the copies of neighbouring groups
+          hide behind the solve of the current one.
 roofline: per-kernel-class CUDA-event timing inside this script (a second pass of the same steps with the
           library's event hooks on); achieved = matvec algorithmic bytes / (sum of the three pass kernels'
           average durations); the dominant kernel and its share of the matvec are named.
-cpu_baseline / --impl reference: the CPU oracle (oracle/ziggy_oracle.py, a restatement of the reference pinned
-          to golden vectors from the unmodified reference) on the host cores, bounded sample B = 1.
+cpu_baseline / --impl reference: the UNMODIFIED reference (`oracle/_ref/ziggy`, staged byte for byte by
+          oracle/make_ref.py; ToeplitzTensor._solve under the legacy-torch shim oracle/ref_shim.py) on the host cores,
+          same configuration, each step a bounded sample (16 of the step's 64 right-hand sides); falls back to the CPU
+          oracle port (oracle/ziggy_oracle.py) when the staged reference is absent.
 
-N > 1 (torchrun): right-hand sides are independent, so each rank solves its own B = 16 shard with no data-path
-collective ("weak" scaling); time = max over ranks.
+N > 1 (torchrun): right-hand sides are independent, so each rank solves its own B = 64 shard with no data-path
+collective ("weak" scaling); time = max over ranks.  The two paths that DO need collectives are measured in the same run
+and reported as extra keys: `svi_cfg3` (observation-sharded mean-field natural-gradient step, one packed all-reduce per
+step) and `slab_cfg5` (512^3 grid sharded over the ranks, two all-to-all transposes per matvec).
 """
 import argparse
 import json
@@ -35,14 +40,31 @@ sys.path.insert(0, ROOT)
 GRID = (1000, 1000)
 ELL, SIG2, JITTER = 0.01, 1.0, 1e-3
 MAXITER, TOL = 20, 1e-8
-B_PER_GPU = 16
+B_PER_GPU = 64
+E2E_GROUP = 16
+CPU_SAMPLE_B = 16
 N_MATVEC = 2 * MAXITER + 1
+METRIC = "toeplitz_matvec_GBps_in_pcg_1e6grid"
+
+
+def workload_config():
+    """identical in both arms (the driver compares it)"""
+    return {"workload": "cfg2: 2D grid 1000x1000 (M=1e6), Matern-5/2 ell=0.01 jitter=1e-3, PCG maxiter=20 tol=1e-8 + HIP-GP preconditioner",
+            "rhs_per_gpu_per_step": B_PER_GPU, "matvecs_per_step": N_MATVEC,
+            "l2": "working set per GPU (5 vectors x 256 MB + 528 MB of half-spectra) exceeds the 126 MB L2; no flush needed"}
 
 
 def alg_bytes_matvec(B, w=4):
     M = GRID[0] * GRID[1]
     E_h = (2 * GRID[0] - 2) * ((2 * GRID[1] - 2) // 2 + 1)
     return w * (2 * M * B + E_h)
+
+
+def alg_bytes_pcg_iteration(B, w=4):
+    """w (13 M B + 2 E_h) -- both matvecs in / out plus the fully fused x, r, p updates and dots"""
+    M = GRID[0] * GRID[1]
+    E_h = (2 * GRID[0] - 2) * ((2 * GRID[1] - 2) // 2 + 1)
+    return w * (13 * M * B + 2 * E_h)
 
 
 def first_row(dtype, device):
@@ -120,56 +142,208 @@ def host_threads():
     return max(1, int(phys))
 
 
-def oracle_step(B, threads=None):
-    """One bounded CPU step: oracle PCG (20 iterations) on B right-hand sides of the 10^6-point grid."""
+# ---------------------------------------------------------------------------------------------------------------------
+# CPU arm: the reference's own implementation of the path on the host cores
+# ---------------------------------------------------------------------------------------------------------------------
+def reference_step(B, threads):
+    """Returns (step_fn, setup_seconds, kind).  kind = "reference": the unmodified ziggy.misc.toeplitz_tensor.ToeplitzTensor
+    (its K matvec, its preconditioner, its conj_grad2) ; "port": the oracle restatement (staged reference absent)."""
     import torch
-    from oracle import ziggy_oracle as zo
-    if threads:
-        torch.set_num_threads(threads)
+    torch.set_num_threads(threads)             # torchrun exports OMP_NUM_THREADS=1: the CPU arm still uses every core
     g1 = torch.linspace(0, 4, GRID[0]); g2 = torch.linspace(-2, 2, GRID[1])
-    kfun = lambda x, y: zo.matern(x, y, SIG2, ELL, 2.5)
-    t0 = time.perf_counter()
-    K = zo.OracleToeplitz([g1, g2], kfun, jitter_val=JITTER)
-    t_setup = time.perf_counter() - t0
     torch.manual_seed(42)
     v = torch.randn(B, GRID[0] * GRID[1])
+    from oracle import ref_shim
+    kind = "reference" if ref_shim.reference_root() is not None else "port"
+    t0 = time.perf_counter()
+    if kind == "reference":
+        ref_shim.import_reference()
+        from ziggy.misc.toeplitz_tensor import ToeplitzTensor
+        from ziggy.kernels import Matern
+        kern = Matern(nu=2.5, length_scale=ELL)
+        kfun = lambda x, y: kern.forward(x, y, params=(SIG2, ELL))
+        K = ToeplitzTensor(xgrids=[g1, g2], kernel=kfun, batch_shape=None, jitter_val=JITTER)
+        solve = lambda: K._solve(v, do_precond=True, maxiter=MAXITER, tol=TOL)
+    else:
+        from oracle import ziggy_oracle as zo
+        K = zo.OracleToeplitz([g1, g2], lambda x, y: zo.matern(x, y, SIG2, ELL, 2.5), jitter_val=JITTER)
+        solve = lambda: K.solve(v, do_precond=True, maxiter=MAXITER, tol=TOL)
+    t_setup = time.perf_counter() - t0
 
     def step():
         t = time.perf_counter()
-        K.solve(v, do_precond=True, maxiter=MAXITER, tol=TOL)
+        solve()
         return time.perf_counter() - t
-    return step, t_setup
+    return step, t_setup, kind
 
 
 def run_reference(args):
-    import torch
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    B = 1
+    B = args.cpu_sample_b
     cores = host_threads()
-    torch.set_num_threads(cores)               # torchrun exports OMP_NUM_THREADS=1: the CPU arm still uses every core
-    step, t_setup = oracle_step(B, threads=cores)
-    for _ in range(min(args.warmup, 1)):
+    step, t_setup, kind = reference_step(B, cores)
+    for _ in range(args.warmup):
         step()
     ts = [step() for _ in range(args.steps)]
     t = sum(ts) / len(ts)
     val = N_MATVEC * alg_bytes_matvec(B) / t / 1e9
     line = {
-        "impl": "reference", "metric": "toeplitz_matvec_GBps_in_pcg_1e6grid", "value": val, "unit": "GB/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": t * 1e3,
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "GB/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "pcg_solve_s": t,
-        "config": {"workload": "cfg2: 2D grid 1000x1000 (M=1e6), Matern-5/2 ell=0.01 jitter=1e-3, PCG maxiter=20 tol=1e-8 + HIP-GP preconditioner",
-                   "rhs_per_step": B, "note": "CPU oracle port of the reference (torch CPU ops, all host threads); bounded sample B=1"},
-        "cpu_baseline": {"value": val, "unit": "GB/s", "cores": cores, "kind": "port",
-                         "sample": "1 rhs x 20 PCG iterations per step (full 10^6 grid); setup %.2fs not timed" % t_setup},
+        "pcg_solve_s": t, "pcg_solve_s_per_rhs": t / B,
+        "config": workload_config(),
+        "cpu_baseline": {"value": val, "unit": "GB/s", "cores": cores, "kind": kind,
+                         "sample": "%d of the step's %d right-hand sides x 20 PCG iterations on the full 10^6 grid per step (value = the sample's own "
+                                   "algorithmic bytes / its time); spectrum set-up %.2f s not timed" % (B, B_PER_GPU, t_setup),
+                         "what": ("unmodified reference: ziggy.misc.toeplitz_tensor.ToeplitzTensor._solve (oracle/_ref, torch CPU, all host threads)"
+                                  if kind == "reference" else "CPU oracle port of the reference (oracle/ziggy_oracle.py; oracle/_ref not staged)")},
         "e2e": {"value": val, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# the two multi-GPU paths that need collectives (extra keys of the N > 1 line; also run at N = 1 as the reference point)
+# ---------------------------------------------------------------------------------------------------------------------
+def svi_cfg3_section(dev, world, rank, steps=20):
+    """BASELINE config 3: 300x300 grid, Matern-3/2, 200-observation minibatches, mean-field natural-gradient step
+    (K_xu on the fly -> 20-iteration PCG -> R^T -> fused statistics), observations of every minibatch sharded over the
+    ranks, ONE packed all-reduce [data_dm; lam_sum; sum a_n] per step (hipgp.py:194-276)."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from hipgp_b200 import hipgp as hh, kernels as hk
+    dtype = torch.float32
+    bsz = 200
+    xgrids = [torch.linspace(-5.7, 1.8, 300, dtype=dtype), torch.linspace(50, 55.5, 300, dtype=dtype)]
+    mod = hh.MeanFieldToeplitzGP(hk.Matern(nu=1.5, dtype=dtype), xgrids, num_obs=2_000_000, sig2_init=1.0, ell_init=0.05,
+                                 dtype=dtype, jitter_val=1e-3).cuda_params(dev.index)
+    opt = torch.optim.SGD([mod.global_theta1, mod.global_theta2], lr=1e-4)
+    rs = np.random.RandomState(42)
+    n = (steps + 3) * bsz
+    X = torch.from_numpy(np.stack([rs.uniform(-5.7, 1.8, n), rs.uniform(50, 55.5, n)], 1)).to(dtype).pin_memory()
+    Y = torch.from_numpy(rs.randn(n, 1)).to(dtype).pin_memory()
+    NS = torch.full((n, 1), 0.3, dtype=dtype).pin_memory()
+
+    def step(i, shard):
+        sl = slice(i * bsz, (i + 1) * bsz)
+        xb = X[sl].to(dev, non_blocking=True); yb = Y[sl].to(dev, non_blocking=True); nb = NS[sl].to(dev, non_blocking=True)
+        el = mod.elbo_and_grad(xb, yb, nb, maxiter_cg=20, shard=shard)
+        opt.step()
+        return el
+
+    def timed(shard):
+        for i in range(3):
+            step(i, shard)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            step(3 + i, shard)
+        e1.record(); torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1) / steps], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+    ms_n = timed(True)                     # sharded over the ranks
+    out = {"ms_per_step": ms_n, "obs_per_s": bsz / (ms_n / 1e3), "batch_size": bsz, "maxiter_cg": 20, "steps": steps, "dtype": "f32",
+           "allreduce_bytes": int((2 * mod.Mprime + 1) * 4) if world > 1 else 0, "n_gpus": world,
+           "epoch_s_extrapolated_2M_obs": 2_000_000 / bsz * ms_n / 1e3}
+    if world > 1:
+        ms_1 = timed(False)                # every rank runs the WHOLE minibatch: the one-GPU step, measured in the same run
+        out["ms_per_step_1gpu_same_run"] = ms_1
+        out["speedup_vs_1gpu"] = ms_1 / ms_n
+        out["efficiency_vs_n1"] = ms_1 / ms_n / world
+    return out
+
+
+def slab_cfg5_section(dev, world, rank):
+    """BASELINE config 5: 512^3 grid (134M inducing points), K matvec and PCG(20) with the grid sharded over the ranks
+    (slab decomposition along axis 0, two all-to-all transposes per matvec); strong scaling against the undecomposed
+    one-GPU plan measured on rank 0 in the same run."""
+    import torch
+    import torch.distributed as dist
+    from hipgp_b200.plan import Plan
+    from hipgp_b200.slab import SlabToeplitz
+    from hipgp_b200 import _lib as L, kernels as hk
+    dtype = torch.float32
+    dims = (512, 512, 512)
+    xg = [torch.linspace(0, 1, m, dtype=dtype, device=dev) for m in dims]
+    h = float(xg[0][1] - xg[0][0])
+    col = hk.first_row(xg, hk.Matern(nu=2.5, dtype=dtype), (1.0, 2.5 * h), jitter=1e-3)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    def timed(fn, n, warm=2):
+        for _ in range(warm):
+            fn()
+        sync_all()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record(); torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1) / n], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    out = {"grid": list(dims), "n_gpus": world, "dtype": "f32"}
+    # one-GPU reference point: the undecomposed plan (rank 0 measures, the others wait)
+    one = torch.zeros(2, device=dev, dtype=torch.float64)
+    if rank == 0:
+        plan = Plan(list(dims), dtype, dev).set_first_row(col)
+        v = torch.randn(1, dims[0] * dims[1] * dims[2], dtype=dtype, device=dev)
+        for _ in range(2):
+            plan.matvec(L.MV_K, v)
+        torch.cuda.synchronize()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            plan.matvec(L.MV_K, v)
+        e1.record(); torch.cuda.synchronize()
+        one[0] = e0.elapsed_time(e1) / 5
+        plan.pcg(v, maxiter=MAXITER, tol=TOL)
+        torch.cuda.synchronize()
+        e0.record(); plan.pcg(v, maxiter=MAXITER, tol=TOL); e1.record(); torch.cuda.synchronize()
+        one[1] = e0.elapsed_time(e1) / 1e3
+        del plan, v
+        torch.cuda.empty_cache()
+    if world > 1:
+        dist.broadcast(one, src=0)
+    out["matvec_ms_1gpu_undecomposed"] = float(one[0]); out["pcg20_s_1gpu_undecomposed"] = float(one[1])
+    if world == 1:
+        out["matvec_ms"] = float(one[0]); out["pcg20_s"] = float(one[1])
+        return out
+    slab = SlabToeplitz(dims, col, dtype, dev)
+    gen = torch.Generator(device=dev); gen.manual_seed(42 + rank)      # counter-based per-slab stream (SURVEY 8d)
+    vs = torch.randn(slab.slab_elems, dtype=dtype, device=dev, generator=gen)
+    out["matvec_ms"] = timed(lambda: slab.matvec_K(vs), 10)
+    out["pcg20_s"] = timed(lambda: slab.solve(vs, do_precond=True, maxiter=MAXITER, tol=TOL), 1, warm=1) / 1e3
+    # the exchange alone: one all-to-all of the packed half-spectrum blocks, as the matvec issues it twice
+    buf = torch.empty(slab.exch_elems, dtype=slab.cdtype, device=dev); rcv = torch.empty_like(buf)
+    a2a_ms = timed(lambda: dist.all_to_all_single(torch.view_as_real(rcv), torch.view_as_real(buf)), 10)
+    esz = 8
+    sent = slab.exch_elems * esz * (world - 1) // world               # bytes that leave this GPU per all-to-all
+    out.update({"alltoall_bytes_per_rank": int(sent), "alltoalls_per_matvec": 2, "alltoall_ms": a2a_ms,
+                "nvlink_GBps_achieved": sent / (a2a_ms / 1e3) / 1e9, "nvlink_frac_of_900": sent / (a2a_ms / 1e3) / 1e9 / 900.0,
+                "alltoall_share_of_matvec": 2 * a2a_ms / out["matvec_ms"],
+                "strong_speedup_vs_1gpu": float(one[0]) / out["matvec_ms"],
+                "strong_eff_vs_1gpu": float(one[0]) / out["matvec_ms"] / world,
+                "pcg_strong_eff_vs_1gpu": float(one[1]) / out["pcg20_s"] / world})
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------------------
 def run_gpu(args):
     import torch
     import torch.distributed as dist
@@ -193,6 +367,7 @@ def run_gpu(args):
     dtype = torch.float32
     B = B_PER_GPU
     M = GRID[0] * GRID[1]
+    warmup = max(args.warmup, 3)
     plan = Plan(GRID, dtype, dev)
     plan.set_first_row(first_row(dtype, dev))
     gen = torch.Generator(device=dev); gen.manual_seed(42 + rank)
@@ -204,7 +379,7 @@ def run_gpu(args):
         return plan.pcg(b, maxiter=MAXITER, tol=TOL, precond=True)
 
     def step_e2e():
-        return plan.pcg_host(b_host, x_host, maxiter=MAXITER, tol=TOL, precond=True)
+        return plan.pcg_host(b_host, x_host, maxiter=MAXITER, tol=TOL, precond=True, group=E2E_GROUP)
 
     def timed(fn, steps):
         barrier()
@@ -223,7 +398,7 @@ def run_gpu(args):
     if sampler:
         sampler.start()
         sampler.wait_running()
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(warmup):
         step_dev()
     m0 = sampler.mark() if sampler else 0
     l0 = plan.launch_count()
@@ -234,6 +409,8 @@ def run_gpu(args):
     for _ in range(2):
         step_e2e()
     ms_e2e = timed(step_e2e, args.steps)
+    xd = step_dev()
+    e2e_matches = bool(torch.equal(xd.cpu(), x_host))       # the pipelined host path returns the device path's solution
 
     # roofline pass: same steps with per-kernel-class events on
     plan.profile(True)
@@ -245,22 +422,50 @@ def run_gpu(args):
     m2 = sampler.mark() if sampler else 0
     clocks = sampler.finish(m0, m1, m0, m2) if sampler else None
 
-    # fp64 and B=1 companions (not the headline; same step definition)
+    # companions (not the headline; same step definition): one right-hand side, plain matvecs, fp64, cuFFT comparison point
     extra = {}
     if world == 1 and not args.quick:          # single-GPU run only: `timed` synchronises all ranks
-        b1 = b[:1].contiguous()
+        nrep = max(5, min(args.steps, 20))
+        b16 = b[:16].contiguous(); b1 = b[:1].contiguous()
         for _ in range(3):
             plan.pcg(b1, maxiter=MAXITER, tol=TOL)
-        extra["pcg_solve_s_B1_f32"] = timed(lambda: plan.pcg(b1, maxiter=MAXITER, tol=TOL), args.steps) / args.steps / 1e3
+        extra["pcg_solve_s_B1_f32"] = timed(lambda: plan.pcg(b1, maxiter=MAXITER, tol=TOL), nrep) / nrep / 1e3
+        for _ in range(2):
+            plan.pcg(b16, maxiter=MAXITER, tol=TOL)
+        extra["pcg_solve_s_B16_f32"] = timed(lambda: plan.pcg(b16, maxiter=MAXITER, tol=TOL), nrep) / nrep / 1e3
         for mode, nm in ((L.MV_K, "K"), (L.MV_CINV, "Cinv"), (L.MV_RT, "RT")):
             for _ in range(3):
-                plan.matvec(mode, b)
-            ms = timed(lambda: plan.matvec(mode, b), args.steps) / args.steps
-            extra["matvec_ms_B16_f32_" + nm] = ms
-        extra["matvec_GBps_B16_f32_K"] = alg_bytes_matvec(B) / extra["matvec_ms_B16_f32_K"] / 1e6
+                plan.matvec(mode, b16)
+            extra["matvec_ms_B16_f32_" + nm] = timed(lambda: plan.matvec(mode, b16), nrep) / nrep
+        extra["matvec_GBps_B16_f32_K"] = alg_bytes_matvec(16) / extra["matvec_ms_B16_f32_K"] / 1e6
+        t0 = time.perf_counter(); plan.set_first_row(first_row(dtype, dev)); torch.cuda.synchronize()
+        extra["spectrum_setup_ms_f32"] = (time.perf_counter() - t0) * 1e3
+        # cuFFT comparison point (library FFTs through torch.fft: rfft2 -> spectrum multiply -> irfft2 -> crop; same embedding)
+        Lf = plan.embedding()[0]
+        S = torch.rand(Lf[0], Lf[1] // 2 + 1, dtype=dtype, device=dev)
+        def cufft_mv():
+            F = torch.fft.rfft2(b16.view(16, GRID[0], GRID[1]), s=(Lf[0], Lf[1]))
+            return torch.fft.irfft2(F * S, s=(Lf[0], Lf[1]))[:, :GRID[0], :GRID[1]]
+        for _ in range(3):
+            cufft_mv()
+        extra["cufft_comparison_matvec_ms_B16_f32"] = timed(cufft_mv, nrep) / nrep
+        del S
+        # fp64 (BASELINE config 2 names both precisions)
+        plan64 = Plan(GRID, torch.float64, dev).set_first_row(first_row(torch.float64, dev))
+        b64 = b16.double()
+        for _ in range(3):
+            plan64.matvec(L.MV_K, b64)
+        extra["matvec_ms_B16_f64_K"] = timed(lambda: plan64.matvec(L.MV_K, b64), nrep) / nrep
+        extra["matvec_GBps_B16_f64_K"] = alg_bytes_matvec(16, 8) / extra["matvec_ms_B16_f64_K"] / 1e6
+        plan64.pcg(b64, maxiter=MAXITER, tol=TOL)
+        extra["pcg_solve_s_B16_f64"] = timed(lambda: plan64.pcg(b64, maxiter=MAXITER, tol=TOL), 5) / 5 / 1e3
+        extra["toeplitz_matvec_GBps_in_pcg_f64"] = N_MATVEC * alg_bytes_matvec(16, 8) / extra["pcg_solve_s_B16_f64"] / 1e9
+        del plan64, b64
+        torch.cuda.empty_cache()
     if world > 1:
         dist.barrier()
 
+    line = None
     if rank == 0:
         t_step = ms_total / args.steps / 1e3
         alg_step = N_MATVEC * alg_bytes_matvec(B) * world
@@ -276,23 +481,24 @@ def run_gpu(args):
         mv_ms = per["rows_fwd"] + per["cols_pass"] + per["rows_inv"]
         dom = max(("rows_fwd", "cols_pass", "rows_inv"), key=lambda k: per[k])
         achieved = alg_bytes_matvec(B) / (mv_ms / 1e3) / 1e9 if mv_ms > 0 else 0.0
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "traffic_r1.json")
+        traffic, traffic_source = None, None
+        tpath = os.path.join(ROOT, "profiles", "traffic_r2.json")
         if os.path.exists(tpath):
             try:
-                traffic = json.load(open(tpath)).get("dram_bytes_per_matvec_B16_f32")
+                tj = json.load(open(tpath))
+                traffic = tj.get("dram_bytes_per_matvec_B16_f32") * (B / 16.0)      # measured at B = 16; bytes scale with the batch
+                traffic_source = tj.get("source")
             except Exception:
                 traffic = None
-        # bounded CPU sample on this box's host cores (rank 0, N = 1 only)
+        # bounded CPU sample on this box's host cores (rank 0, N = 1 only): the reference arm of this script, one warm-up + one step
         cpu = None
         if world == 1 and not args.no_cpu:
-            import torch as _t
-            step, t_setup = oracle_step(1)
-            step()
-            tc = step()
-            cpu = {"value": N_MATVEC * alg_bytes_matvec(1) / tc / 1e9, "unit": "GB/s", "cores": _t.get_num_threads(),
-                   "kind": "port", "pcg_solve_s": tc,
-                   "sample": "CPU oracle, 1 rhs x 20 PCG iterations on the full 10^6 grid (1 warm-up + 1 timed solve)"}
+            try:
+                r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                                   capture_output=True, text=True, timeout=900)
+                cpu = json.loads(r.stdout.strip().splitlines()[-1])["cpu_baseline"]
+            except Exception as e:
+                cpu = {"error": repr(e)[:200]}
         # per-pass streaming bytes (what each pass moves when its input / output do not stay on chip),
         # averaged over the launches of one PCG iteration, against the same HBM peak
         Mv = 4 * GRID[0] * GRID[1] * B                                   # one vector, all right-hand sides
@@ -304,28 +510,60 @@ def run_gpu(args):
         per_kernel = {k: {"streaming_bytes": stream[k], "ms": per[k],
                           "achieved_GBps": stream[k] / (per[k] / 1e3) / 1e9 if per[k] > 0 else None,
                           "frac_of_hbm_peak": stream[k] / (per[k] / 1e3) / 1e9 / peak if per[k] > 0 else None} for k in stream}
+        it_frac = MAXITER * alg_bytes_pcg_iteration(B) / t_step / 1e9 / peak
+        cfg = workload_config()
         line = {
-            "metric": "toeplitz_matvec_GBps_in_pcg_1e6grid", "value": value, "unit": "GB/s", "n_gpus": world,
-            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps,
+            "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world,
+            "steps": args.steps, "warmup": warmup, "ms_per_step": ms_total / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "pcg_solve_s": t_step,
-            "config": {"workload": "cfg2: 2D grid 1000x1000 (M=1e6), Matern-5/2 ell=0.01 jitter=1e-3, PCG maxiter=20 tol=1e-8 + HIP-GP preconditioner",
-                       "rhs_per_gpu": B, "matvecs_per_step": N_MATVEC, "embedding": list(plan.embedding()[0]),
-                       "l2": "working set per GPU (5 vectors x 64 MB + 135 MB of half-spectra) exceeds the 126 MB L2; no flush needed",
-                       "parallelism": "rhs-sharded x%d, no data-path collective" % world},
+            "pcg_solve_s": t_step, "pcg_solve_s_per_rhs": t_step / B,
+            "config": cfg,
+            "parallelism": "rhs-sharded x%d, no data-path collective (the collective-bearing paths are the svi_cfg3 / slab_cfg5 keys)" % world,
+            "embedding": list(plan.embedding()[0]),
             "e2e": {"value": e2e_val, "unit": "GB/s", "h2d_bytes_per_step": int(b_host.numel() * 4) * world,
-                    "d2h_bytes_per_step": int(x_host.numel() * 4) * world, "ms_per_step": ms_e2e / args.steps},
+                    "d2h_bytes_per_step": int(x_host.numel() * 4) * world, "ms_per_step": ms_e2e / args.steps,
+                    "how": "hipgp_pcg_host_pipelined: groups of %d right-hand sides, H2D / D2H of neighbouring groups on two copy streams behind the solve" % E2E_GROUP,
+                    "matches_device_path_bitwise": e2e_matches, "frac_of_value": e2e_val / value if value else None},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak if peak else None, "traffic": traffic,
+                         "frac": achieved / peak if peak else None, "traffic": traffic, "traffic_source": traffic_source,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
                          "kernel": dom, "kernel_share_of_matvec": per[dom] / mv_ms if mv_ms else None,
                          "per_launch_ms": per, "algorithmic_bytes_per_matvec": alg_bytes_matvec(B), "per_kernel_streaming": per_kernel,
-                         "note": "achieved = contract bytes w(2MB+E_h) of one matvec / (rows_fwd + cols_pass + rows_inv average launch durations), CUDA events around every launch in a second pass of the same steps; the contract figure assumes the half-spectrum never leaves the chip -- per_kernel_streaming gives each pass against the bytes it actually has to stream; the column pass is shared-memory-bandwidth bound (DESIGN.md 4a: 79 % of that roofline)"},
+                         "pcg_iteration_contract_frac": it_frac,
+                         "note": "achieved = contract bytes w(2MB+E_h) of one matvec / (rows_fwd + cols_pass + rows_inv average launch durations), CUDA events around every launch in a second pass of the same steps; the contract figure assumes the half-spectrum never leaves the chip -- per_kernel_streaming gives each pass against the bytes it actually has to stream; pcg_iteration_contract_frac = 20 x w(13MB+2E_h) / step time / peak; the passes are bound by FP32 issue (2 cycles per packed op) + shared-memory exchange, not by HBM (DESIGN.md 4a, profiles/README.md r2)"},
             "cpu_baseline": cpu,
         }
         line.update(extra)
+
+    # the collective-bearing multi-GPU paths (and their one-GPU reference points).  A watchdog guarantees the headline
+    # line: if a section hangs (a rank lost in a collective) rank 0 prints what it has and every rank leaves.
+    if not args.quick and not args.no_multi:
+        def bail():
+            if rank == 0:
+                line["sections_error"] = "a multi-GPU section exceeded %d s; headline printed without it" % args.section_timeout
+                print(json.dumps(line), flush=True)
+            os._exit(0)
+        wd = threading.Timer(args.section_timeout, bail)
+        wd.daemon = True
+        wd.start()
+        del b
+        torch.cuda.empty_cache()
+        for name, fn in (("svi_cfg3", lambda: svi_cfg3_section(dev, world, rank)), ("slab_cfg5", lambda: slab_cfg5_section(dev, world, rank))):
+            try:
+                res = fn()
+            except Exception as e:   # the headline must survive a failure of a companion section
+                res = {"error": repr(e)[:300]}
+                if world > 1:        # the other ranks may be inside a collective: leave through the watchdog path
+                    if rank == 0:
+                        line[name] = res
+                    bail()
+            if rank == 0:
+                line[name] = res
+            torch.cuda.empty_cache()
+        wd.cancel()
+    if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -337,8 +575,11 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--quick", action="store_true", help="skip the companion measurements")
+    ap.add_argument("--quick", action="store_true", help="skip the companion measurements and the multi-GPU sections")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline sample")
+    ap.add_argument("--no-multi", action="store_true", help="skip the svi_cfg3 / slab_cfg5 sections")
+    ap.add_argument("--section-timeout", type=int, default=420, help="watchdog for the multi-GPU sections (seconds)")
+    ap.add_argument("--cpu-sample-b", type=int, default=CPU_SAMPLE_B, help="right-hand sides per CPU step (bounded sample)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -1,0 +1,329 @@
+// cols_blk_kernel.cuh -- column pass for three-stage radix lists (R0, R1, R2) with BLOCK-LOCAL middle sections (round 2).
+//
+// After the first DIF stage (radix R0, stride S0 = Ln / R0) a line is R0 independent sub-transforms of BS = Ln / R0
+// neighbouring positions: the second forward stage, the last forward stage, the spectrum multiply, the first inverse stage
+// and the second inverse stage never leave their block of BS positions.  Only the first forward and the last inverse stage
+// couple the blocks.  cols_fast_kernel separates ALL stages by CTA barriers, which keeps the 16 warps of an SM in lock step:
+// everybody loads, then everybody computes, then everybody stores (ncu, profiles/ncu_full_r1j.json: FMA pipe 42 %, shared-memory
+// wavefronts 41 %, and the two do not overlap).  Here block b belongs to the GS = NT / R0 threads [b GS, (b+1) GS) -- one
+// warp at 2048 points -- which run the three block-local sections back to back with only a group barrier (__syncwarp when GS
+// is 32, a named barrier otherwise): the warps of an SM drift apart and the shared-memory phases of one overlap the
+// arithmetic of the others.  CTA barriers per tile: 3 instead of 6.
+//   * spectrum staging is block-local too (every group copies and waits for its own BS positions);
+//   * the next tile's input rows are prefetched behind the LAST inverse stage (the side buffer holds spectrum until every
+//     group has left its block-local sections);
+//   * per-stage twiddle tables live in shared memory when they fit (fp32): with 209 KB of the SM carved out for shared memory
+//     the L1 keeps almost nothing (ncu: 12 % hit rate), so every table load of cols_fast_kernel is an L2 round trip at the
+//     head of a section.
+// Same math, same digit-reversed layout, same modes as cols_fast_kernel.
+#pragma once
+#include "fast_kernels.cuh"
+
+namespace hipgp {
+
+#ifdef HIPGP_EMU
+static inline void nbar_sync(int id, int count) { emu::g_named_barrier[id].sync(count); }
+static inline void warp_sync_all() {
+    const int tid = (int)(threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z));
+    emu::g_warp_barrier[tid >> 5].wait();
+}
+#else
+__device__ __forceinline__ void nbar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void warp_sync_all() { __syncwarp(); }
+#endif
+
+template <int GS> __device__ __forceinline__ void blk_sync(int b) {
+    if (GS == 32) warp_sync_all(); else nbar_sync(1 + b, GS);
+}
+
+// twiddles w^{j r}, r = 1..R-1, of a stage: from the shared-memory copy of the [r][j] table or from global memory
+template <int R, int S, bool SM, class T>
+__device__ __forceinline__ void blk_twiddles(cplx<T>* w, const cplx<T>* tab, int j) {
+#pragma unroll
+    for (int r = 1; r < R; ++r) w[r] = SM ? tab[(r - 1) * S + j] : ldg_c(tab + (r - 1) * S + j);
+}
+
+template <class T, int NL, int NT, int MINB, int R0, int R1, int R2>
+struct ColsBlkCfg {
+    using G = TileGeo<T, NL, R0, R1, R2>;
+    static constexpr int Ln = G::Ln, BS = Ln / R0, GS = NT / R0;
+    static constexpr int IB2 = (BS / R1) * NL, IB3 = (BS / R2) * NL;         // items of one block in the middle / last stage
+    static constexpr bool ok = (NT % R0 == 0) && (GS % 32 == 0) && (GS == 32 || R0 <= 15) && (IB2 % GS == 0) && (IB3 % GS == 0) &&
+                               ((IB2 / GS) * R1 <= 16) && ((IB3 / GS) * R2 <= 16) && (BS % R2 == 0);
+    static constexpr size_t tw_bytes = sizeof(cplx<T>) * (size_t)((R0 - 1) * (Ln / R0) + (R1 - 1) * (BS / R1));
+    static constexpr size_t side_bytes = (size_t)(Ln + Ln / R2) * NL * 8;
+    // (MINB resident CTAs per SM must keep fitting: 228 KB per SM, 1 KB reserved per CTA)
+    static constexpr bool tw_smem = (size_t)MINB * (G::smem_bytes() + side_bytes + tw_bytes + 1024) <= 228 * 1024;
+    static constexpr size_t smem_bytes = G::smem_bytes() + side_bytes + (tw_smem ? tw_bytes : 0);
+};
+
+template <class T, int NL, int NT, int MINB, int R0, int R1, int R2>
+__global__ void __launch_bounds__(NT, MINB) cols_blk_kernel(ColsParams<T> P) {
+    using Cfg = ColsBlkCfg<T, NL, NT, MINB, R0, R1, R2>;
+    using G = typename Cfg::G;
+    constexpr int Ln = G::Ln, RLAST = R2, LPT = LaneInfo<T>::LPT, TBL = NL * LPT, S0 = Ln / R0;
+    constexpr int BS = Cfg::BS, GS = Cfg::GS, S1 = BS / R1;
+    constexpr bool TWS = Cfg::tw_smem;
+    static_assert(Cfg::ok, "radix list / tile shape not usable with block-local middle sections");
+    constexpr int LEG0 = G::leg(S0), LEG1 = G::leg(S1);
+    constexpr int SPEC_LANE = 8;                                  // bytes of real spectrum per lane (2 x fp32 or 1 x fp64)
+    constexpr int SIDE_SLOTS = Ln + Ln / RLAST;
+    constexpr int SIDE_LANES = SIDE_SLOTS * NL / 2;
+    HIPGP_DYN_SMEM(smem_raw);
+    Lane<T>* s = reinterpret_cast<Lane<T>*>(smem_raw);
+    unsigned char* side = smem_raw + G::smem_bytes();
+    const int tid = threadIdx.x;
+    if (P.done_flag && *P.done_flag) return;
+    const int blk = tid / GS, u = tid - blk * GS;                 // this thread's block of BS positions / its rank in the group
+
+    // per-stage twiddle tables: shared-memory copies (persistent kernel: filled once per CTA)
+    const cplx<T>* tw0 = P.f.twst + P.f.twoff[0];
+    const cplx<T>* tw1 = P.f.twst + P.f.twoff[1];
+    if (TWS) {
+        cplx<T>* t0 = reinterpret_cast<cplx<T>*>(side + Cfg::side_bytes);
+        cplx<T>* t1 = t0 + (R0 - 1) * S0;
+        for (int i = tid; i < (R0 - 1) * S0; i += NT) t0[i] = ldg_c(tw0 + i);
+        for (int i = tid; i < (R1 - 1) * S1; i += NT) t1[i] = ldg_c(tw1 + i);
+        tw0 = t0; tw1 = t1;
+        __syncthreads();
+    }
+
+    const int mode = P.mode;
+    const size_t pitch = (size_t)P.pitch;
+    const size_t spitch = P.spec_pitch ? (size_t)P.spec_pitch : (size_t)P.pitch;
+    const long ntiles = (long)P.nx * P.ny * P.nz;
+    // (32-bit tile arithmetic: the launcher guarantees ntiles < 2^31; 64-bit divisions cost ~100 instructions per thread and tile)
+    auto tile_origin = [&](long t, long& c0, size_t& ioff, size_t& ooff) {
+        const unsigned tt = (unsigned)t, nx = (unsigned)P.nx, ny = (unsigned)P.ny, nz = (unsigned)P.nz;
+        unsigned bx, by, bz;
+        if (P.batch_fastest) { bz = tt % nz; const unsigned r = tt / nz; bx = r % nx; by = r / nx; }
+        else { bx = tt % nx; const unsigned r = tt / nx; by = r % ny; bz = r / ny; }
+        c0 = (long)bx * TBL;
+        ioff = (size_t)by * P.in_ostride + (size_t)bz * P.in_bstride + c0;
+        ooff = (size_t)by * P.out_ostride + (size_t)bz * P.out_bstride + c0;
+    };
+    auto sslot = [](int p) { return p + (p >> G::LOGRL); };       // padded position of the staged spectrum
+    const bool spec_smem = P.spec_stage != 0;
+    const int n_in = P.n_in, n_out = P.n_out;
+    const bool stage_in = P.in_stage != 0;
+    const bool zero_hi = is_pow2(R0) && n_in <= Ln / 2;
+    const bool out_lo = is_pow2(R0) && n_out <= Ln / 2;
+    const size_t rstep = (size_t)S0 * pitch;
+
+    auto prefetch_input = [&](long t) {
+        long c0; size_t ioff, ooff;
+        tile_origin(t, c0, ioff, ooff);
+        const long nvalid = P.inner - c0;
+        const cplx<T>* in = P.in + ioff;
+        constexpr int NIT = (SIDE_LANES + NT - 1) / NT;
+        const int total = n_in * NL;
+#pragma unroll
+        for (int k = 0; k < NIT; ++k) {
+            const int w = tid + k * NT;
+            const int i = w / NL, lane = w - i * NL;
+            if (w < total && (long)lane * LPT < nvalid) cp_async<16>(side + (size_t)w * 16, in + (size_t)i * pitch + lane * LPT);
+        }
+        cp_async_commit();
+    };
+
+    long t = blockIdx.x;
+    if (stage_in && t < ntiles) prefetch_input(t);
+    for (; t < ntiles; t += gridDim.x) {
+        long c0; size_t ioff, ooff;
+        tile_origin(t, c0, ioff, ooff);
+        const long nvalid = P.inner - c0;
+        const cplx<T>* in = P.in + ioff;
+        cplx<T>* out = P.out + ooff;
+        // the previous tile's last stage has to be done with the tile buffer, and this tile's input must have landed
+        cp_async_wait_all();
+        __syncthreads();
+
+        if (mode != CM_INV) {
+            // ---- first forward stage (couples the blocks): operands from the side buffer or from global memory ----
+#pragma unroll 1
+            for (int it = tid; it < S0 * NL; it += NT) {
+                const int lane = it % NL, j = it / NL;
+                const bool ok = (long)lane * LPT < nvalid;
+                cplx<T> w[R0];
+                blk_twiddles<R0, S0, TWS>(w, tw0, j);
+                Lane<T> v[R0];
+                if (stage_in) {
+                    const Lane<T>* sp = reinterpret_cast<const Lane<T>*>(side) + (j * NL + lane);
+                    if (zero_hi) {
+#pragma unroll
+                        for (int r = 0; r < R0 / 2; ++r) v[r] = (ok && j + r * S0 < n_in) ? sp[r * S0 * NL] : lzero<T>();
+                        lbfly_zero_hi<R0, T>(v);
+                    } else {
+#pragma unroll
+                        for (int r = 0; r < R0; ++r) v[r] = (ok && j + r * S0 < n_in) ? sp[r * S0 * NL] : lzero<T>();
+                        lbfly<R0, false, T>(v);
+                    }
+                } else {
+                    const cplx<T>* gp = in + (size_t)j * pitch + lane * LPT;
+                    if (zero_hi) {
+#pragma unroll
+                        for (int r = 0; r < R0 / 2; ++r) v[r] = (ok && j + r * S0 < n_in) ? lane_from_global(gp + r * rstep) : lzero<T>();
+                        lbfly_zero_hi<R0, T>(v);
+                    } else {
+#pragma unroll
+                        for (int r = 0; r < R0; ++r) v[r] = (ok && j + r * S0 < n_in) ? lane_from_global(gp + r * rstep) : lzero<T>();
+                        lbfly<R0, false, T>(v);
+                    }
+                }
+#pragma unroll
+                for (int r = 1; r < R0; ++r) v[r] = lmul(v[r], w[r]);
+                Lane<T>* base = s + (G::slot(j) * NL + lane);
+#pragma unroll
+                for (int r = 0; r < R0; ++r) base[r * LEG0] = v[r];
+            }
+            __syncthreads();
+            // passes that stage no spectrum leave the side buffer idle from here on: the next tile's input rows start right away
+            if (!(mode == CM_FUSED && spec_smem) && stage_in && t + gridDim.x < ntiles) prefetch_input(t + gridDim.x);
+        }
+
+        // ======== block-local sections: group `blk` owns positions [blk BS, (blk + 1) BS) of every lane of the tile ========
+        const int pb = blk * BS;
+        if (mode == CM_FUSED && spec_smem) {
+            // this block's rows of the real spectrum tile -> side buffer (free now), behind the second forward stage
+            const unsigned char* sp = reinterpret_cast<const unsigned char*>(P.spec) + (size_t)c0 * sizeof(T);
+            constexpr int ROWB = NL * SPEC_LANE;
+            constexpr int CH = ROWB >= 16 ? 16 : 8, NCH = ROWB / CH;
+            constexpr int NIT = (BS * NCH + GS - 1) / GS;
+#pragma unroll
+            for (int k = 0; k < NIT; ++k) {
+                const int w = u + k * GS;
+                const int p = pb + w / NCH, c = w % NCH;
+                if (w < BS * NCH) cp_async<CH>(side + (size_t)sslot(p) * ROWB + c * CH, sp + (size_t)p * spitch * sizeof(T) + c * CH);
+            }
+            cp_async_commit();
+        }
+        if (mode != CM_INV) {
+            // ---- second forward stage: radix R1 inside the block ----
+            constexpr int NIT = Cfg::IB2 / GS;
+            Lane<T> v[NIT][R1];
+            cplx<T> w[NIT][R1];
+            Lane<T>* base[NIT];
+#pragma unroll
+            for (int k = 0; k < NIT; ++k) {
+                const int q = u + k * GS;
+                const int lane = q % NL, j = q / NL;
+                base[k] = s + (G::slot(pb + j) * NL + lane);
+                blk_twiddles<R1, S1, TWS>(w[k], tw1, j);
+#pragma unroll
+                for (int r = 0; r < R1; ++r) v[k][r] = base[k][r * LEG1];
+            }
+#pragma unroll
+            for (int k = 0; k < NIT; ++k) {
+                lbfly<R1, false, T>(v[k]);
+#pragma unroll
+                for (int r = 1; r < R1; ++r) v[k][r] = lmul(v[k][r], w[k][r]);
+#pragma unroll
+                for (int r = 0; r < R1; ++r) base[k][r * LEG1] = v[k][r];
+            }
+            if (mode == CM_FUSED && spec_smem) cp_async_wait_all();
+            blk_sync<GS>(blk);
+        }
+        // ---- last forward stage + spectrum + first inverse stage: RLAST neighbouring positions, in registers ----
+        {
+            constexpr int NIT = Cfg::IB3 / GS;
+#pragma unroll
+            for (int k = 0; k < NIT; ++k) {
+                const int q = u + k * GS;
+                const int lane = q % NL;
+                const bool ok = (long)lane * LPT < nvalid;
+                const int p0 = pb + (q / NL) * RLAST;
+                Lane<T>* base = s + (G::slot(p0) * NL + lane);
+                Lane<T> v[RLAST];
+                if (mode == CM_INV) {
+                    const cplx<T>* gp = in + cols_rowoff<T>(p0, P.pitch, P.in_split_len, P.in_split_stride) + lane * LPT;
+#pragma unroll
+                    for (int r = 0; r < RLAST; ++r) v[r] = ok ? lane_from_global(gp + r * pitch) : lzero<T>();
+                } else {
+#pragma unroll
+                    for (int r = 0; r < RLAST; ++r) v[r] = base[r * NL];
+                    lbfly<RLAST, false, T>(v);
+                }
+                if (mode == CM_FUSED) {
+                    if (spec_smem) {
+                        const unsigned char* sp = side + ((size_t)sslot(p0) * NL + lane) * SPEC_LANE;
+#pragma unroll
+                        for (int r = 0; r < RLAST; ++r) v[r] = lane_spec_smem(v[r], sp + r * NL * SPEC_LANE);
+                    } else if (ok) {
+                        const size_t sidx = (size_t)p0 * spitch + c0 + lane * LPT;
+#pragma unroll
+                        for (int r = 0; r < RLAST; ++r) v[r] = lane_spec(v[r], P.spec, P.spec_kind, sidx + (size_t)r * spitch);
+                    }
+                }
+                if (mode == CM_FWD) {
+                    if (ok) {
+                        cplx<T>* gp = out + cols_rowoff<T>(p0, P.pitch, P.out_split_len, P.out_split_stride) + lane * LPT;
+#pragma unroll
+                        for (int r = 0; r < RLAST; ++r) lane_to_global(gp + r * pitch, v[r]);
+                    }
+                } else {
+                    lbfly<RLAST, true, T>(v);
+#pragma unroll
+                    for (int r = 0; r < RLAST; ++r) base[r * NL] = v[r];
+                }
+            }
+        }
+        if (mode == CM_FWD) continue;
+        blk_sync<GS>(blk);
+        // ---- second inverse stage: radix R1 inside the block ----
+        {
+            constexpr int NIT = Cfg::IB2 / GS;
+            Lane<T> v[NIT][R1];
+            cplx<T> w[NIT][R1];
+            Lane<T>* base[NIT];
+#pragma unroll
+            for (int k = 0; k < NIT; ++k) {
+                const int q = u + k * GS;
+                const int lane = q % NL, j = q / NL;
+                base[k] = s + (G::slot(pb + j) * NL + lane);
+                blk_twiddles<R1, S1, TWS>(w[k], tw1, j);
+#pragma unroll
+                for (int r = 0; r < R1; ++r) v[k][r] = base[k][r * LEG1];
+            }
+#pragma unroll
+            for (int k = 0; k < NIT; ++k) {
+#pragma unroll
+                for (int r = 1; r < R1; ++r) v[k][r] = lmulc(v[k][r], w[k][r]);
+                lbfly<R1, true, T>(v[k]);
+#pragma unroll
+                for (int r = 0; r < R1; ++r) base[k][r * LEG1] = v[k][r];
+            }
+        }
+        __syncthreads();
+        // ---- every group is done with its spectrum rows: next tile's input rows travel behind the last inverse stage ----
+        if (mode == CM_FUSED && spec_smem && stage_in && t + gridDim.x < ntiles) prefetch_input(t + gridDim.x);
+        // ---- last inverse stage (couples the blocks) straight to global memory (crop = skipped stores) ----
+        {
+#pragma unroll 1
+            for (int it = tid; it < S0 * NL; it += NT) {
+                const int lane = it % NL, j = it / NL;
+                const bool ok = (long)lane * LPT < nvalid;
+                cplx<T> w[R0];
+                blk_twiddles<R0, S0, TWS>(w, tw0, j);
+                const Lane<T>* base = s + (G::slot(j) * NL + lane);
+                Lane<T> v[R0];
+#pragma unroll
+                for (int r = 0; r < R0; ++r) v[r] = base[r * LEG0];
+#pragma unroll
+                for (int r = 1; r < R0; ++r) v[r] = lmulc(v[r], w[r]);
+                cplx<T>* gp = out + (size_t)j * pitch + lane * LPT;
+                lbfly<R0, true, T>(v);
+                if (ok) {
+                    if (out_lo) {
+#pragma unroll
+                        for (int r = 0; r < R0 / 2; ++r) if (j + r * S0 < n_out) lane_to_global(gp + r * rstep, v[r]);
+                    } else {
+#pragma unroll
+                        for (int r = 0; r < R0; ++r) if (j + r * S0 < n_out) lane_to_global(gp + r * rstep, v[r]);
+                    }
+                }
+            }
+        }
+    }
+}
+
+}  // namespace hipgp

@@ -67,6 +67,25 @@ struct Barrier {
         if (expected > 0 && arrived >= expected) { arrived = 0; ++gen; cv.notify_all(); }
     }
 };
+// named barriers (bar.sync id, count / bar.arrive id, count): a counting barrier whose arrivals need not wait
+struct NamedBarrier {
+    std::mutex mu;
+    std::condition_variable cv;
+    int arrived = 0;
+    unsigned long gen = 0;
+    void reset() { arrived = 0; }
+    void arrive(int expected) {
+        std::unique_lock<std::mutex> lk(mu);
+        if (++arrived >= expected) { arrived = 0; ++gen; cv.notify_all(); }
+    }
+    void sync(int expected) {
+        std::unique_lock<std::mutex> lk(mu);
+        const unsigned long g = gen;
+        if (++arrived >= expected) { arrived = 0; ++gen; cv.notify_all(); return; }
+        cv.wait(lk, [&] { return gen != g; });
+    }
+};
+extern NamedBarrier g_named_barrier[16];
 extern thread_local dim3 t_threadIdx, t_blockIdx;
 extern dim3 g_blockDim, g_gridDim;
 extern Barrier g_block_barrier;
@@ -90,6 +109,7 @@ void launch(dim3 grid, dim3 block, size_t smem, F&& body) {
             if (t == 0) {
                 g_block_barrier.reset(T);
                 for (int w = 0; w < 64; ++w) g_warp_barrier[w].reset(32);
+                for (int w = 0; w < 16; ++w) g_named_barrier[w].reset();
             }
             start.wait();
             body();

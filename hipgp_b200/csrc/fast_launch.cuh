@@ -2,6 +2,7 @@
 #pragma once
 #include "plan_types.cuh"
 #include "fast_kernels.cuh"
+#include "cols_blk_kernel.cuh"
 
 namespace hipgp {
 
@@ -136,6 +137,49 @@ static void launch_cols_fast_t(hipgp_plan* pl, ColsParams<T>& P, long n_outer, l
     pl->launches++;
 }
 
+// block-local variant of the column pass for three-stage lists (cols_blk_kernel.cuh); false = not applicable
+template <class T, int LEN, int... Rs> struct ColsBlkLaunch {
+    static bool run(hipgp_plan*, ColsParams<T>&, long, long, cudaStream_t) { return false; }
+};
+template <class T, int LEN, int R0, int R1, int R2> struct ColsBlkLaunch<T, LEN, R0, R1, R2> {
+    using C = FastCfg<T, R0, R1, R2>;
+    using Cfg = ColsBlkCfg<T, C::NLC, C::NTC, C::MINBC, R0, R1, R2>;
+    static bool run(hipgp_plan* pl, ColsParams<T>& P, long n_outer, long B, cudaStream_t st) {
+        // (measured, profiles/README.md r2c: a gain where the twiddle tables fit next to the tile -- fp32 --, a loss otherwise)
+        if constexpr (!Cfg::ok || !Cfg::tw_smem) { (void)pl; (void)P; (void)n_outer; (void)B; (void)st; return false; }
+        else {
+            static const char* env_blk = getenv("HIPGP_COLS_BLK");
+            if (env_blk && env_blk[0] == '0') return false;
+            if ((long)((P.inner + C::NLC * C::LPT - 1) / (C::NLC * C::LPT)) * n_outer * B >= (1L << 31)) return false;
+            using G = typename Cfg::G;
+            constexpr int TBL = C::NLC * C::LPT;
+            P.TB = TBL; P.TBP = TBL;
+            if ((P.in_split_len && (P.mode != CM_INV || P.in_split_len % G::RLAST)) || (P.out_split_len && (P.mode != CM_FWD || P.out_split_len % G::RLAST)))
+                throw Error("split row blocks are supported for forward-only outputs / inverse-only inputs, in multiples of the last radix");
+            static const char* env_ns = getenv("HIPGP_NO_STAGE");
+            const bool use_side = !env_ns;
+            P.spec_stage = (use_side && P.mode == CM_FUSED && P.spec_kind == SPEC_REAL) ? 1 : 0;
+            P.in_stage = (use_side && P.mode != CM_INV && (size_t)P.n_in * C::NLC * 16 <= Cfg::side_bytes) ? 1 : 0;
+            const size_t smem = Cfg::smem_bytes;
+            P.nx = (int)((P.inner + TBL - 1) / TBL); P.ny = (int)n_outer; P.nz = (int)B;
+            {
+                const size_t spec_bytes = (size_t)G::Ln * (size_t)P.inner * (P.spec_kind == SPEC_REAL ? sizeof(T) : 2 * sizeof(T));
+                P.batch_fastest = (P.mode == CM_FUSED && B > 1 && spec_bytes > ((size_t)48 << 20) && (size_t)TBL * sizeof(cplx<T>) >= 128) ? 1 : 0;
+            }
+            auto k = cols_blk_kernel<T, C::NLC, C::NTC, C::MINBC, R0, R1, R2>;
+            if (smem > 40 * 1024) HIPGP_SET_MAX_SMEM(k, smem);
+            const long ntiles = (long)P.nx * P.ny * P.nz;
+            const long grid = std::min<long>(ntiles, resident_ctas(k, C::NTC, smem));
+            PROF_BEGIN(pl, 1, st);
+            HIPGP_LAUNCH(k, dim3((unsigned)grid), dim3(C::NTC), smem, st, P);
+            PROF_END(pl, st);
+            launch_check("column pass (block-local)", C::Ln, C::NLC, C::NTC, smem, grid);
+            pl->launches++;
+            return true;
+        }
+    }
+};
+
 // the lane kernels move 16-byte lanes: pointers and strides must keep every lane aligned
 template <class T>
 static bool cols_lane_aligned(const ColsParams<T>& P) {
@@ -150,7 +194,8 @@ template <class T, int LEN> struct FastList;
 #define X(LEN, ...)                                                                                         \
     template <class T> struct FastList<T, LEN> {                                                            \
         static void rows(hipgp_plan* pl, bool inv, RowsParams<T>& P, cudaStream_t st) { launch_rows_fast_t<T, __VA_ARGS__>(pl, inv, P, st); } \
-        static void cols(hipgp_plan* pl, ColsParams<T>& P, long no, long B, cudaStream_t st) { launch_cols_fast_t<T, LEN, __VA_ARGS__>(pl, P, no, B, st); } \
+        static void cols(hipgp_plan* pl, ColsParams<T>& P, long no, long B, cudaStream_t st) {         \
+            if (!ColsBlkLaunch<T, LEN, __VA_ARGS__>::run(pl, P, no, B, st)) launch_cols_fast_t<T, LEN, __VA_ARGS__>(pl, P, no, B, st); } \
     };
 HIPGP_FAST_LIST(X)
 #undef X

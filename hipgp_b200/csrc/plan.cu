@@ -658,6 +658,9 @@ int hipgp_plan_destroy(hipgp_plan* pl) {
                       &pl->corrLag})
         b->release(t);
     if (pl->pinned) cudaFreeHost(pl->pinned);
+#ifndef HIPGP_EMU
+    for (auto& cs : pl->copy_streams) if (cs) cudaStreamDestroy(cs);
+#endif
     delete pl;
     API_END
 }
@@ -772,6 +775,74 @@ int hipgp_pcg_host(hipgp_plan* pl, const void* b_host, void* x_host, int64_t B, 
     API_END
 }
 
+// The same solve with the transfers hidden: the right-hand sides are processed in groups of `group`; the host-to-device
+// copy of group g+1 and the device-to-host copy of group g-1 run on the plan's two copy streams while group g is solved
+// on the caller's stream (events order them).  Every group is an independent batched solve: the stopping rule
+// all_b sqrt(r_b.r_b) < tol (cg.py:70) is evaluated over the right-hand sides of ONE group, so a group may stop before
+// another one does; iters_out receives the maximum over the groups.  Host buffers should be pinned.
+int hipgp_pcg_host_pipelined(hipgp_plan* pl, const void* b_host, void* x_host, int64_t B, int maxiter, double tol, int precond,
+                             int64_t group, int* iters_out, void* stream) {
+    API_BEGIN
+    set_device(pl);
+    if (iters_out) *iters_out = 0;
+    if (B < 0) throw Error("negative number of right-hand sides");
+    if (B == 0) return 0;
+    if (!b_host || !x_host) throw Error("null vector pointer");
+    if (group <= 0 || group > B) group = B;
+    cudaStream_t s = (cudaStream_t)stream;
+#ifndef HIPGP_EMU
+    if (!pl->copy_streams[0]) {
+        CK(cudaStreamCreateWithFlags(&pl->copy_streams[0], cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&pl->copy_streams[1], cudaStreamNonBlocking));
+    }
+#endif
+    const size_t row = (size_t)pl->M * elem_size(pl);
+    pl->stage_in.ensure((size_t)B * row, &pl->dev_bytes); pl->stage_out.ensure((size_t)B * row, &pl->dev_bytes);
+    const long ng = (long)((B + group - 1) / group);
+    std::vector<cudaEvent_t> in_ready(ng), solved(ng);
+#ifndef HIPGP_EMU
+    for (long g = 0; g < ng; ++g) { CK(cudaEventCreateWithFlags(&in_ready[g], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&solved[g], cudaEventDisableTiming)); }
+    cudaStream_t cin = pl->copy_streams[0], cout = pl->copy_streams[1];
+    // the copy streams start after whatever the caller has queued on its stream (the staging buffers may still be in use)
+    cudaEvent_t start; CK(cudaEventCreateWithFlags(&start, cudaEventDisableTiming));
+    CK(cudaEventRecord(start, s)); CK(cudaStreamWaitEvent(cin, start, 0)); CK(cudaStreamWaitEvent(cout, start, 0));
+#else
+    cudaStream_t cin = s, cout = s;
+#endif
+    for (long g = 0; g < ng; ++g) {       // all uploads are queued up front: they run ahead of the solves on their own stream
+        const long b0 = g * group, nb = std::min<long>(group, B - b0);
+        CK(cudaMemcpyAsync((char*)pl->stage_in.p + b0 * row, (const char*)b_host + b0 * row, nb * row, cudaMemcpyHostToDevice, cin));
+#ifndef HIPGP_EMU
+        CK(cudaEventRecord(in_ready[g], cin));
+#endif
+    }
+    int iters_max = 0;
+    for (long g = 0; g < ng; ++g) {
+        const long b0 = g * group, nb = std::min<long>(group, B - b0);
+#ifndef HIPGP_EMU
+        CK(cudaStreamWaitEvent(s, in_ready[g], 0));
+#endif
+        int it = 0;
+        void* bg = (char*)pl->stage_in.p + b0 * row; void* xg = (char*)pl->stage_out.p + b0 * row;
+        DISPATCH(pl, pcg<float>(pl, bg, xg, nb, maxiter, tol, precond != 0, &it, nullptr, nullptr, nullptr, nullptr, s),
+                 pcg<double>(pl, bg, xg, nb, maxiter, tol, precond != 0, &it, nullptr, nullptr, nullptr, nullptr, s));
+        iters_max = std::max(iters_max, it);
+#ifndef HIPGP_EMU
+        CK(cudaEventRecord(solved[g], s));
+        CK(cudaStreamWaitEvent(cout, solved[g], 0));
+#endif
+        CK(cudaMemcpyAsync((char*)x_host + b0 * row, xg, nb * row, cudaMemcpyDeviceToHost, cout));
+    }
+#ifndef HIPGP_EMU
+    CK(cudaStreamSynchronize(cout));
+    CK(cudaStreamSynchronize(s));
+    for (long g = 0; g < ng; ++g) { cudaEventDestroy(in_ready[g]); cudaEventDestroy(solved[g]); }
+    cudaEventDestroy(start);
+#endif
+    if (iters_out) *iters_out = iters_max;
+    API_END
+}
+
 int hipgp_compute_kn(hipgp_plan* pl, const void* Knm, void* kn, int64_t B, int maxiter, double tol, int* iters_out, void* stream) {
     API_BEGIN
     set_device(pl);
@@ -866,6 +937,7 @@ thread_local dim3 t_threadIdx, t_blockIdx;
 dim3 g_blockDim, g_gridDim;
 Barrier g_block_barrier;
 Barrier g_warp_barrier[64];
+NamedBarrier g_named_barrier[16];
 unsigned char* g_dyn_smem = nullptr;
 double g_shfl_scratch[64][32][2];
 }

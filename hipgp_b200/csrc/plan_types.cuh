@@ -275,6 +275,7 @@ struct hipgp_plan {
     DevBuf stage_in, stage_out;            // device staging for the *_host entry points
     DevBuf corrU, corrV, corrS, corrLag;   // Toeplitz-column quadratic form (corr_api.inl): spectra of a chunk of pairs, their sum, lags
     void* pinned = nullptr;                // host flags mirror
+    cudaStream_t copy_streams[2] = {nullptr, nullptr};   // H2D / D2H streams of hipgp_pcg_host_pipelined
     long pcg_B = 0;
     int slab_rank = 0, slab_nranks = 1;      // slab-decomposed grid (axis 0 split over ranks); 1 = not decomposed
     void* run_x = nullptr; long run_B = 0; bool run_precond = true; double run_tol = 0; bool run_active = false;   // begin/step state

@@ -1,37 +1,63 @@
 // vec_api.inl -- C ABI for the stand-alone fused CG vector kernels and their scratch space.
+#include <map>
 #include <mutex>
+#include <utility>
 namespace hipgp {
+// Partial-sum scratch, one buffer per (device, stream): the kernel and its reduction are ordered on the caller's stream,
+// so two streams (or two devices of one process) must never share a buffer.
 static std::mutex g_scratch_mu;
-static DevBuf g_scratch;
+static std::map<std::pair<int, cudaStream_t>, DevBuf> g_scratch;
 static size_t g_scratch_total = 0;
 static const int kChunks = 64;
+static const long kMaxGridY = 65535;
+
+static double* scratch_for(cudaStream_t s, size_t bytes) {
+    int dev = 0;
+    CK(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(g_scratch_mu);
+    DevBuf& b = g_scratch[std::make_pair(dev, s)];
+    if (bytes > b.bytes) {
+        // an older, smaller buffer may still be read by work queued on this stream
+        if (b.p) CK(cudaStreamSynchronize(s));
+        b.ensure(bytes, &g_scratch_total);
+    }
+    return b.as<double>();
+}
 
 template <class T>
 static void vec_op(int op, void* x, void* r, const void* a, const void* b2, const double* num, const double* den, double* out,
                    long B, long M, cudaStream_t s) {
-    std::lock_guard<std::mutex> lk(g_scratch_mu);
+    if (B <= 0 || M <= 0) return;
     int nchunk = (int)std::min<long>(kChunks, std::max<long>(1, (M + 4095) / 4096));
-    g_scratch.ensure(sizeof(double) * (size_t)B * kChunks, &g_scratch_total);
+    double* scr = scratch_for(s, sizeof(double) * (size_t)B * kChunks);
     auto k = vec_kernel<T>;
-    HIPGP_LAUNCH(k, dim3(nchunk, (unsigned)B), dim3(256), 0, s, op, (T*)x, (T*)r, (const T*)a, (const T*)b2, num, den,
-                 g_scratch.as<double>(), M, nchunk);
-    CK_LAUNCH();
+    for (long b0 = 0; b0 < B; b0 += kMaxGridY) {        // grid.y is limited to 65535 right-hand sides per launch
+        const long nb = std::min(kMaxGridY, B - b0);
+        const size_t o = (size_t)b0 * (size_t)M;
+        HIPGP_LAUNCH(k, dim3(nchunk, (unsigned)nb), dim3(256), 0, s, op, x ? (T*)x + o : nullptr, r ? (T*)r + o : nullptr,
+                     a ? (const T*)a + o : nullptr, b2 ? (const T*)b2 + o : nullptr, num ? num + b0 : nullptr, den ? den + b0 : nullptr,
+                     scr + (size_t)b0 * nchunk, M, nchunk);
+        CK_LAUNCH();
+    }
     if (op != 2) {
         auto k2 = vec_reduce_kernel;
-        HIPGP_LAUNCH(k2, dim3((unsigned)((B + 127) / 128)), dim3(128), 0, s, g_scratch.as<double>(), out, nchunk, B);
+        HIPGP_LAUNCH(k2, dim3((unsigned)((B + 127) / 128)), dim3(128), 0, s, scr, out, nchunk, B);
         CK_LAUNCH();
     }
 }
 template <class T>
 static void mf_rowstats(const void* kn, const void* qm, const void* qS, long B, long E, void* out, cudaStream_t s) {
-    std::lock_guard<std::mutex> lk(g_scratch_mu);
     const int nchunk = (int)std::min<long>(kChunks, std::max<long>(1, (E + 8191) / 8192));
-    g_scratch.ensure(sizeof(double) * (size_t)B * 3 * kChunks, &g_scratch_total);
+    double* scr = scratch_for(s, sizeof(double) * (size_t)B * 3 * kChunks);
     auto k = mf_rowstats_kernel<T>;
-    HIPGP_LAUNCH(k, dim3(nchunk, (unsigned)B), dim3(256), 0, s, (const T*)kn, (const T*)qm, (const T*)qS, g_scratch.as<double>(), E, nchunk);
-    CK_LAUNCH();
+    for (long b0 = 0; b0 < B; b0 += kMaxGridY) {
+        const long nb = std::min(kMaxGridY, B - b0);
+        HIPGP_LAUNCH(k, dim3(nchunk, (unsigned)nb), dim3(256), 0, s, (const T*)kn + (size_t)b0 * (size_t)E, (const T*)qm, (const T*)qS,
+                     scr + (size_t)b0 * 3 * nchunk, E, nchunk);
+        CK_LAUNCH();
+    }
     auto k2 = mf_rowstats_reduce_kernel<T>;
-    HIPGP_LAUNCH(k2, dim3((unsigned)((3 * B + 127) / 128)), dim3(128), 0, s, g_scratch.as<double>(), (T*)out, nchunk, B);
+    HIPGP_LAUNCH(k2, dim3((unsigned)((3 * B + 127) / 128)), dim3(128), 0, s, scr, (T*)out, nchunk, B);
     CK_LAUNCH();
 }
 template <class T>
@@ -53,7 +79,13 @@ int hipgp_meanfield_rowstats(int dtype, const void* kn, const void* qm, const vo
 int hipgp_meanfield_colstats(int dtype, const void* kn, const void* w1, const void* w2, int64_t B, int64_t E, void* dm, void* lam,
                              void* stream) {
     API_BEGIN
-    if (B <= 0 || E <= 0) return 0;
+    if (E <= 0) return 0;
+    if (B <= 0) {   // an empty shard contributes zeros (the caller all-reduces these buffers)
+        const size_t w = dtype == HIPGP_F32 ? 4 : 8;
+        CK(cudaMemsetAsync(dm, 0, w * (size_t)E, (cudaStream_t)stream));
+        CK(cudaMemsetAsync(lam, 0, w * (size_t)E, (cudaStream_t)stream));
+        return 0;
+    }
     if (dtype == HIPGP_F32) mf_colstats<float>(kn, w1, w2, (long)B, (long)E, dm, lam, (cudaStream_t)stream);
     else mf_colstats<double>(kn, w1, w2, (long)B, (long)E, dm, lam, (cudaStream_t)stream);
     API_END

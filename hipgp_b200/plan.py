@@ -153,9 +153,17 @@ class Plan:
                                                           _stream_ptr(self.device)))
         return out_host
 
-    def pcg_host(self, b_host, x_host, maxiter=20, tol=1e-10, precond=True):
+    def pcg_host(self, b_host, x_host, maxiter=20, tol=1e-10, precond=True, group=None):
+        """Host buffers in / out (H2D + solve + D2H).  `group`: process the right-hand sides in independent groups of that
+        many and hide the copies of neighbouring groups behind the solve (hipgp_pcg_host_pipelined)."""
         assert not b_host.is_cuda and not x_host.is_cuda and b_host.is_contiguous() and x_host.is_contiguous()
         iters, ncb = C.c_int(), C.c_int()
+        if group:
+            with torch.cuda.device(self.device):
+                L.check(self.lib, self.lib.hipgp_pcg_host_pipelined(self._h, C.c_void_p(b_host.data_ptr()), C.c_void_p(x_host.data_ptr()),
+                                                                     b_host.shape[0], int(maxiter), float(tol), 1 if precond else 0,
+                                                                     int(group), C.byref(iters), _stream_ptr(self.device)))
+            return x_host, iters.value
         with torch.cuda.device(self.device):
             L.check(self.lib, self.lib.hipgp_pcg_host(self._h, C.c_void_p(b_host.data_ptr()), C.c_void_p(x_host.data_ptr()),
                                                        b_host.shape[0], int(maxiter), float(tol), 1 if precond else 0,

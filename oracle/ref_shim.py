@@ -1,9 +1,11 @@
 """Legacy-API shim that lets the UNMODIFIED reference (`/root/reference/ziggy`, pinned to
 torch 1.4) import and run on torch >= 2.x.  TEST INFRASTRUCTURE ONLY.
 
-Used in this container only, by `tests/golden/make_golden.py` (to generate the committed golden
-vectors) and by `tests/test_oracle_vs_reference.py` (skipped when /root/reference is absent, e.g. on
-the GPU box).  Nothing in `hipgp_b200/` may import this module.
+Used by `tests/golden/make_golden.py` (to generate the committed golden vectors, in the build container), by
+`tests/test_oracle_vs_reference.py` / `tests/test_gpu_dropin.py` and by `bench.py --impl reference`.  The reference is
+taken from `/root/reference` when that exists (build container) and otherwise from the staged, git-ignored, byte-identical
+copy `oracle/_ref/` written by `oracle/make_ref.py` (which is what travels to the GPU box); tests skip when neither is
+there.  Nothing in `hipgp_b200/` may import this module.
 
 What it patches (all removed from torch after 1.7):
   * `torch.fft(x, signal_ndim)` / `torch.ifft(x, signal_ndim)` -- function form, complex numbers as
@@ -19,7 +21,20 @@ import types
 import torch
 import torch.fft as _tfft
 
-REFERENCE_ROOT = "/root/reference"
+import os as _os
+
+_STAGED = _os.path.join(_os.path.dirname(_os.path.abspath(__file__)), "_ref")
+
+
+def reference_root():
+    """Directory that holds the unmodified `ziggy` package: /root/reference, else the staged copy oracle/_ref, else None."""
+    for root in ("/root/reference", _STAGED):
+        if _os.path.isdir(_os.path.join(root, "ziggy")):
+            return root
+    return None
+
+
+REFERENCE_ROOT = reference_root() or "/root/reference"
 
 
 class _CallableFFTModule(types.ModuleType):
@@ -61,11 +76,11 @@ def install():
 
 def import_reference():
     """Returns the unmodified reference package `ziggy` (raises if /root/reference is absent)."""
-    import os
-    if not os.path.isdir(os.path.join(REFERENCE_ROOT, "ziggy")):
-        raise ImportError("reference tree not present at %s" % REFERENCE_ROOT)
+    root = reference_root()
+    if root is None:
+        raise ImportError("reference tree not present (neither /root/reference nor oracle/_ref; run oracle/make_ref.py)")
     install()
-    if REFERENCE_ROOT not in sys.path:
-        sys.path.insert(0, REFERENCE_ROOT)
+    if root not in sys.path:
+        sys.path.insert(0, root)
     import ziggy  # noqa: F401
     return ziggy

@@ -208,3 +208,48 @@ def test_toeplitz_quadform_lane_layout(lib):
     want = zo.sym_toeplitz_derivative_quadratic_form(u.T.astype(np.float64), v.T.astype(np.float64))
     assert rel(out, want) < 1e-5, rel(out, want)
     lib.hipgp_plan_destroy(plan)
+
+
+def _numpy_matvec(col2d, v, which):
+    """crop IFFT(f(D) * FFT pad v) in fp64, D = max(Re FFT(even embedding), 1e-6) (toeplitz_tensor.py:21-33,70-83,114-125)."""
+    m0, m1 = col2d.shape
+    c = np.concatenate([col2d, col2d[-2:0:-1]], axis=0)
+    c = np.concatenate([c, c[:, -2:0:-1]], axis=1)
+    D = np.maximum(np.fft.fft2(c).real, 1e-6)
+    f = D if which == 0 else 1.0 / D
+    out = []
+    for row in v:
+        x = np.zeros(c.shape); x[:m0, :m1] = row.reshape(m0, m1)
+        out.append(np.fft.ifft2(f * np.fft.fft2(x)).real[:m0, :m1].reshape(-1))
+    return np.stack(out)
+
+
+@pytest.mark.parametrize("dt,B", [(np.float32, 1), (np.float32, 3), (np.float64, 2)])
+def test_block_local_column_pass_2048(lib, dt, B):
+    """The block-local column kernel (cols_blk_kernel.cuh) at the config-2 column length (1000 -> 2048 points): warp-owned
+    blocks between the first forward and the last inverse stage, shared-memory twiddle tables (fp32), several tiles per
+    persistent CTA, a partial last tile, both dtypes."""
+    m0, m1 = 1000, 9
+    x0 = np.linspace(0, 4, m0)[:, None]; x1 = np.linspace(-2, 2, m1)[None, :]
+    r = np.sqrt((x0 - x0[0, 0]) ** 2 + (x1 - x1[0, 0]) ** 2) / 0.05
+    col = (1 + np.sqrt(5) * r + 5 * r * r / 3) * np.exp(-np.sqrt(5) * r)
+    col[0, 0] += 1e-3
+    m = np.array([m0, m1], dtype=np.int64)
+    plan = C.c_void_p()
+    assert lib.hipgp_plan_create(2, m.ctypes.data_as(L._pi64), L.F32 if dt == np.float32 else L.F64, 0, C.byref(plan)) == 0
+    Ln = np.zeros(2, dtype=np.int64); Lw = np.zeros(2, dtype=np.int64)
+    assert lib.hipgp_plan_embedding(plan, Ln.ctypes.data_as(L._pi64), Lw.ctypes.data_as(L._pi64)) == 0
+    assert Ln[0] == 2048
+    colf = np.ascontiguousarray(col.astype(dt).reshape(-1))
+    ncl = C.c_int64()
+    assert lib.hipgp_plan_set_first_row(plan, ptr(colf), 1e-6, C.byref(ncl), None) == 0, lib.hipgp_last_error()
+    rng = np.random.RandomState(5)
+    v = np.ascontiguousarray(rng.randn(B, m0 * m1).astype(dt))
+    tol = 1e-5 if dt == np.float32 else 1e-10
+    for mode in (0, 1):
+        out = np.zeros_like(v)
+        assert lib.hipgp_matvec(plan, mode, ptr(v), ptr(out), B, None) == 0, lib.hipgp_last_error()
+        ref = _numpy_matvec(colf.astype(np.float64).reshape(m0, m1), v.astype(np.float64), mode)
+        lim = tol if mode == 0 else (2e-4 if dt == np.float32 else 1e-9)   # C^-1 amplifies the fp32 rounding of the small eigenvalues
+        assert rel(out, ref) < lim, (mode, rel(out, ref))
+    lib.hipgp_plan_destroy(plan)
