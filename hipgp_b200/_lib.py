@@ -43,12 +43,14 @@ SIGNATURES = {
     "hipgp_vec_p_update": (_i, [_i, _vp, _vp, _vp, _vp, _i64, _i64, _vp]),
     "hipgp_kxu": (_i, [_i, _i, _i, _d, _pd, _i, _d, _vp, _i64, _i, _pi64, _vp, _vp, _i, _vp, _vp]),
     "hipgp_kernel_pairwise": (_i, [_i, _i, _i, _d, _pd, _i, _d, _vp, _i64, _vp, _i64, _i, _vp, _i, _vp, _vp]),
+    "hipgp_kxu_param_grad": (_i, [_i, _i, _i, _d, _pd, _i, _vp, _i64, _i, _pi64, _vp, _vp, _i64, _vp, _i, _vp, _vp, _vp]),
     "hipgp_doubly_diag": (_i, [_i, _vp, _i64, _i, _d, _pd, _i, _vp, _vp, _vp, _i, _vp, _vp]),
     "hipgp_meanfield_rowstats": (_i, [_i, _vp, _vp, _vp, _i64, _i64, _vp, _vp]),
     "hipgp_meanfield_colstats": (_i, [_i, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp]),
     "hipgp_block_lam": (_i, [_i, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _d, _d, _vp, _vp]),
     "hipgp_block_diag_multiply": (_i, [_i, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _vp, _vp]),
     "hipgp_toeplitz_quadform": (_i, [_vp, _vp, _vp, _i64, _d, _vp, _vp]),
+    "hipgp_rt_column_grad": (_i, [_vp, _vp, _vp, _i64, _d, _vp, _vp]),
     "hipgp_plan_set_slab": (_i, [_vp, _i, _i]),
     "hipgp_slab_sizes": (_i, [_vp, _pi64, _pi64]),
     "hipgp_slab_stage1": (_i, [_vp, _vp, _vp, _vp]),

@@ -27,6 +27,7 @@ struct PcgDev {
     double* zr_prev;   // r.z of the previous iterate
     double* pAp;
     double* rr;
+    const double* rr_all;   // all B residual norms when `rr` points into a group of right-hand sides (nullptr: rr itself)
     double* partial;   // one slot per global row
     unsigned* row_cnt; // [B] rows finished for this rhs (self-resetting)
     unsigned* rhs_cnt; // [1] rhs finished (self-resetting)
@@ -84,7 +85,7 @@ __device__ __forceinline__ void pcg_finalize(const PcgDev& st, int kind, long g0
                     if (nb == (unsigned)st.B) {
                         __threadfence();
                         bool all = true;
-                        const volatile double* rr = st.rr;
+                        const volatile double* rr = st.rr_all ? st.rr_all : st.rr;
                         for (int i = 0; i < st.B; ++i) all = all && (sqrt(rr[i]) < st.tol);
                         st.rhs_cnt[0] = 0;
                         st.flags[1] += 1;

@@ -173,6 +173,80 @@ template <class T> __device__ __forceinline__ double block_sum_256(double v) {
     return t;
 }
 
+// ---- hyper-parameter derivatives of the point kernels (learn_kernel = True; the reference lets autograd differentiate
+// kernels.py:73-79,145-158).  dk/dsig2 = k / sig2;  dk/dell_d closed form: SqExp k t_d^2 / ell_d (t_d = (x_d-u_d)/ell_d);
+// Matern-1/2 k r/ell^2;  Matern-3/2 sig2 a^2 e^-a / ell (a = sqrt3 r/ell);  Matern-5/2 sig2 (a^2/3)(1+a) e^-a / ell (a = sqrt5 r/ell).
+template <class T>
+__device__ __forceinline__ void eval_point_grad(const KxuParams& P, const T* x, const T* u, double* dsig2, double* dell) {
+    dell[0] = dell[1] = dell[2] = 0.0;
+    if (P.kernel_id == 0) {
+        double sq = 0, td[3] = {0, 0, 0};
+        for (int d = 0; d < P.ndim; ++d) { const double t = ((double)x[d] - (double)u[d]) / P.ell[d]; td[d] = t * t; sq += t * t; }
+        const double e = ::exp(-0.5 * sq);
+        *dsig2 = e;
+        for (int d = 0; d < P.ndim; ++d) dell[d] = P.sig2 * e * td[d] / P.ell[d];
+        return;
+    }
+    double sq = 0;
+    for (int d = 0; d < P.ndim; ++d) { const double t = (double)x[d] - (double)u[d]; sq += t * t; }
+    const double r = ::sqrt(sq), ell = P.ell0;
+    if (P.kernel_id == 1) {
+        const double e = ::exp(-r / ell);
+        *dsig2 = e; dell[0] = P.sig2 * e * r / (ell * ell);
+    } else if (P.kernel_id == 2) {
+        const double a = 1.7320508075688772 * r / ell, e = ::exp(-a);
+        *dsig2 = (1.0 + a) * e; dell[0] = P.sig2 * a * a * e / ell;
+    } else {
+        const double a = 2.23606797749979 * r / ell, e = ::exp(-a);
+        *dsig2 = (1.0 + a + a * a / 3.0) * e; dell[0] = P.sig2 * (a * a / 3.0) * (1.0 + a) * e / ell;
+    }
+}
+
+// partial[(b * gridDim.x + blockIdx.x) * 4 + {0, 1, 2, 3}] = sum over this block's columns of G[b][j] * {dk/dsig2, dk/dell_0..2}
+// (modes POINT and SEMI_MC; grid as kxu_kernel)
+template <class T>
+__global__ void __launch_bounds__(256) kxu_grad_kernel(KxuParams P, const T* __restrict__ xb, const T* __restrict__ grids,
+                                                       const T* __restrict__ ypts, const T* __restrict__ alphas,
+                                                       const T* __restrict__ G, double* __restrict__ partial) {
+    const long b = blockIdx.y;
+    T x[3] = {0, 0, 0};
+    for (int d = 0; d < P.ndim; ++d) x[d] = xb[b * P.ndim + d];
+    double xnorm = 0;
+    for (int d = 0; d < P.ndim; ++d) xnorm += (double)x[d] * (double)x[d];
+    xnorm = ::sqrt(xnorm);
+    double acc[4] = {0, 0, 0, 0};
+    const long j0 = (long)blockIdx.x * (blockDim.x * 4);
+    for (int it = 0; it < 4; ++it) {
+        const long j = j0 + it * blockDim.x + threadIdx.x;
+        if (j >= P.M) break;
+        long rem = j;
+        T u[3] = {0, 0, 0};
+        if (ypts) { for (int d = 0; d < P.ndim; ++d) u[d] = ypts[j * P.ndim + d]; }
+        else { for (int d = P.ndim - 1; d >= 0; --d) { const int jd = (int)(rem % P.m[d]); rem /= P.m[d]; u[d] = grids[P.goff[d] + jd]; } }
+        const double g = (double)G[b * P.M + j];
+        double ds, de[3];
+        if (P.mode == 0) {
+            eval_point_grad<T>(P, x, u, &ds, de);
+            acc[0] += g * ds; acc[1] += g * de[0]; acc[2] += g * de[1]; acc[3] += g * de[2];
+        } else {          // SEMI_MC: mean over the stratified points alpha_t x, times |x|
+            double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+            for (int t = 0; t < P.npts; ++t) {
+                T xa[3];
+                const T al = alphas[t];
+                for (int d = 0; d < P.ndim; ++d) xa[d] = x[d] * al;
+                eval_point_grad<T>(P, u, xa, &ds, de);
+                s0 += ds; s1 += de[0]; s2 += de[1]; s3 += de[2];
+            }
+            const double f = g * xnorm / (double)P.npts;
+            acc[0] += f * s0; acc[1] += f * s1; acc[2] += f * s2; acc[3] += f * s3;
+        }
+    }
+    for (int c = 0; c < 4; ++c) {
+        const double t = block_sum_256<T>(acc[c]);
+        if (threadIdx.x == 0) partial[((size_t)b * gridDim.x + blockIdx.x) * 4 + c] = t;
+    }
+}
+
 // grid (nchunk, B), block 256; op 0: dot(a,b) | op 1: x += al p, r -= al Ap, dot(r,r) | op 2: p = z + be p
 template <class T>
 __global__ void __launch_bounds__(256) vec_kernel(int op, T* x, T* r, const T* a, const T* b2, const double* s_num, const double* s_den,

@@ -133,7 +133,7 @@ static void ws_elems(int D, const int* L, long P, const int* n_in, const int* n_
 
 // The pruned D-dimensional circular convolution:  out = crop_{n_out} IFFT( spec * FFT pad_{n_in} in ).
 template <class T>
-static void run_pipeline(hipgp_plan* pl, Geom<T>& g, const int* n_in, const int* n_out, const void* spec, int spec_kind,
+static void run_pipeline_group(hipgp_plan* pl, Geom<T>& g, const int* n_in, const int* n_out, const void* spec, int spec_kind,
                          long B, const RowsFusion& ff, const RowsFusion& fi, const PcgDev& st, bool gated, cudaStream_t s) {
     const int D = g.D;
     long w1, w2;
@@ -192,6 +192,54 @@ static void run_pipeline(hipgp_plan* pl, Geom<T>& g, const int* n_in, const int*
     R.total_rows = B * rows_out; R.nrows = (int)rows_out; R.n_real = n_out[D - 1];
     if (D == 1) { R.spec = spec; R.spec_kind = spec_kind; }
     launch_rows<T>(pl, true, R, s, fast);
+}
+
+
+// Right-hand sides per pass group (an experiment kept behind HIPGP_L2_GROUP_MB, default off).  Idea: 3-D pipelines make five
+// passes over two workspaces; if the workspaces of a GROUP of right-hand sides fit the 126 MB L2 together, every pass after
+// the first finds its input there instead of in HBM.  Measured on a B200 (profiles/README.md r2f, cfg4 B = 200 K matvec):
+// 7.21 ms ungrouped, 8.7 / 9.5 / 11.1 ms with 120 / 80 / 40 MB groups -- the small launches lose more than the L2 hits
+// return (the passes are issue / latency bound, not HBM bound), as at cfg2 in round 1.  So whole batches by default.
+template <class T>
+static long pass_group(hipgp_plan* pl, Geom<T>& g, const int* n_in, const int* n_out, long B) {
+    static const char* env = getenv("HIPGP_L2_GROUP_MB");
+    const double budget_mb = env ? atof(env) : 0.0;
+    if (budget_mb <= 0 || B <= 1) return B;
+    long w1, w2;
+    ws_elems(g.D, g.L, g.P, n_in, n_out, 1, &w1, &w2);
+    long vin = 1, vout = 1;
+    for (int d = 0; d < g.D; ++d) { vin *= n_in[d]; vout *= n_out[d]; }
+    const double per_rhs = (double)sizeof(cplx<T>) * (double)(w1 + w2) + (double)sizeof(T) * (double)(vin + vout);
+    long grp = (long)(budget_mb * 1048576.0 / per_rhs);
+    (void)pl;
+    return std::max<long>(1, std::min<long>(B, grp));
+}
+
+template <class T>
+static void run_pipeline(hipgp_plan* pl, Geom<T>& g, const int* n_in, const int* n_out, const void* spec, int spec_kind,
+                         long B, const RowsFusion& ff, const RowsFusion& fi, const PcgDev& st, bool gated, cudaStream_t s) {
+    const long grp = pass_group<T>(pl, g, n_in, n_out, B);
+    if (grp >= B) { run_pipeline_group<T>(pl, g, n_in, n_out, spec, spec_kind, B, ff, fi, st, gated, s); return; }
+    long vin = 1, vout = 1, rows_in = 1, rows_out = 1;
+    for (int d = 0; d < g.D; ++d) { vin *= n_in[d]; vout *= n_out[d]; }
+    for (int d = 0; d + 1 < g.D; ++d) { rows_in *= n_in[d]; rows_out *= n_out[d]; }
+    auto shift = [](const void* p, long elems) -> const void* { return p ? (const void*)((const T*)p + elems) : nullptr; };
+    for (long b0 = 0; b0 < B; b0 += grp) {
+        const long nb = std::min(grp, B - b0);
+        RowsFusion f2 = ff, i2 = fi;
+        // forward-side vectors have the input extents, inverse-side vectors the output extents (PCG: both are M)
+        f2.in = shift(ff.in, b0 * vin); f2.v0 = (void*)shift(ff.v0, b0 * vin); f2.v1 = (void*)shift(ff.v1, b0 * vin); f2.v2 = shift(ff.v2, b0 * vin);
+        i2.out = (void*)shift(fi.out, b0 * vout); i2.v0 = (void*)shift(fi.v0, b0 * vout);
+        PcgDev s2 = st;
+        if (st.zr) {          // per-right-hand-side scalars / counters of this group; the stop test still spans all B
+            s2.zr = st.zr + b0; s2.zr_prev = st.zr_prev + b0; s2.pAp = st.pAp + b0; s2.rr = st.rr + b0;
+            s2.rr_all = st.rr_all ? st.rr_all : st.rr;
+            s2.row_cnt = st.row_cnt + b0;
+            // partial sums: one slot per global row of the launch (forward launches count input rows, inverse ones output rows)
+            s2.partial = st.partial + b0 * std::max(rows_in, rows_out);
+        }
+        run_pipeline_group<T>(pl, g, n_in, n_out, spec, spec_kind, nb, f2, i2, s2, gated, s);
+    }
 }
 
 // forward-only transform of a real (L_0..L_{D-1}) fp64 array into W1 (raw spectrum, pipeline layout)
@@ -655,7 +703,7 @@ int hipgp_plan_destroy(hipgp_plan* pl) {
     for (DevBuf* b : {&pl->specK, &pl->specCinv, &pl->specW, &pl->Dm, &pl->Dinv, &pl->Dsqrt, &pl->colK, &pl->colG, &pl->colS,
                       &pl->tmpA, &pl->tmpB, &pl->costab, &pl->counts, &pl->W1, &pl->W2, &pl->vr, &pl->vp, &pl->vz, &pl->vAp,
                       &pl->partial, &pl->scal, &pl->cnt, &pl->flags, &pl->stage_in, &pl->stage_out, &pl->corrU, &pl->corrV, &pl->corrS,
-                      &pl->corrLag})
+                      &pl->corrLag, &pl->gradA})
         b->release(t);
     if (pl->pinned) cudaFreeHost(pl->pinned);
 #ifndef HIPGP_EMU

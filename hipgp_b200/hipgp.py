@@ -81,6 +81,10 @@ class ToeplitzInducingGP(nn.Module):
         """the structured K_uu for the current kernel parameters; cached while (sig2, ell, jitter) stay unchanged
         (the reference rebuilds it every minibatch, hipgp.py:143)."""
         sig2, ell = self.get_kernel_params()
+        if torch.is_grad_enabled() and any(isinstance(p, torch.Tensor) and p.requires_grad for p in (sig2, ell)):
+            # learn_kernel=True: the first row has to carry this step's autograd graph (hipgp.py:139-146 rebuilds it every call)
+            kfun = _GridKernelFn(self.kernel, (sig2, ell))
+            return ToeplitzTensor(xgrids=self.xgrids, kernel=kfun, batch_shape=None, jitter_val=self.jitter_val)
         key = (float(sig2), tuple(np.atleast_1d(ell.detach().cpu().numpy()).tolist()) if isinstance(ell, torch.Tensor)
                else float(ell), float(self.jitter_val), str(self.xgrids[0].device))
         if self._Kmm_cache is None or self._Kmm_cache[0] != key:
@@ -93,7 +97,9 @@ class ToeplitzInducingGP(nn.Module):
         """kn = R^T Kmm^{-1} Kmn : (bsz, M) -> (bsz, M')  (hipgp.py:117-146)"""
         if Kmm is None:
             Kmm = self.make_Kmm()
-        if Knm.requires_grad:
+        if torch.is_grad_enabled() and (Knm.requires_grad or Kmm.column.requires_grad):
+            # differentiable route (learn_kernel=True): InvMatmul (second PCG + Toeplitz-column quadratic form in backward) and the
+            # R^T matvec with its column gradient
             d0 = Kmm.inv_matmul(Knm, do_precond=True, maxiter=maxiter_cg, tol=tol)
             return Kmm._matmul_by_RT(d0)
         return Kmm._plan.compute_kn(Knm, maxiter=maxiter_cg, tol=tol)
@@ -197,6 +203,10 @@ class MeanFieldToeplitzGP(ToeplitzInducingGP):
         sl = hdist.shard_slice(bsz) if sharded else slice(0, bsz)
         xb, yb = xbatch[sl], ybatch[sl]
         nb = noise_std_batch[sl] if noise_std_batch is not None else None
+        learn_hyper = torch.is_grad_enabled() and (self.learn_kernel or (self.learn_noise and nb is None))
+        if learn_hyper:
+            return self._elbo_and_grad_traced(xb, yb, nb, bsz, sharded, maxiter_cg, integrated_obs, semi_integrated_estimator,
+                                              semi_integrated_samps, Kmm)
         with torch.no_grad():
             Knm, Knn_diag = self._make_grams(xb, integrated_obs=integrated_obs,
                                              semi_integrated_estimator=semi_integrated_estimator,
@@ -215,21 +225,85 @@ class MeanFieldToeplitzGP(ToeplitzInducingGP):
             mse = (knt_m - y) ** 2
             variance = Knn_diag.reshape(-1) - knt_kn + knSkn
             batch_an = -0.5 * ivar_noise * (mse + variance) - log_noise_std - 0.5 * np.log(2 * np.pi)
-            # natural-gradient statistics, hipgp.py:241-250
-            bdiff = ivar_noise * (knt_m - y)
-            dm_sum, lam_sum = self._batch_stats(kn, bdiff, ivar_noise)
             an_sum = batch_an.sum().reshape(1)
-            if sharded:
-                hdist.allreduce_packed([dm_sum, lam_sum, an_sum])      # the one data-path collective of the step
-            bscale = self.N / bsz
-            data_dm = -dm_sum[:, None]
-            dm = bscale * data_dm - qm
-            deta1, deta2 = self._natural_gradient(dm, lam_sum, qm, bscale)
-            self.global_theta1.grad = -deta1
-            self.global_theta2.grad = -deta2
-            kl_to_prior = self.get_kl_to_prior(qm, qS)
-            elbo_estimate = an_sum[0] / bsz - (kl_to_prior / self.N)
+            elbo_estimate = self._natural_gradient_step(kn, knt_m, y, ivar_noise, an_sum, qm, qS, bsz, sharded)
         return elbo_estimate
+
+    def _natural_gradient_step(self, kn, knt_m, y, ivar_noise, an_sum, qm, qS, bsz, sharded):
+        """natural-gradient statistics (hipgp.py:241-250), their all-reduce over the shards of the minibatch, the two
+        `.grad` fields; returns the (detached) ELBO estimate"""
+        bdiff = ivar_noise * (knt_m - y)
+        dm_sum, lam_sum = self._batch_stats(kn, bdiff, ivar_noise)
+        if sharded:
+            hdist.allreduce_packed([dm_sum, lam_sum, an_sum])      # the one data-path collective of the step
+        bscale = self.N / bsz
+        data_dm = -dm_sum[:, None]
+        dm = bscale * data_dm - qm
+        deta1, deta2 = self._natural_gradient(dm, lam_sum, qm, bscale)
+        self.global_theta1.grad = -deta1
+        self.global_theta2.grad = -deta2
+        kl_to_prior = self.get_kl_to_prior(qm, qS)
+        return an_sum[0] / bsz - (kl_to_prior / self.N)
+
+    def compute_batch_an(self, xbatch, ybatch, noise_std_batch=None, qm=None, qS=None, Knm=None, Knn_diag=None, kn=None,
+                         maxiter_cg=10, integrated_obs=False, semi_integrated_estimator="analytic", semi_integrated_samps=10,
+                         Kmm=None, **_ignored):
+        """a_n = -1/2 ln 2 pi sigma_n^2 - 1/(2 sigma_n^2) [K_nn - k_n^T k_n + k_n^T S k_n + (k_n^T m - y)^2]  (hipgp.py:370-414),
+        in differentiable torch ops on k_n: this is the route the hyper-parameter gradients take"""
+        if qm is None or qS is None:
+            qm, qS = self.standard_variational_params()
+        if Knm is None or Knn_diag is None:
+            Knm, Knn_diag = self._make_grams(xbatch, integrated_obs=integrated_obs, semi_integrated_estimator=semi_integrated_estimator,
+                                             semi_integrated_samps=semi_integrated_samps)
+        if kn is None:
+            kn = self.compute_kn(Knm, maxiter_cg=maxiter_cg, Kmm=Kmm)
+        y = ybatch.reshape(-1)
+        knt_kn = torch.sum(kn * kn, dim=-1)
+        knt_m = kn.matmul(qm).reshape(-1)
+        knSkn = self._knSkn_traced(kn, qS)
+        if noise_std_batch is not None:
+            ivar_noise = (1 / (noise_std_batch ** 2)).reshape(-1)
+            log_noise_std = torch.log(noise_std_batch).reshape(-1)
+        else:
+            ivar_noise = torch.exp(-self.log_noise2)
+            log_noise_std = 0.5 * self.log_noise2
+        mse = (knt_m - y) ** 2
+        variance = Knn_diag.reshape(-1) - knt_kn + knSkn
+        return -0.5 * ivar_noise * (mse + variance) - log_noise_std - 0.5 * np.log(2 * np.pi)
+
+    def _knSkn_traced(self, kn, qS):
+        return torch.sum((kn * qS.t()) * kn, dim=-1)          # hipgp.py:523-524
+
+    def elbo(self, xbatch, ybatch, noise_std_batch=None, maxiter_cg=10, integrated_obs=False, semi_integrated_estimator="analytic",
+             semi_integrated_samps=10, Kmm=None, print_debug_info=False):
+        """the ELBO estimate with every gradient on the tape (hipgp.py:160-192)"""
+        Knm, Knn_diag = self._make_grams(xbatch, integrated_obs=integrated_obs, semi_integrated_estimator=semi_integrated_estimator,
+                                         semi_integrated_samps=semi_integrated_samps)
+        kn = self.compute_kn(Knm, maxiter_cg=maxiter_cg, Kmm=Kmm)
+        qm, qS = self.standard_variational_params()
+        batch_an = self.compute_batch_an(xbatch, ybatch, noise_std_batch, qm=qm, qS=qS, Knm=Knm, Knn_diag=Knn_diag, kn=kn)
+        return torch.mean(batch_an) - (self.get_kl_to_prior(qm, qS) / self.N)
+
+    def _elbo_and_grad_traced(self, xb, yb, nb, bsz, sharded, maxiter_cg, integrated_obs, estimator, samps, Kmm):
+        """learn_kernel / learn_noise: the reference keeps the ELBO on the autograd tape through k_n = R^T K^-1 K_un down to
+        log_sig2 / log_ell / log_noise2 ("we still trace kernel grads", hipgp.py:214-218) while the natural gradients of the
+        variational parameters are set by hand.  Here K_xu, the first row, the solve and R^T are custom autograd nodes around
+        the CUDA kernels; the statistics downstream of k_n are torch ops.  Sharded minibatches: every rank backpropagates its
+        own part of the ELBO; the caller all-reduces the hyper-parameter gradients (as DistributedDataParallel would)."""
+        Knm, Knn_diag = self._make_grams(xb, integrated_obs=integrated_obs, semi_integrated_estimator=estimator, semi_integrated_samps=samps)
+        kn = self.compute_kn(Knm, maxiter_cg=maxiter_cg, Kmm=Kmm)
+        with torch.no_grad():
+            qm, qS = self.standard_variational_params()
+        batch_an = self.compute_batch_an(xb, yb, nb, qm=qm, qS=qS, Knm=Knm, Knn_diag=Knn_diag, kn=kn)
+        with torch.no_grad():
+            knd = kn.detach()
+            y = yb.reshape(-1)
+            ivar_noise = (1 / (nb ** 2)).reshape(-1) if nb is not None else torch.exp(-self.log_noise2) * torch.ones_like(y)
+            knt_m = self._row_stats(knd, qm, qS)[0]
+            an_sum = batch_an.detach().sum().reshape(1)
+            self._natural_gradient_step(knd, knt_m, y, ivar_noise, an_sum, qm, qS, bsz, sharded)
+        # traced estimate: this rank's observations over the GLOBAL minibatch size (= torch.mean when not sharded)
+        return batch_an.sum() / bsz - (self.get_kl_to_prior(qm, qS) / self.N)
 
     def predict(self, x, integrated_obs=False, semi_integrated_estimator="analytic", semi_integrated_samps=10,
                 maxiter_cg=50, Kmm=None, _on_device=False):
@@ -262,6 +336,9 @@ class BlockToeplitzGP(MeanFieldToeplitzGP):
         ToeplitzInducingGP.__init__(self, kernel, xgrids, num_obs, sig2_init=sig2_init, ell_init=ell_init,
                                     noise2_init=noise2_init, learn_kernel=learn_kernel, learn_noise=learn_noise, dtype=dtype,
                                     whitened_type=whitened_type, parameterization=parameterization, jitter_val=jitter_val)
+        if learn_kernel or learn_noise:
+            raise NotImplementedError("hipgp_b200.BlockToeplitzGP: hyper-parameter learning (learn_kernel / learn_noise) is wired for the "
+                                      "mean-field family only; the block family keeps its kernel parameters fixed")
         input_dim = len(xgrids)
         if block_sizes is not None:
             assert input_dim == len(block_sizes), "xgrids ndim = {}, block ndim = {}".format(input_dim, len(block_sizes))

@@ -52,6 +52,58 @@ def _f(v):
     return float(v.detach()) if isinstance(v, torch.Tensor) else float(v)
 
 
+def _wants_grad(*vals):
+    return torch.is_grad_enabled() and any(isinstance(v, torch.Tensor) and v.requires_grad for v in vals)
+
+
+class _KxuParamGrad(torch.autograd.Function):
+    """K_xu (or a pairwise kernel matrix) as a differentiable function of (sig2, ell): the forward is the same CUDA call
+    as the no-grad path, the backward reduces G * dk/d(sig2, ell_d) on the fly (hipgp_kxu_param_grad) -- the (B, M)
+    derivative matrices are never formed.  learn_kernel=True in the reference differentiates kernels.py:73-79,145-158
+    with autograd."""
+
+    @staticmethod
+    def forward(ctx, sig2_t, ell_t, call, meta):
+        ctx.meta = meta
+        ctx.ell_numel = ell_t.numel()
+        ctx.sig2_dtype, ctx.ell_dtype, ctx.ell_shape = sig2_t.dtype, ell_t.dtype, ell_t.shape
+        return call((sig2_t.detach(), ell_t.detach()))
+
+    @staticmethod
+    def backward(ctx, G):
+        m = ctx.meta
+        lib = L.load()
+        G = G.to(m["dtype"]).contiguous()
+        B, Mcols = G.shape
+        nbx = (Mcols + 1023) // 1024
+        partial = torch.empty((B, nbx, 4), dtype=torch.float64, device=G.device)
+        with torch.cuda.device(G.device):
+            L.check(lib, lib.hipgp_kxu_param_grad(_DT[m["dtype"]], m["kernel_id"], m["mode"], m["sig2"], m["ellv"], m["n_ell"], _ptr(m["x"]), B,
+                                                  m["D"], m["marr"], _ptr(m["grids"]), _ptr(m["ypts"]), Mcols, _ptr(m["mc_alphas"]), m["npts"],
+                                                  _ptr(G), C.cast(C.c_void_p(partial.data_ptr()), L._pd), _stream(G.device)))
+        tot = partial.sum(dim=(0, 1))
+        g_sig2 = tot[0].to(ctx.sig2_dtype).reshape(()) if ctx.needs_input_grad[0] else None
+        g_ell = None
+        if ctx.needs_input_grad[1]:
+            g_ell = (tot[1:4].sum() if ctx.ell_numel == 1 else tot[1:1 + ctx.ell_numel]).to(ctx.ell_dtype).reshape(ctx.ell_shape)
+        return g_sig2, g_ell, None, None
+
+
+def _with_param_grad(call, params, meta):
+    """run `call(params)`; route it through _KxuParamGrad when a hyper-parameter tensor requires a gradient"""
+    sig2, ell = params
+    if not _wants_grad(sig2, ell):
+        return call(params)
+    if meta["kernel_id"] == L.K_GNEITING or meta["mode"] not in (L.KXU_POINT, L.KXU_SEMI_MC):
+        raise NotImplementedError("hipgp_b200: hyper-parameter gradients (learn_kernel=True) are built for the SqExp / Matern point "
+                                  "kernels and their Monte-Carlo line integrals; not for this kernel / estimator")
+    dev = meta["x"].device
+    s_t = sig2 if isinstance(sig2, torch.Tensor) else torch.tensor(float(sig2), dtype=torch.float64, device=dev)
+    e_t = ell if isinstance(ell, torch.Tensor) else torch.tensor(np.asarray(ell, dtype=np.float64), device=dev)
+    meta["sig2"] = _f(sig2)
+    return _KxuParamGrad.apply(s_t, e_t, call, meta)
+
+
 def _pairwise(kernel_id, mode, x, y, params, dtype, alpha=1.0, mc_alphas=None):
     """out (n, m) = k(x_i, y_j);   x: (n, D), y: (m, D)"""
     _need_cuda(x, y, mc_alphas)
@@ -64,14 +116,19 @@ def _pairwise(kernel_id, mode, x, y, params, dtype, alpha=1.0, mc_alphas=None):
     n, D = x.shape
     m = y.shape[0]
     ellv, n_ell = _ell_array(ell, D)
-    out = torch.empty((n, m), dtype=dtype, device=x.device)
     npts = 0
     if mc_alphas is not None:
         mc_alphas = mc_alphas.detach().to(dtype).contiguous(); npts = mc_alphas.numel()
-    with torch.cuda.device(x.device):
-        L.check(lib, lib.hipgp_kernel_pairwise(_DT[dtype], kernel_id, mode, _f(sig2), ellv, n_ell, float(alpha), _ptr(x), n,
-                                               _ptr(y), m, D, _ptr(mc_alphas), npts, _ptr(out), _stream(x.device)))
-    return out
+
+    def call(p):
+        out = torch.empty((n, m), dtype=dtype, device=x.device)
+        with torch.cuda.device(x.device):
+            L.check(lib, lib.hipgp_kernel_pairwise(_DT[dtype], kernel_id, mode, _f(p[0]), ellv, n_ell, float(alpha), _ptr(x), n,
+                                                   _ptr(y), m, D, _ptr(mc_alphas), npts, _ptr(out), _stream(x.device)))
+        return out
+    meta = dict(kernel_id=kernel_id, mode=mode, dtype=dtype, ellv=ellv, n_ell=n_ell, x=x, D=D, marr=None, grids=None, ypts=y,
+                mc_alphas=mc_alphas, npts=npts)
+    return _with_param_grad(call, params, meta)
 
 
 def _on_grid(kernel_id, mode, x, xgrids, params, dtype, alpha=1.0, mc_alphas=None):
@@ -88,15 +145,20 @@ def _on_grid(kernel_id, mode, x, xgrids, params, dtype, alpha=1.0, mc_alphas=Non
     grids = torch.cat([g.detach().to(dtype).reshape(-1) for g in xgrids]).contiguous()
     ellv, n_ell = _ell_array(ell, D)
     M = int(np.prod(dims))
-    out = torch.empty((n, M), dtype=dtype, device=x.device)
     npts = 0
     if mc_alphas is not None:
         mc_alphas = mc_alphas.detach().to(dtype).contiguous(); npts = mc_alphas.numel()
     marr = (C.c_int64 * D)(*dims)
-    with torch.cuda.device(x.device):
-        L.check(lib, lib.hipgp_kxu(_DT[dtype], kernel_id, mode, _f(sig2), ellv, n_ell, float(alpha), _ptr(x), n, D, marr,
-                                   _ptr(grids), _ptr(mc_alphas), npts, _ptr(out), _stream(x.device)))
-    return out
+
+    def call(p):
+        out = torch.empty((n, M), dtype=dtype, device=x.device)
+        with torch.cuda.device(x.device):
+            L.check(lib, lib.hipgp_kxu(_DT[dtype], kernel_id, mode, _f(p[0]), ellv, n_ell, float(alpha), _ptr(x), n, D, marr,
+                                       _ptr(grids), _ptr(mc_alphas), npts, _ptr(out), _stream(x.device)))
+        return out
+    meta = dict(kernel_id=kernel_id, mode=mode, dtype=dtype, ellv=ellv, n_ell=n_ell, x=x, D=D, marr=marr, grids=grids, ypts=None,
+                mc_alphas=mc_alphas, npts=npts)
+    return _with_param_grad(call, params, meta)
 
 
 def mc_alphas(npts, dtype, device):
@@ -323,5 +385,5 @@ def first_row(xgrids, kernel, params, jitter=None):
     x0 = torch.stack([g[0] for g in xgrids]).reshape(1, -1)
     row = kernel.forward_grid(x0, xgrids, params).reshape(-1)
     if jitter is not None:
-        row[0] += jitter
+        row = torch.cat([row[:1] + jitter, row[1:]])        # (out of place: the row may carry the hyper-parameter graph)
     return row

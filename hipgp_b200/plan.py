@@ -130,6 +130,18 @@ class Plan:
                                                          _stream_ptr(self.device)))
         return out
 
+    def rt_column_grad(self, vec, grad_out, scale=1.0):
+        """d/d column of sum_b grad_out_b . (R^T vec_b)  (autograd through toeplitz_tensor.py:21-33,85-97 in the reference).
+        vec (B, M), grad_out (B, M').  Returns (M,)."""
+        v = self._vec(vec, self.M, "vec"); g = self._vec(grad_out, self.Mprime, "grad_out")
+        if v.shape[0] != g.shape[0]:
+            raise ValueError("vec and grad_out must have the same number of rows")
+        out = torch.empty(self.M, dtype=self.dtype, device=self.device)
+        with torch.cuda.device(self.device):
+            L.check(self.lib, self.lib.hipgp_rt_column_grad(self._h, C.c_void_p(v.data_ptr()), C.c_void_p(g.data_ptr()), v.shape[0],
+                                                             float(scale), C.c_void_p(out.data_ptr()), _stream_ptr(self.device)))
+        return out
+
     def toeplitz_quadform(self, left, right, scale=1.0):
         """sum_j u_j^T (dT/dc_i) v_j over the FLATTENED M-vectors (gpt_toeplitz.py:169-209
         `sym_toeplitz_derivative_quadratic_form`); left / right are (S, M).  Returns (M,)."""
@@ -300,25 +312,32 @@ def row_dot(a, b):
 
 
 class _ToeplitzMatvec(torch.autograd.Function):
-    """The four structured matvecs as differentiable LINEAR maps of their vector argument, like the torch ops of the
-    reference (toeplitz_tensor.py:70-125): K and the C^-1 block are symmetric, R^T and R are each other's transpose.
-    The dependence on the Toeplitz column (through the spectrum) is NOT differentiated here -- a graph that asks for it
-    fails loudly instead of returning a gradient with that term missing (InvMatmul handles the column for the solve)."""
+    """The four structured matvecs as differentiable maps, like the torch ops of the reference (toeplitz_tensor.py:70-125).
+    In the vector argument they are linear: K and the C^-1 block are symmetric, R^T and R are each other's transpose.
+    In the Toeplitz column (kernel hyper-parameters through the spectrum): built for R^T -- the one matvec the model
+    differentiates (k_n = R^T K^-1 K_un, hipgp.py:139-146; the solve's column gradient is InvMatmul.backward) -- through
+    `hipgp_rt_column_grad`; the other three fail loudly instead of returning a gradient with that term missing."""
     _ADJOINT = {L.MV_K: L.MV_K, L.MV_CINV: L.MV_CINV, L.MV_RT: L.MV_R, L.MV_R: L.MV_RT}
 
     @staticmethod
     def forward(ctx, plan, column, vec, mode):
         ctx.plan, ctx.mode = plan, mode
+        ctx.save_for_backward(vec)
         return plan.matvec(mode, vec)
 
     @staticmethod
     def backward(ctx, grad_output):
+        (vec,) = ctx.saved_tensors
+        g = grad_output.contiguous()
+        gc = None
         if ctx.needs_input_grad[1]:
-            raise NotImplementedError("hipgp_b200: gradient of a structured matvec with respect to the Toeplitz column "
-                                      "(kernel hyper-parameters through the spectrum, toeplitz_tensor.py:70-125) is not built; "
-                                      "InvMatmul.backward covers the column gradient of the solve")
-        gv = ctx.plan.matvec(_ToeplitzMatvec._ADJOINT[ctx.mode], grad_output.contiguous()) if ctx.needs_input_grad[2] else None
-        return None, None, gv, None
+            if ctx.mode != L.MV_RT:
+                raise NotImplementedError("hipgp_b200: gradient of this structured matvec with respect to the Toeplitz column "
+                                          "(toeplitz_tensor.py:70-125) is not built; R^T (hipgp_rt_column_grad) and the solve "
+                                          "(InvMatmul.backward) are")
+            gc = ctx.plan.rt_column_grad(vec.detach(), g)
+        gv = ctx.plan.matvec(_ToeplitzMatvec._ADJOINT[ctx.mode], g) if ctx.needs_input_grad[2] else None
+        return None, gc, gv, None
 
 
 def matvec_autograd(plan, mode, vec, column=None):

@@ -114,6 +114,13 @@ int hipgp_kxu(int dtype, int kernel_id, int mode, double sig2, const double* ell
 int hipgp_kernel_pairwise(int dtype, int kernel_id, int mode, double sig2, const double* ell, int n_ell, double gneiting_alpha,
                           const void* x_dev, int64_t n, const void* y_dev, int64_t m, int ndim,
                           const void* mc_alphas_dev, int npts, void* out_dev, void* stream);
+/* hyper-parameter derivatives of K_xu for learn_kernel=True (the reference lets autograd differentiate kernels.py:73-79,
+ * 145-158): per-block partial sums of G * {dk/dsig2, dk/dell_0, dk/dell_1, dk/dell_2} over the columns of row b; `partial` holds
+ * B * ceil(M/1024) * 4 doubles, the caller adds them up.  Either the 1-D grids (grids != NULL, as hipgp_kxu) or an explicit
+ * second point set ypts (n_y x ndim, as hipgp_kernel_pairwise).  Modes POINT and SEMI_MC; SqExp / Matern kernels. */
+int hipgp_kxu_param_grad(int dtype, int kernel_id, int mode, double sig2, const double* ell, int n_ell, const void* x_dev, int64_t B,
+                         int ndim, const int64_t* m, const void* grids_dev, const void* ypts_dev, int64_t n_y, const void* mc_alphas_dev,
+                         int npts, const void* G_dev, double* partial_dev, void* stream);
 /* KernelDoublyDiagInterpolator.forward (kernels.py:199-218); table = distance_grid, slopes, knn (ntab each, device) */
 int hipgp_doubly_diag(int dtype, const void* x_dev, int64_t B, int ndim, double sig2, const double* ell, int n_ell,
                       const void* distance_grid_dev, const void* slopes_dev, const void* knn_dev, int ntab,
@@ -145,6 +152,11 @@ int hipgp_block_diag_multiply(int dtype, const void* S_dev, const void* v_dev, c
  * over the flattened index.  InvMatmul.backward is this with S = B, u = left solves, v = right solves, scale = -1. */
 int hipgp_toeplitz_quadform(hipgp_plan* plan, const void* left_dev, const void* right_dev, int64_t S, double scale,
                             void* out_dev, void* stream);
+/* gradient of sum_b grad_out_b . (R^T vec_b) with respect to the Toeplitz column (learn_kernel=True; the reference gets it
+ * from autograd through toeplitz_tensor.py:21-33,85-97: D_sqrt = sqrt(max(Re FFT C, 1e-6))).  vec (B,M), grad_out (B,M'),
+ * out (M) in the plan dtype, multiplied by `scale`.  Clamped eigenvalues contribute nothing (torch.clamp's gradient). */
+int hipgp_rt_column_grad(hipgp_plan* plan, const void* vec_dev, const void* grad_out_dev, int64_t B, double scale, void* out_dev,
+                         void* stream);
 
 /* ---- slab-decomposed 3-D grids (axis 0 split over `nranks` GPUs; K and C^-1 matvecs; one right-hand side).
  * The reference has no multi-GPU path; this is the grid-sharded route of SURVEY.md 8e.  A matvec is

@@ -14,6 +14,9 @@ own implementation.  Files:
                                gradients of InvMatmul.backward (_inv_matmul.py:28-64) through ToeplitzTensor.inv_matmul
   block_step_<dtype>.npz       BlockToeplitzGP (hipgp.py:527-690): define_block_chunks (util.py:79-126) index maps in 2-D and 3-D,
                                get_lam, block_diag_multiply, compute_knSkn, elbo_and_grad (block branch :251-261), predict
+  learn_kernel_<dtype>.npz     learn_kernel=True / learn_noise=True: MeanFieldToeplitzGP.elbo_and_grad followed by (-elbo).backward() as
+                               svigp_fit does (svi_gp.py:317-329): the autograd gradients of log_sig2, log_ell, log_noise2 (through
+                               kernels.py, ToeplitzTensor.__init__, InvMatmul, _matmul_by_RT), and the column gradient of R^T alone
   notebook_counts.npz          preconditioner-analysis.ipynb saved outputs (raw lines 101-103,142-144,183-185,224-226)
 """
 import os
@@ -242,6 +245,60 @@ def make_svi_step():
         print("svi_step", dname, float(elbo))
 
 
+def make_learn_kernel():
+    """Hyper-parameter gradients of the reference (hipgp.py:208-218, svi_gp.py:317-329) on a small 2-D problem, plus the
+    gradient of sum(G * R^T v) with respect to the Toeplitz column (autograd through toeplitz_tensor.py:21-33,85-97)."""
+    for dname, dtype in DT.items():
+        out = {}
+        for tag, kname, learn_noise in (("matern32", "matern32", False), ("sqexp_noise", "sqexp", True), ("matern52", "matern52", False)):
+            torch.manual_seed(31)
+            grids = [(-5.7, 1.8, 14), (50., 55.5, 11)]
+            xgrids = [torch.linspace(lo, hi, m, dtype=dtype) for lo, hi, m in grids]
+            kern = get_kernel(kname, dtype)
+            mod = zh.MeanFieldToeplitzGP(kern, xgrids, num_obs=500, sig2_init=0.9, ell_init=0.7, noise2_init=0.2, dtype=dtype, jitter_val=1e-3,
+                                         learn_kernel=True, learn_noise=learn_noise)
+            lo = torch.tensor([g[0] for g in grids], dtype=dtype); hi = torch.tensor([g[1] for g in grids], dtype=dtype)
+            xb = lo + (hi - lo) * torch.rand(8, 2, dtype=dtype)
+            yb = torch.randn(8, 1, dtype=dtype)
+            nb = None if learn_noise else 0.3 + 0.1 * torch.rand(8, 1, dtype=dtype)
+            th1 = mod.global_theta1.data.clone(); th2 = mod.global_theta2.data.clone()
+            elbo = mod.elbo_and_grad(xb, yb, nb, maxiter_cg=60)
+            (-elbo).backward()
+            out[tag + "_grids"] = np.array(grids); out[tag + "_x"] = xb.numpy(); out[tag + "_y"] = yb.numpy()
+            if nb is not None:
+                out[tag + "_noise_std"] = nb.numpy()
+            out[tag + "_theta1"] = th1.numpy(); out[tag + "_theta2"] = th2.numpy(); out[tag + "_elbo"] = float(elbo)
+            out[tag + "_g_log_sig2"] = float(mod.log_sig2.grad); out[tag + "_g_log_ell"] = float(mod.log_ell.grad)
+            if learn_noise:
+                out[tag + "_g_log_noise2"] = float(mod.log_noise2.grad)
+            out[tag + "_g1"] = mod.global_theta1.grad.detach().numpy(); out[tag + "_g2"] = mod.global_theta2.grad.detach().numpy()
+            out[tag + "_params"] = np.array([0.9, 0.7, 0.2, 1e-3, 500])
+            print("learn_kernel", dname, tag, float(elbo), float(mod.log_sig2.grad), float(mod.log_ell.grad))
+        # R^T column gradient alone, 2-D and 3-D, with clamped eigenvalues in the SqExp case
+        for tag, grids, kname, sig2, ell in (("rt2d", [(0., 1., 9), (0., 2., 12)], "matern32", 1.2, 0.4),
+                                             ("rt3d", [(0., 1., 5), (0., 1., 4), (0., 2., 6)], "sqexp", 0.8, 0.5)):
+            torch.manual_seed(32)
+            xgrids = [torch.linspace(lo, hi, m, dtype=dtype) for lo, hi, m in grids]
+            kern = get_kernel(kname, dtype)
+            kfun = lambda x, y: kern.forward(x, y, params=(sig2, ell))
+            tt = ToeplitzTensor(xgrids=xgrids, kernel=kfun, batch_shape=None, jitter_val=1e-3)
+            col = tt.column.detach().clone().requires_grad_(True)
+            # rebuild the spectrum from a column that is on the tape, exactly as toeplitz_tensor.py:19-33 does
+            C = tt.circulant_embed(col.view(tt.dims)); Cc = tt.make_complex(C)
+            D = torch.fft(Cc, signal_ndim=tt.ndim)
+            D0 = D[..., 0].clamp(min=1e-6)
+            tt.D_sqrt = torch.stack([torch.sqrt(D0), torch.zeros_like(D0)], dim=-1)
+            M = int(np.prod(tt.dims)); E = int(np.prod(tt.C.shape))
+            v = torch.randn(3, M, dtype=dtype); G = torch.randn(3, E, dtype=dtype)
+            tt.set_batch_shape((3,))
+            y = tt._matmul_by_RT(v)
+            (y * G).sum().backward()
+            out[tag + "_grids"] = np.array(grids); out[tag + "_column"] = tt.column.detach().numpy(); out[tag + "_v"] = v.numpy()
+            out[tag + "_G"] = G.numpy(); out[tag + "_gcol"] = col.grad.numpy(); out[tag + "_nclamped"] = int((D[..., 0] < 1e-6).sum())
+            print("rt column grad", dname, tag, "clamped", out[tag + "_nclamped"], float(col.grad.norm()))
+        np.savez_compressed(os.path.join(HERE, "learn_kernel_%s.npz" % dname), **out)
+
+
 def make_quadform():
     """sym_toeplitz_derivative_quadratic_form on seeded vectors, and autograd through the reference's InvMatmul."""
     from ziggy.misc.gpt_toeplitz import sym_toeplitz_derivative_quadratic_form as quad
@@ -326,6 +383,9 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "block":
         make_block_step()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "learn_kernel":
+        make_learn_kernel()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "quadform":
         make_quadform()
         sys.exit(0)
@@ -337,3 +397,4 @@ if __name__ == "__main__":
     make_cfg1()
     make_quadform()
     make_block_step()
+    make_learn_kernel()

@@ -63,9 +63,13 @@ def test_medium_sizes_properties(dims, B):
         RRTv = plan.matvec(L.MV_R, RTv)
         vin = v.double().cpu().numpy()
         assert relerr(Kv.cpu().numpy(), dense_apply(col, dims, vin, lambda d: d)) < tol
-        # the preconditioner amplifies the smallest eigenvalues: compare on the scale the fp32 spectrum can resolve
-        ptol = tol if dname == "f64" else 3e-3
-        assert relerr(Pv.cpu().numpy(), dense_apply(col, dims, vin, lambda d: 1.0 / d)) < ptol
+        # fp32 preconditioner against the fp64 truth: explicit first-order bound 1e-5 + kappa(D) 2^-24 / 2 (kappa = max D / min D of
+        # the clamped spectrum; the eigenvalues are only known to fp32 relative to max |D|).  Measured on a B200: 7.7e-6 .. 6.5e-5
+        # over these cases with the bound at 3e-5 .. 1.5e-3; config 2 at full size: 3.4e-5 (bound 5.7e-4).
+        Dsp = plan.spectrum(L.SPEC_D)
+        ptol = tol if dname == "f64" else 1e-5 + 0.5 * float(Dsp.max() / Dsp.min()) * 2.0 ** -24
+        perr = relerr(Pv.cpu().numpy(), dense_apply(col, dims, vin, lambda d: 1.0 / d))
+        assert perr < ptol, (perr, ptol)
         vKv = (v.double() * Kv.double()).sum(1)
         assert float(((RTv.double() ** 2).sum(1) - vKv).abs().max() / vKv.abs().max()) < 10 * tol
         assert relerr(RRTv.cpu().numpy(), Kv.cpu().numpy()) < 10 * tol

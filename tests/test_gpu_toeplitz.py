@@ -49,15 +49,12 @@ def test_matvecs_vs_reference_golden(path):
     if dname == "f64":
         assert relerr(got, g["Cinv_v"]) < tol
     else:
-        # The fp32 reference computes D by an fp32 FFT, so its smallest eigenvalues (the ones that dominate
-        # C^-1) carry ~1e-7*|D|max of noise; ours are computed in fp64 and rounded.  Judge both against the
-        # fp64 reference: we must be at least as close to it as the fp32 reference is.
-        g64 = np.load(path.replace("_f32", "_f64"), allow_pickle=True)
-        v64 = g64["v"]
-        if np.array_equal(v64.astype(np.float32), g["v"]):
-            truth = g64["Cinv_v"]
-            assert relerr(got, truth) <= max(2.0 * relerr(g["Cinv_v"], truth), tol)
-        assert relerr(got, g["Cinv_v"]) < 3e-3
+        # fp32 preconditioner: applying diag(1/D) with eigenvalues that are only known to fp32 relative to max|D| has the
+        # first-order error kappa(D) * 2^-24 (kappa = max D / min D of the clamped spectrum) -- for the reference, whose D comes
+        # from an fp32 FFT, and for this library alike.  Explicit bound, no escape hatch:  1e-5 + kappa * 2^-24
+        # (measured on a B200: <= 4.4e-5 over the golden cases, where the bound is 1.4e-4 .. 3.8e-4 for the ill-conditioned ones).
+        kappa = float(D.max() / D.min())
+        assert relerr(got, g["Cinv_v"]) <= 1e-5 + kappa * 2.0 ** -24, (relerr(got, g["Cinv_v"]), kappa)
 
 
 @pytest.mark.parametrize("path", FILES, ids=lambda p: os.path.basename(p)[9:-4])
