@@ -11,8 +11,8 @@ metric  : Toeplitz matvec GB/s = algorithmic bytes of the step's 41 structured m
           `pcg_solve_s` (the other half of BASELINE.json's metric) is reported beside it.
 value   : inputs resident in HBM (plan.pcg on device tensors).
 e2e     : the same step through the C-ABI host entry point (hipgp_pcg_host_pipelined): pinned host b -> H2D -> solve
-          -> D2H x, every step; the right-hand sides travel in groups of 16 so that the copies of neighbouring groups
-          hide behind the solve of the current one.
+          -> D2H x, every step; the right-hand sides travel as a small first group, the bulk, and a small last
+          group, so that all copies but the first upload and the last download hide behind a solve.
 roofline: per-kernel-class CUDA-event timing inside this script (a second pass of the same steps with the
           library's event hooks on); achieved = matvec algorithmic bytes / (sum of the three pass kernels'
           average durations); the dominant kernel and its share of the matvec are named.
@@ -41,7 +41,7 @@ GRID = (1000, 1000)
 ELL, SIG2, JITTER = 0.01, 1.0, 1e-3
 MAXITER, TOL = 20, 1e-8
 B_PER_GPU = 64
-E2E_GROUP = 16
+E2E_GROUP = 8
 CPU_SAMPLE_B = 16
 N_MATVEC = 2 * MAXITER + 1
 METRIC = "toeplitz_matvec_GBps_in_pcg_1e6grid"
@@ -522,7 +522,7 @@ def run_gpu(args):
             "embedding": list(plan.embedding()[0]),
             "e2e": {"value": e2e_val, "unit": "GB/s", "h2d_bytes_per_step": int(b_host.numel() * 4) * world,
                     "d2h_bytes_per_step": int(x_host.numel() * 4) * world, "ms_per_step": ms_e2e / args.steps,
-                    "how": "hipgp_pcg_host_pipelined: groups of %d right-hand sides, H2D / D2H of neighbouring groups on two copy streams behind the solve" % E2E_GROUP,
+                    "how": "hipgp_pcg_host_pipelined: groups of %d / %d / %d right-hand sides, H2D / D2H of neighbouring groups on two copy streams behind the solves" % (E2E_GROUP, B_PER_GPU - 2 * E2E_GROUP, E2E_GROUP),
                     "matches_device_path_bitwise": e2e_matches, "frac_of_value": e2e_val / value if value else None},
             "gpu_launches": int(launches),
             "clocks": clocks,

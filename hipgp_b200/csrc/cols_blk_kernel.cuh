@@ -12,12 +12,18 @@
 //   * spectrum staging is block-local too (every group copies and waits for its own BS positions);
 //   * the next tile's input rows are prefetched behind the LAST inverse stage (the side buffer holds spectrum until every
 //     group has left its block-local sections);
+//   * TMA: when the pass reads a plain [batch][row][bin] workspace, the tile's input rows arrive as a few 3-D tensor boxes
+//     (cp.async.bulk.tensor, zero fill past the last row = the zero padding of the transform, so the first stage loads
+//     without predicates) and the real spectrum tile as ONE box whose middle extent is one larger than the tensor's -- the
+//     out-of-bounds row is exactly the bank-conflict padding of the staged layout; one thread issues, an mbarrier completes.
+//     (ncu on the cp.async version: the per-thread LDGSTS address registers sat on the long scoreboard, 9 % of all samples.)
 //   * per-stage twiddle tables live in shared memory when they fit (fp32): with 209 KB of the SM carved out for shared memory
 //     the L1 keeps almost nothing (ncu: 12 % hit rate), so every table load of cols_fast_kernel is an L2 round trip at the
 //     head of a section.
 // Same math, same digit-reversed layout, same modes as cols_fast_kernel.
 #pragma once
 #include "fast_kernels.cuh"
+#include "tma_maps.cuh"
 
 namespace hipgp {
 
@@ -58,7 +64,7 @@ struct ColsBlkCfg {
 };
 
 template <class T, int NL, int NT, int MINB, int R0, int R1, int R2>
-__global__ void __launch_bounds__(NT, MINB) cols_blk_kernel(ColsParams<T> P) {
+__global__ void __launch_bounds__(NT, MINB) cols_blk_kernel(const HIPGP_GRID_CONSTANT ColsParams<T> P, const HIPGP_GRID_CONSTANT ColsTmaMaps maps) {
     using Cfg = ColsBlkCfg<T, NL, NT, MINB, R0, R1, R2>;
     using G = typename Cfg::G;
     constexpr int Ln = G::Ln, RLAST = R2, LPT = LaneInfo<T>::LPT, TBL = NL * LPT, S0 = Ln / R0;
@@ -79,6 +85,11 @@ __global__ void __launch_bounds__(NT, MINB) cols_blk_kernel(ColsParams<T> P) {
     // per-stage twiddle tables: shared-memory copies (persistent kernel: filled once per CTA)
     const cplx<T>* tw0 = P.f.twst + P.f.twoff[0];
     const cplx<T>* tw1 = P.f.twst + P.f.twoff[1];
+    __shared__ unsigned long long s_bar[2];                       // [0] input rows, [1] spectrum tile (TMA completion); 8-byte aligned by type
+    const bool tma_in = P.tma_in != 0, tma_spec = P.tma_spec != 0;
+    unsigned ph_in = 0, ph_spec = 0;
+    if ((tma_in || tma_spec) && tid == 0) { tma_bar_init(&s_bar[0]); tma_bar_init(&s_bar[1]); tma_fence_before_issue(); }
+    if (tma_in || tma_spec) __syncthreads();
     if (TWS) {
         cplx<T>* t0 = reinterpret_cast<cplx<T>*>(side + Cfg::side_bytes);
         cplx<T>* t1 = t0 + (R0 - 1) * S0;
@@ -93,12 +104,14 @@ __global__ void __launch_bounds__(NT, MINB) cols_blk_kernel(ColsParams<T> P) {
     const size_t spitch = P.spec_pitch ? (size_t)P.spec_pitch : (size_t)P.pitch;
     const long ntiles = (long)P.nx * P.ny * P.nz;
     // (32-bit tile arithmetic: the launcher guarantees ntiles < 2^31; 64-bit divisions cost ~100 instructions per thread and tile)
+    unsigned tile_bz = 0;                                          // batch index of the tile tile_origin() was last asked about
     auto tile_origin = [&](long t, long& c0, size_t& ioff, size_t& ooff) {
         const unsigned tt = (unsigned)t, nx = (unsigned)P.nx, ny = (unsigned)P.ny, nz = (unsigned)P.nz;
         unsigned bx, by, bz;
         if (P.batch_fastest) { bz = tt % nz; const unsigned r = tt / nz; bx = r % nx; by = r / nx; }
         else { bx = tt % nx; const unsigned r = tt / nx; by = r % ny; bz = r / ny; }
         c0 = (long)bx * TBL;
+        tile_bz = bz;
         ioff = (size_t)by * P.in_ostride + (size_t)bz * P.in_bstride + c0;
         ooff = (size_t)by * P.out_ostride + (size_t)bz * P.out_bstride + c0;
     };
@@ -126,8 +139,25 @@ __global__ void __launch_bounds__(NT, MINB) cols_blk_kernel(ColsParams<T> P) {
         cp_async_commit();
     };
 
+    // TMA version of the same: boxes of tma_in_rows rows x TBL bins of batch entry bz, dense in the side buffer (row i at
+    // lane i * NL); rows >= n_in are outside the tensor and arrive as zeros.  Called by ONE thread.
+    auto issue_input = [&](long t) {
+        long c0; size_t ioff, ooff;
+        tile_origin(t, c0, ioff, ooff);
+        const unsigned box_bytes = (unsigned)P.tma_in_rows * NL * 16u;
+        tma_fence_before_issue();
+        tma_bar_expect(&s_bar[0], box_bytes * (unsigned)P.tma_in_nbox);
+        for (int k = 0; k < P.tma_in_nbox; ++k)
+            tma_load_box3(side + (size_t)k * box_bytes, &maps.in, (int)(2 * c0), k * P.tma_in_rows, (int)tile_bz, &s_bar[0]);
+    };
+    auto stage_next = [&](long tn) {
+        if (tn >= ntiles) return;
+        if (tma_in) { if (tid == 0) issue_input(tn); }
+        else if (stage_in) prefetch_input(tn);
+    };
+
     long t = blockIdx.x;
-    if (stage_in && t < ntiles) prefetch_input(t);
+    stage_next(t);
     for (; t < ntiles; t += gridDim.x) {
         long c0; size_t ioff, ooff;
         tile_origin(t, c0, ioff, ooff);
@@ -135,7 +165,8 @@ __global__ void __launch_bounds__(NT, MINB) cols_blk_kernel(ColsParams<T> P) {
         const cplx<T>* in = P.in + ioff;
         cplx<T>* out = P.out + ooff;
         // the previous tile's last stage has to be done with the tile buffer, and this tile's input must have landed
-        cp_async_wait_all();
+        if (tma_in) { tma_bar_wait(&s_bar[0], ph_in, 8, NT); ph_in ^= 1u; }
+        else cp_async_wait_all();
         __syncthreads();
 
         if (mode != CM_INV) {
@@ -147,7 +178,12 @@ __global__ void __launch_bounds__(NT, MINB) cols_blk_kernel(ColsParams<T> P) {
                 cplx<T> w[R0];
                 blk_twiddles<R0, S0, TWS>(w, tw0, j);
                 Lane<T> v[R0];
-                if (stage_in) {
+                if (tma_in) {        // rows past n_in were zero-filled by the TMA unit; lanes past the last line carry padding bins
+                    const Lane<T>* sp = reinterpret_cast<const Lane<T>*>(side) + (j * NL + lane);
+#pragma unroll
+                    for (int r = 0; r < R0 / 2; ++r) v[r] = sp[r * S0 * NL];
+                    lbfly_zero_hi<R0, T>(v);
+                } else if (stage_in) {
                     const Lane<T>* sp = reinterpret_cast<const Lane<T>*>(side) + (j * NL + lane);
                     if (zero_hi) {
 #pragma unroll
@@ -178,12 +214,20 @@ __global__ void __launch_bounds__(NT, MINB) cols_blk_kernel(ColsParams<T> P) {
             }
             __syncthreads();
             // passes that stage no spectrum leave the side buffer idle from here on: the next tile's input rows start right away
-            if (!(mode == CM_FUSED && spec_smem) && stage_in && t + gridDim.x < ntiles) prefetch_input(t + gridDim.x);
+            if (!(mode == CM_FUSED && spec_smem)) stage_next(t + gridDim.x);
         }
 
         // ======== block-local sections: group `blk` owns positions [blk BS, (blk + 1) BS) of every lane of the tile ========
         const int pb = blk * BS;
-        if (mode == CM_FUSED && spec_smem) {
+        if (mode == CM_FUSED && spec_smem && tma_spec) {
+            // the whole real spectrum tile as ONE padded box (the out-of-bounds 17th row of every group of 16 positions is the
+            // bank-conflict padding of the staged layout) -> side buffer (free now), behind the second forward stage
+            if (tid == 0) {
+                tma_fence_before_issue();
+                tma_bar_expect(&s_bar[1], (unsigned)Cfg::side_bytes);
+                tma_load_box3(side, &maps.spec, (int)c0, 0, 0, &s_bar[1]);
+            }
+        } else if (mode == CM_FUSED && spec_smem) {
             // this block's rows of the real spectrum tile -> side buffer (free now), behind the second forward stage
             const unsigned char* sp = reinterpret_cast<const unsigned char*>(P.spec) + (size_t)c0 * sizeof(T);
             constexpr int ROWB = NL * SPEC_LANE;
@@ -220,7 +264,10 @@ __global__ void __launch_bounds__(NT, MINB) cols_blk_kernel(ColsParams<T> P) {
 #pragma unroll
                 for (int r = 0; r < R1; ++r) base[k][r * LEG1] = v[k][r];
             }
-            if (mode == CM_FUSED && spec_smem) cp_async_wait_all();
+            if (mode == CM_FUSED && spec_smem) {
+                if (tma_spec) { tma_bar_wait(&s_bar[1], ph_spec, 9, NT); ph_spec ^= 1u; }
+                else cp_async_wait_all();
+            }
             blk_sync<GS>(blk);
         }
         // ---- last forward stage + spectrum + first inverse stage: RLAST neighbouring positions, in registers ----
@@ -295,7 +342,7 @@ __global__ void __launch_bounds__(NT, MINB) cols_blk_kernel(ColsParams<T> P) {
         }
         __syncthreads();
         // ---- every group is done with its spectrum rows: next tile's input rows travel behind the last inverse stage ----
-        if (mode == CM_FUSED && spec_smem && stage_in && t + gridDim.x < ntiles) prefetch_input(t + gridDim.x);
+        if (mode == CM_FUSED && spec_smem) stage_next(t + gridDim.x);
         // ---- last inverse stage (couples the blocks) straight to global memory (crop = skipped stores) ----
         {
 #pragma unroll 1

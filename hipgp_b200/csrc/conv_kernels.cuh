@@ -328,6 +328,8 @@ struct ColsParams {
     int spec_stage;               // specialised kernels: real spectrum tile staged through shared memory
     int in_stage;                 // specialised kernels: input rows prefetched through the shared-memory side buffer
     int nx, ny, nz;               // specialised (persistent) kernels: tile grid = line tiles x outer x batch
+    int tma_in, tma_in_rows, tma_in_nbox;   // block-local column kernel: input rows arrive as tma_in_nbox TMA boxes of tma_in_rows rows
+    int tma_spec;                 // ... and the real spectrum tile as ONE padded TMA box
     int batch_fastest;            // ... walked batch-fastest (big spectra: a spectrum tile is reused by the CTAs running side by side)
     const int* done_flag;         // optional PCG early-exit flag
     // slab-decomposed grids: rows of the output (FWD) / input (INV) are scattered / gathered in blocks of `split_len`

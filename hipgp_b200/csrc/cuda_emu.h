@@ -198,7 +198,7 @@ static inline const char* cudaGetErrorString(cudaError_t) { return "emu"; }
 #include <algorithm>
 #include <vector>
 
-#define HIPGP_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
+#define HIPGP_DYN_SMEM(name) extern __shared__ __align__(128) unsigned char name[]   /* 128: TMA tensor boxes land in it */
 #define HIPGP_LAUNCH(kernel, grid, block, smem, stream, ...) \
     kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
 #define HIPGP_SET_MAX_SMEM(kernel, bytes) \

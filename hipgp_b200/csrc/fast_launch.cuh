@@ -166,12 +166,36 @@ template <class T, int LEN, int R0, int R1, int R2> struct ColsBlkLaunch<T, LEN,
                 const size_t spec_bytes = (size_t)G::Ln * (size_t)P.inner * (P.spec_kind == SPEC_REAL ? sizeof(T) : 2 * sizeof(T));
                 P.batch_fastest = (P.mode == CM_FUSED && B > 1 && spec_bytes > ((size_t)48 << 20) && (size_t)TBL * sizeof(cplx<T>) >= 128) ? 1 : 0;
             }
+            // TMA staging (tiled tensor maps): input rows when the pass reads a plain [batch][row][bin] array whose rows fill at
+            // most half the transform (the tensor's row extent is n_in, so the zero padding is the unit's out-of-bounds fill);
+            // the real spectrum tile as one padded box.  Anything else keeps the cp.async staging.
+            ColsTmaMaps maps{};
+            P.tma_in = P.tma_spec = 0;
+            static const char* env_nt = getenv("HIPGP_NO_TMA_COLS");
+            if (!env_nt) {
+                constexpr int HALF = C::Ln / 2;
+                const int nbox = (HALF + 255) / 256;
+                if (P.in_stage && P.n_in <= HALF && P.in_ostride == 0 && n_outer == 1 && HALF % nbox == 0 && is_pow2(R0)) {
+                    const unsigned long long dim[3] = {(unsigned long long)(2 * P.pitch), (unsigned long long)P.n_in, (unsigned long long)B};
+                    const unsigned long long bstr = (unsigned long long)(P.in_bstride ? P.in_bstride : (long)P.n_in * P.pitch);
+                    const unsigned long long str[2] = {(unsigned long long)P.pitch * sizeof(cplx<T>), bstr * sizeof(cplx<T>)};
+                    const unsigned box[3] = {(unsigned)(2 * TBL), (unsigned)(HALF / nbox), 1u};
+                    if (encode_map3(&maps.in, P.in, (int)sizeof(T), dim, str, box)) { P.tma_in = 1; P.tma_in_rows = HALF / nbox; P.tma_in_nbox = nbox; }
+                }
+                if (P.spec_stage && C::Ln / R2 <= 256 && (TBL * sizeof(T)) % 16 == 0) {
+                    const long sp = P.spec_pitch ? P.spec_pitch : P.pitch;
+                    const unsigned long long dim[3] = {(unsigned long long)sp, (unsigned long long)R2, (unsigned long long)(C::Ln / R2)};
+                    const unsigned long long str[2] = {(unsigned long long)sp * sizeof(T), (unsigned long long)sp * R2 * sizeof(T)};
+                    const unsigned box[3] = {(unsigned)TBL, (unsigned)(R2 + 1), (unsigned)(C::Ln / R2)};
+                    if (encode_map3(&maps.spec, P.spec, (int)sizeof(T), dim, str, box)) P.tma_spec = 1;
+                }
+            }
             auto k = cols_blk_kernel<T, C::NLC, C::NTC, C::MINBC, R0, R1, R2>;
             if (smem > 40 * 1024) HIPGP_SET_MAX_SMEM(k, smem);
             const long ntiles = (long)P.nx * P.ny * P.nz;
             const long grid = std::min<long>(ntiles, resident_ctas(k, C::NTC, smem));
             PROF_BEGIN(pl, 1, st);
-            HIPGP_LAUNCH(k, dim3((unsigned)grid), dim3(C::NTC), smem, st, P);
+            HIPGP_LAUNCH(k, dim3((unsigned)grid), dim3(C::NTC), smem, st, P, maps);
             PROF_END(pl, st);
             launch_check("column pass (block-local)", C::Ln, C::NLC, C::NTC, smem, grid);
             pl->launches++;

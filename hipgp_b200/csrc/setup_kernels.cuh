@@ -39,6 +39,81 @@ __global__ void __launch_bounds__(256) dct1_axis_kernel(const double* __restrict
     out[o + (size_t)k * inner + i] = acc * scale;
 }
 
+// The same DCT-I as a TILED fp64 contraction (round 2: the dense transform above is the one genuine matrix product of the
+// path -- (m x m cosine matrix) x (m x inner) per outer index -- and at config 2 the one-output-per-thread kernel above spent
+// 1.13 ms per launch, 8 launches per spectrum set-up).  64 x 64 output tile per CTA, 16-deep k tiles in shared memory,
+// 16 x 16 threads with 4 x 4 fp64 accumulators each; the cosine operand is generated from the length-N table (index
+// (j k) mod N) while its tile is staged, so no m x m matrix is ever stored.
+//   LAST == false: out[o][k][i] = scale * sum_j w_j cos(pi j k / (m-1)) in[o][j][i]      (tile rows = k, tile columns = i)
+//   LAST == true : inner == 1:  out[o][k]   = scale * sum_j in[o][j] w_j cos(pi j k / (m-1))  (tile rows = o, tile columns = k)
+template <bool LAST>
+__global__ void __launch_bounds__(256) dct1_tile_kernel(const double* __restrict__ in, double* __restrict__ out,
+                                                        const double* __restrict__ costab, int m, long inner, long outer, double scale) {
+    constexpr int TM = 64, TN = 64, TK = 16;
+    __shared__ double As[TK][TM + 2];      // As[jj][row]
+    __shared__ double Bs[TK][TN + 2];      // Bs[jj][col]
+    const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
+    const int N = m > 1 ? 2 * (m - 1) : 1;
+    const long r0 = (long)blockIdx.y * TM, c0 = (long)blockIdx.x * TN;
+    const long o = LAST ? 0 : (long)blockIdx.z;
+    const long nrows = LAST ? outer : m, ncols = LAST ? m : inner;
+    const double* inb = in + (LAST ? 0 : (size_t)o * m * inner);
+    double acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+    for (int j0 = 0; j0 < m; j0 += TK) {
+        // stage the two operand tiles
+        for (int e = threadIdx.x; e < TK * TM; e += 256) {
+            if (LAST) {          // A(row = o, j) = in[o][j]: consecutive threads walk j (contiguous)
+                const int jj = e % TK, rr = e / TK;
+                const long row = r0 + rr; const int j = j0 + jj;
+                As[jj][rr] = (row < nrows && j < m) ? inb[(size_t)row * m + j] : 0.0;
+            } else {             // A(row = k, j) = w_j cos(pi j k / (m-1))
+                const int rr = e % TM, jj = e / TM;
+                const long k = r0 + rr; const int j = j0 + jj;
+                double v = 0.0;
+                if (k < nrows && j < m) { const double w = (j == 0 || j == m - 1) ? 1.0 : 2.0; v = m > 1 ? w * costab[((unsigned)j * (unsigned)k) % (unsigned)N] : 1.0; }
+                As[jj][rr] = v;
+            }
+        }
+        for (int e = threadIdx.x; e < TK * TN; e += 256) {
+            const int cc = e % TN, jj = e / TN;
+            const long col = c0 + cc; const int j = j0 + jj;
+            double v = 0.0;
+            if (col < ncols && j < m) {
+                if (LAST) { const double w = (j == 0 || j == m - 1) ? 1.0 : 2.0; v = m > 1 ? w * costab[((unsigned)j * (unsigned)col) % (unsigned)N] : 1.0; }
+                else v = inb[(size_t)j * inner + col];
+            }
+            Bs[jj][cc] = v;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int jj = 0; jj < TK; ++jj) {
+            double a[4], b[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) { a[t] = As[jj][ty * 4 + t]; b[t] = Bs[jj][tx * 4 + t]; }
+#pragma unroll
+            for (int x = 0; x < 4; ++x)
+#pragma unroll
+                for (int y = 0; y < 4; ++y) acc[x][y] += a[x] * b[y];
+        }
+        __syncthreads();
+    }
+    double* outb = out + (LAST ? 0 : (size_t)o * m * inner);
+#pragma unroll
+    for (int x = 0; x < 4; ++x) {
+        const long row = r0 + ty * 4 + x;
+        if (row >= nrows) continue;
+#pragma unroll
+        for (int y = 0; y < 4; ++y) {
+            const long col = c0 + tx * 4 + y;
+            if (col < ncols) outb[(size_t)row * (LAST ? m : inner) + col] = acc[x][y] * scale;
+        }
+    }
+}
+
 template <class T>
 __global__ void to_double_kernel(const T* __restrict__ in, double* __restrict__ out, long n) {
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;

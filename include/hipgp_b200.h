@@ -83,8 +83,9 @@ int hipgp_pcg_begin(hipgp_plan* plan, const void* b_dev, void* x_dev, int64_t B,
 int hipgp_pcg_step(hipgp_plan* plan, int niter, int* done_out, int* iters_out, double* max_resid_out, void* stream);
 int hipgp_pcg_host(hipgp_plan* plan, const void* b_host, void* x_host, int64_t B, int maxiter, double tol, int precond,
                    int* iters_out, int* callbacks_out, double* resid_out, void* stream);
-/* host-buffer solve with the copies hidden behind the solves: right-hand sides go in groups of `group` (<= 0: all at once),
- * H2D of group g+1 and D2H of group g-1 overlap the solve of group g (two plan-owned copy streams).  Each group is an
+/* host-buffer solve with the copies hidden behind the solves: a first and a last group of `group` right-hand sides and one
+ * big group in between (uniform groups of `group` when B < 4 group; <= 0: all at once); H2D of group g+1 and D2H of group
+ * g-1 overlap the solve of group g (two plan-owned copy streams).  Each group is an
  * independent batched solve (the stopping rule of cg.py:70 spans one group); iters_out = max over groups.  Pinned buffers. */
 int hipgp_pcg_host_pipelined(hipgp_plan* plan, const void* b_host, void* x_host, int64_t B, int maxiter, double tol,
                              int precond, int64_t group, int* iters_out, void* stream);

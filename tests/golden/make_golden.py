@@ -17,6 +17,8 @@ own implementation.  Files:
   learn_kernel_<dtype>.npz     learn_kernel=True / learn_noise=True: MeanFieldToeplitzGP.elbo_and_grad followed by (-elbo).backward() as
                                svigp_fit does (svi_gp.py:317-329): the autograd gradients of log_sig2, log_ell, log_noise2 (through
                                kernels.py, ToeplitzTensor.__init__, InvMatmul, _matmul_by_RT), and the column gradient of R^T alone
+  bidiag_<dtype>.npz           misc/bidiag.py:5-148 (Golub-Kahan bidiagonalisation solve c = K^{-1/2} b) over ToeplitzMatmul's R^T / R
+                               matvecs, closures as in run_pcg_vs_cholesky.py:105-108; 1-D and 2-D grids
   notebook_counts.npz          preconditioner-analysis.ipynb saved outputs (raw lines 101-103,142-144,183-185,224-226)
 """
 import os
@@ -299,6 +301,30 @@ def make_learn_kernel():
         np.savez_compressed(os.path.join(HERE, "learn_kernel_%s.npz" % dname), **out)
 
 
+def make_bidiag():
+    """bidiag_solve (bidiag.py:129-148) with A = R^T, A* = R of ToeplitzMatmul (toeplitz_expanded.py:163-187)."""
+    from ziggy.misc import bidiag as zb
+    for dname, dtype in DT.items():
+        out = {}
+        for tag, grids, kname, sig2, ell, nobs, max_iter in (("g1d", [(0., 5., 60)], "matern52", 0.1, 0.4, 3, 25),
+                                                             ("g2d", [(0., 1., 9), (0., 2., 7)], "matern32", 1.0, 0.5, 2, 20)):
+            torch.manual_seed(41)
+            xgrids = [torch.linspace(lo, hi, m, dtype=dtype) for lo, hi, m in grids]
+            kern = get_kernel(kname, dtype)
+            kfun = lambda x, y: kern.forward(x, y, params=(sig2, ell))
+            M = int(np.prod([g[2] for g in grids])); Mp = int(np.prod([2 * g[2] - 2 for g in grids]))
+            b = torch.randn(M, nobs, dtype=dtype)
+            K_matmul = toeplitz_expanded.ToeplitzMatmul(xgrids, kfun, batch_shape=b.shape[-1:])
+            A_matmul = lambda x: K_matmul(x.t(), multiply_type="RTv").t()
+            Astar_matmul = lambda x: K_matmul(x.t(), multiply_type="Rv").t()
+            U, V, al, be = zb.golub_kahan_bidiag(A_matmul, Astar_matmul, (Mp, M), max_iter, dtype, b.device, b, tol=1e-5, run_all=True)
+            c = zb.bidiag_solve(A_matmul, Astar_matmul, (Mp, M), max_iter, dtype, b.device, b, tol=1e-5)
+            out[tag + "_grids"] = np.array(grids); out[tag + "_params"] = np.array([sig2, ell, max_iter]); out[tag + "_b"] = b.numpy()
+            out[tag + "_c"] = c.numpy(); out[tag + "_alphas"] = al.numpy(); out[tag + "_betas"] = be.numpy(); out[tag + "_V"] = V.numpy()
+            print("bidiag", dname, tag, "J", al.shape[0], float(c.norm()))
+        np.savez_compressed(os.path.join(HERE, "bidiag_%s.npz" % dname), **out)
+
+
 def make_quadform():
     """sym_toeplitz_derivative_quadratic_form on seeded vectors, and autograd through the reference's InvMatmul."""
     from ziggy.misc.gpt_toeplitz import sym_toeplitz_derivative_quadratic_form as quad
@@ -383,6 +409,9 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "block":
         make_block_step()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "bidiag":
+        make_bidiag()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "learn_kernel":
         make_learn_kernel()
         sys.exit(0)
@@ -398,3 +427,4 @@ if __name__ == "__main__":
     make_quadform()
     make_block_step()
     make_learn_kernel()
+    make_bidiag()

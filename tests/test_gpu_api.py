@@ -222,7 +222,8 @@ def test_batched_pcg_nan_row_is_isolated():
 def test_matvecs_are_differentiable_linear_maps(golden_dir):
     """The reference's matvecs are torch ops, hence differentiable in their vector argument (toeplitz_tensor.py:70-125);
     the drop-in matches: K and C^-1 are their own adjoints, R^T and R each other's; compute_kn with a differentiable
-    K_nm back-propagates through R^T and the PCG solve; a graph that needs the COLUMN gradient of a matvec fails loudly."""
+    K_nm back-propagates through R^T and the PCG solve; the COLUMN gradient exists for R^T (hipgp_rt_column_grad, tested in
+    tests/test_gpu_learn_kernel.py) and the solve (InvMatmul.backward); the other matvecs fail loudly instead of dropping it."""
     from hipgp_b200.toeplitz_tensor import ToeplitzTensor
     g = np.load(os.path.join(golden_dir, "toeplitz_2d_25x25_matern52_f64.npz"), allow_pickle=True)
     dtype = torch.float64
@@ -246,8 +247,10 @@ def test_matvecs_are_differentiable_linear_maps(golden_dir):
     (kn * w[:2]).sum().backward()
     want = tt._solve(tt._matmul_by_R(w[:2]), maxiter=80, tol=1e-13)
     assert relerr(Knm.grad, want.cpu().numpy()) < 1e-8
-    # the column gradient of a matvec is not built: loud failure, not a silently incomplete gradient
+    # column gradients: R^T has one; K (not differentiated by any caller of the reference) fails loudly, not silently
     tt.column.requires_grad_(True)
-    out = tt._matmul_by_RT(v)
+    tt._matmul_by_RT(v).sum().backward()
+    assert tt.column.grad is not None and bool(torch.isfinite(tt.column.grad).all())
+    out = tt._matmul_by_K(v)
     with pytest.raises(NotImplementedError, match="Toeplitz column"):
         out.sum().backward()

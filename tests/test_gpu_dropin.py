@@ -6,6 +6,7 @@ git-ignored, ships to the GPU box like the built .so):
 
   * `ziggy.hipgp.MeanFieldToeplitzGP` / `BlockToeplitzGP` (hipgp.py:449-690): `elbo_and_grad` + `predict` against the golden
     vectors generated from the reference running on its own torch implementation (tests/golden/make_golden.py);
+  * `ziggy.misc.bidiag` (bidiag.py:5-148, unchanged) over the drop-in ToeplitzMatmul's R^T / R matvecs;
   * the body of `experiments-hip-gp/run_solve_kn_experiment.py:27-73` (config 1: seeded vectors, CG then PCG through
     `toeplitz_expanded.gram_solve`, callback counts 28/196/1978 and 6/19/89 in fp32).
 
@@ -127,6 +128,36 @@ print("DROPIN_OK")
 '''
 
 
+BIDIAG = PRELUDE + r'''
+# SURVEY.md 8f rank 4: the Golub-Kahan bidiagonalisation route to K^{-1/2} b (ziggy/misc/bidiag.py:5-148) is generic host
+# code over two matvec closures; it runs UNCHANGED (imported from the staged reference) on the structured CUDA matvecs
+# R^T / R of the drop-in ToeplitzMatmul, closures as in run_pcg_vs_cholesky.py:105-108.
+from ziggy.misc import bidiag as zb
+assert os.path.realpath(zb.__file__).startswith(os.path.realpath(%(ref)r))
+for dname in ("f64", "f32"):
+    g = np.load(os.path.join(GOLD, "bidiag_%%s.npz" %% dname)); dtype = DT[dname]
+    for tag, kern in (("g1d", zk.Matern(nu=2.5, dtype=dtype)), ("g2d", zk.Matern(nu=1.5, dtype=dtype))):
+        sig2, ell, max_iter = [float(t) for t in g[tag + "_params"]]
+        xgrids = [torch.linspace(lo, hi, int(m), dtype=dtype, device="cuda") for lo, hi, m in g[tag + "_grids"]]
+        kfun = lambda x, y: kern.forward(x, y, params=(sig2, ell))
+        b = torch.from_numpy(g[tag + "_b"]).cuda()
+        M = b.shape[0]; Mp = int(np.prod([2 * len(x) - 2 for x in xgrids]))
+        K_matmul = zte.ToeplitzMatmul(xgrids, kfun, batch_shape=b.shape[-1:])
+        A_matmul = lambda x: K_matmul(x.t(), multiply_type="RTv").t()
+        Astar_matmul = lambda x: K_matmul(x.t(), multiply_type="Rv").t()
+        U, V, al, be = zb.golub_kahan_bidiag(A_matmul, Astar_matmul, (Mp, M), int(max_iter), dtype, b.device, b, tol=1e-5, run_all=True)
+        c = zb.bidiag_solve(A_matmul, Astar_matmul, (Mp, M), int(max_iter), dtype, b.device, b, tol=1e-5)
+        assert tuple(c.shape) == tuple(g[tag + "_c"].shape) and al.shape[0] == g[tag + "_alphas"].shape[0]
+        if dname == "f64":
+            assert relerr(al, g[tag + "_alphas"]) < 1e-8 and relerr(be, g[tag + "_betas"]) < 1e-8, (tag, relerr(al, g[tag + "_alphas"]))
+            assert relerr(V, g[tag + "_V"]) < 1e-6 and relerr(c, g[tag + "_c"]) < 1e-6, (tag, relerr(c, g[tag + "_c"]))
+        else:           # fp32: the Krylov basis loses digits with every re-orthogonalisation; the leading coefficients pin the matvecs
+            assert relerr(al[:5], g[tag + "_alphas"][:5]) < 1e-4 and relerr(be[:5], g[tag + "_betas"][:5]) < 1e-3
+            assert bool(torch.isfinite(c).all())
+print("DROPIN_OK")
+'''
+
+
 def _run(script):
     if not os.path.isdir(os.path.join(REF, "ziggy")):
         pytest.skip("oracle/_ref not staged (python oracle/make_ref.py in the build container)")
@@ -144,3 +175,7 @@ def test_reference_block_model_on_cuda_dropins():
 
 def test_reference_solve_kn_experiment_on_cuda_dropins():
     _run(SOLVE_KN)
+
+
+def test_reference_bidiag_solver_on_cuda_matvecs():
+    _run(BIDIAG)
