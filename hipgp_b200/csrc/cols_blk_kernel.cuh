@@ -49,6 +49,24 @@ __device__ __forceinline__ void blk_twiddles(cplx<T>* w, const cplx<T>* tab, int
     for (int r = 1; r < R; ++r) w[r] = SM ? tab[(r - 1) * S + j] : ldg_c(tab + (r - 1) * S + j);
 }
 
+// v[r] *= w^{j r} (or its conjugate), r = 1..R-1, with the table loads issued in chunks of CH: at radix 16 the 15 twiddles of
+// a butterfly would otherwise all be live next to its 16 lanes (94 of 128 registers) and the kernel spills -- and a spill
+// reload is an L2 round trip here, because with 225 KB of the SM carved out for shared memory there is no L1 to speak of.
+template <int R, int S, bool SM, bool CONJ, int CH, class T>
+__device__ __forceinline__ void blk_twiddle_mul(Lane<T>* v, const cplx<T>* tab, int j) {
+#pragma unroll
+    for (int r0 = 1; r0 < R; r0 += CH) {
+        cplx<T> w[CH];
+#pragma unroll
+        for (int c = 0; c < CH; ++c) if (r0 + c < R) w[c] = SM ? tab[(r0 + c - 1) * S + j] : ldg_c(tab + (r0 + c - 1) * S + j);
+#pragma unroll
+        for (int c = 0; c < CH; ++c) if (r0 + c < R) v[r0 + c] = CONJ ? lmulc(v[r0 + c], w[c]) : lmul(v[r0 + c], w[c]);
+#ifndef HIPGP_EMU
+        if (r0 + CH < R) asm volatile("" ::: "memory");       // keeps the next chunk's loads behind this chunk's arithmetic
+#endif
+    }
+}
+
 template <class T, int NL, int NT, int MINB, int R0, int R1, int R2>
 struct ColsBlkCfg {
     using G = TileGeo<T, NL, R0, R1, R2>;
@@ -70,6 +88,7 @@ __global__ void __launch_bounds__(NT, MINB) cols_blk_kernel(const HIPGP_GRID_CON
     constexpr int Ln = G::Ln, RLAST = R2, LPT = LaneInfo<T>::LPT, TBL = NL * LPT, S0 = Ln / R0;
     constexpr int BS = Cfg::BS, GS = Cfg::GS, S1 = BS / R1;
     constexpr bool TWS = Cfg::tw_smem;
+    constexpr int TWCH = R0 >= 16 ? 5 : R0;                      // twiddle loads per chunk in the first / last stage
     static_assert(Cfg::ok, "radix list / tile shape not usable with block-local middle sections");
     constexpr int LEG0 = G::leg(S0), LEG1 = G::leg(S1);
     constexpr int SPEC_LANE = 8;                                  // bytes of real spectrum per lane (2 x fp32 or 1 x fp64)
@@ -85,10 +104,9 @@ __global__ void __launch_bounds__(NT, MINB) cols_blk_kernel(const HIPGP_GRID_CON
     // per-stage twiddle tables: shared-memory copies (persistent kernel: filled once per CTA)
     const cplx<T>* tw0 = P.f.twst + P.f.twoff[0];
     const cplx<T>* tw1 = P.f.twst + P.f.twoff[1];
-    __shared__ unsigned long long s_bar[2];                       // [0] input rows, [1] spectrum tile (TMA completion); 8-byte aligned by type
+    __shared__ unsigned long long s_bar[3];                       // [0] input rows, [1] spectrum tile (TMA completion), [2] "every warp has read its spectrum rows"
     const bool tma_in = P.tma_in != 0, tma_spec = P.tma_spec != 0;
-    unsigned ph_in = 0, ph_spec = 0;
-    if ((tma_in || tma_spec) && tid == 0) { tma_bar_init(&s_bar[0]); tma_bar_init(&s_bar[1]); tma_fence_before_issue(); }
+    if ((tma_in || tma_spec) && tid == 0) { tma_bar_init(&s_bar[0]); tma_bar_init(&s_bar[1]); warps_bar_init(&s_bar[2], NT / 32); tma_fence_before_issue(); }
     if (tma_in || tma_spec) __syncthreads();
     if (TWS) {
         cplx<T>* t0 = reinterpret_cast<cplx<T>*>(side + Cfg::side_bytes);
@@ -156,16 +174,19 @@ __global__ void __launch_bounds__(NT, MINB) cols_blk_kernel(const HIPGP_GRID_CON
         else if (stage_in) prefetch_input(tn);
     };
 
-    long t = blockIdx.x;
-    stage_next(t);
-    for (; t < ntiles; t += gridDim.x) {
+    stage_next((long)blockIdx.x);
+    // (the mbarrier phases are the parity of the tile iteration: both barriers complete exactly once per tile)
+    for (unsigned iter = 0;; ++iter) {
+        const long t = (long)blockIdx.x + (long)iter * gridDim.x;
+        if (t >= ntiles) break;
+        const unsigned ph = iter & 1u;
         long c0; size_t ioff, ooff;
         tile_origin(t, c0, ioff, ooff);
         const long nvalid = P.inner - c0;
         const cplx<T>* in = P.in + ioff;
         cplx<T>* out = P.out + ooff;
         // the previous tile's last stage has to be done with the tile buffer, and this tile's input must have landed
-        if (tma_in) { tma_bar_wait(&s_bar[0], ph_in, 8, NT); ph_in ^= 1u; }
+        if (tma_in) tma_bar_wait(&s_bar[0], ph, 8, NT);
         else cp_async_wait_all();
         __syncthreads();
 
@@ -175,8 +196,6 @@ __global__ void __launch_bounds__(NT, MINB) cols_blk_kernel(const HIPGP_GRID_CON
             for (int it = tid; it < S0 * NL; it += NT) {
                 const int lane = it % NL, j = it / NL;
                 const bool ok = (long)lane * LPT < nvalid;
-                cplx<T> w[R0];
-                blk_twiddles<R0, S0, TWS>(w, tw0, j);
                 Lane<T> v[R0];
                 if (tma_in) {        // rows past n_in were zero-filled by the TMA unit; lanes past the last line carry padding bins
                     const Lane<T>* sp = reinterpret_cast<const Lane<T>*>(side) + (j * NL + lane);
@@ -206,8 +225,7 @@ __global__ void __launch_bounds__(NT, MINB) cols_blk_kernel(const HIPGP_GRID_CON
                         lbfly<R0, false, T>(v);
                     }
                 }
-#pragma unroll
-                for (int r = 1; r < R0; ++r) v[r] = lmul(v[r], w[r]);
+                blk_twiddle_mul<R0, S0, TWS, false, TWCH>(v, tw0, j);
                 Lane<T>* base = s + (G::slot(j) * NL + lane);
 #pragma unroll
                 for (int r = 0; r < R0; ++r) base[r * LEG0] = v[r];
@@ -265,7 +283,7 @@ __global__ void __launch_bounds__(NT, MINB) cols_blk_kernel(const HIPGP_GRID_CON
                 for (int r = 0; r < R1; ++r) base[k][r * LEG1] = v[k][r];
             }
             if (mode == CM_FUSED && spec_smem) {
-                if (tma_spec) { tma_bar_wait(&s_bar[1], ph_spec, 9, NT); ph_spec ^= 1u; }
+                if (tma_spec) tma_bar_wait(&s_bar[1], ph, 9, NT);
                 else cp_async_wait_all();
             }
             blk_sync<GS>(blk);
@@ -315,6 +333,14 @@ __global__ void __launch_bounds__(NT, MINB) cols_blk_kernel(const HIPGP_GRID_CON
             }
         }
         if (mode == CM_FWD) continue;
+        // the side buffer held the spectrum: once EVERY warp is through the multiply it is free, and the next tile's input rows can
+        // start travelling behind the second inverse stage already (one lane per warp arrives, thread 0 waits and issues)
+        const bool early_in = tma_in && mode == CM_FUSED && spec_smem;
+        if (early_in) {
+            warp_sync_all();                                  // every lane of this warp is done with its spectrum rows
+            if (tid == 0) { warps_bar_arrive_and_wait(&s_bar[2], ph, 10, NT / 32); stage_next(t + gridDim.x); }
+            else if ((tid & 31) == 0) warps_bar_arrive(&s_bar[2], 10, NT / 32);
+        }
         blk_sync<GS>(blk);
         // ---- second inverse stage: radix R1 inside the block ----
         {
@@ -342,30 +368,29 @@ __global__ void __launch_bounds__(NT, MINB) cols_blk_kernel(const HIPGP_GRID_CON
         }
         __syncthreads();
         // ---- every group is done with its spectrum rows: next tile's input rows travel behind the last inverse stage ----
-        if (mode == CM_FUSED && spec_smem) stage_next(t + gridDim.x);
+        if (mode == CM_FUSED && spec_smem && !early_in) stage_next(t + gridDim.x);
         // ---- last inverse stage (couples the blocks) straight to global memory (crop = skipped stores) ----
         {
 #pragma unroll 1
             for (int it = tid; it < S0 * NL; it += NT) {
                 const int lane = it % NL, j = it / NL;
                 const bool ok = (long)lane * LPT < nvalid;
-                cplx<T> w[R0];
-                blk_twiddles<R0, S0, TWS>(w, tw0, j);
                 const Lane<T>* base = s + (G::slot(j) * NL + lane);
                 Lane<T> v[R0];
 #pragma unroll
                 for (int r = 0; r < R0; ++r) v[r] = base[r * LEG0];
-#pragma unroll
-                for (int r = 1; r < R0; ++r) v[r] = lmulc(v[r], w[r]);
-                cplx<T>* gp = out + (size_t)j * pitch + lane * LPT;
+                blk_twiddle_mul<R0, S0, TWS, true, TWCH>(v, tw0, j);
                 lbfly<R0, true, T>(v);
                 if (ok) {
+                    // (one 64-bit base per thread, 32-bit element offsets for the R0 / 2 row blocks: an embedded line spans < 2^31 elements)
+                    cplx<T>* gp = out + (size_t)((unsigned)j * (unsigned)P.pitch + (unsigned)(lane * LPT));
+                    const unsigned rs = (unsigned)S0 * (unsigned)P.pitch;
                     if (out_lo) {
 #pragma unroll
-                        for (int r = 0; r < R0 / 2; ++r) if (j + r * S0 < n_out) lane_to_global(gp + r * rstep, v[r]);
+                        for (int r = 0; r < R0 / 2; ++r) if (j + r * S0 < n_out) lane_to_global(gp + (size_t)((unsigned)r * rs), v[r]);
                     } else {
 #pragma unroll
-                        for (int r = 0; r < R0; ++r) if (j + r * S0 < n_out) lane_to_global(gp + r * rstep, v[r]);
+                        for (int r = 0; r < R0; ++r) if (j + r * S0 < n_out) lane_to_global(gp + (size_t)((unsigned)r * rs), v[r]);
                     }
                 }
             }

@@ -103,6 +103,34 @@ __device__ __forceinline__ void tma_bar_wait(unsigned long long* bar, unsigned p
     emu::g_named_barrier[emu_id].sync(emu_count);
 #endif
 }
+// plain arrival-count barrier between one lane per warp and ONE waiting thread (which is itself one of the arriving lanes):
+// the other lanes arrive without waiting.  Emulation: named barrier `emu_id`, arrive / sync of `count` participants.
+__device__ __forceinline__ void warps_bar_init(unsigned long long* bar, unsigned count) {
+#ifndef HIPGP_EMU
+    mbar_init(bar, count);
+#else
+    (void)bar; (void)count;
+#endif
+}
+__device__ __forceinline__ void warps_bar_arrive(unsigned long long* bar, int emu_id, int count) {
+#ifndef HIPGP_EMU
+    (void)emu_id; (void)count;
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+#else
+    (void)bar;
+    emu::g_named_barrier[emu_id].arrive(count);
+#endif
+}
+__device__ __forceinline__ void warps_bar_arrive_and_wait(unsigned long long* bar, unsigned parity, int emu_id, int count) {
+#ifndef HIPGP_EMU
+    (void)emu_id; (void)count;
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+    mbar_wait(bar, parity);
+#else
+    (void)bar; (void)parity;
+    emu::g_named_barrier[emu_id].sync(count);
+#endif
+}
 __device__ __forceinline__ void tma_fence_before_issue() {
 #ifndef HIPGP_EMU
     fence_proxy_async();
