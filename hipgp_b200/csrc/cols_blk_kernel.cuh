@@ -185,10 +185,13 @@ __global__ void __launch_bounds__(NT, MINB) cols_blk_kernel(const HIPGP_GRID_CON
         const long nvalid = P.inner - c0;
         const cplx<T>* in = P.in + ioff;
         cplx<T>* out = P.out + ooff;
-        // the previous tile's last stage has to be done with the tile buffer, and this tile's input must have landed
-        if (tma_in) tma_bar_wait(&s_bar[0], ph, 8, NT);
-        else cp_async_wait_all();
-        __syncthreads();
+        // This tile's input must have landed.  The previous tile's last inverse stage and this tile's first forward stage touch
+        // the SAME tile-buffer slots from the SAME thread (item (lane, j) reads / writes positions j + r S0), so nothing but
+        // program order is needed between them: with TMA staging (every thread waits on the mbarrier itself) there is no CTA
+        // barrier here and the warps run from one tile's last stage straight into the next tile's first stage.
+        // (Forward-only passes end a tile in the block-local last forward stage, a different thread-to-slot mapping: barrier.)
+        if (tma_in) { tma_bar_wait(&s_bar[0], ph, 8, NT); if (mode != CM_FUSED) __syncthreads(); }
+        else { cp_async_wait_all(); __syncthreads(); }
 
         if (mode != CM_INV) {
             // ---- first forward stage (couples the blocks): operands from the side buffer or from global memory ----

@@ -146,10 +146,12 @@ template <class T, int LEN, int R0, int R1, int R2> struct ColsBlkLaunch<T, LEN,
     using Cfg = ColsBlkCfg<T, C::NLC, C::NTC, C::MINBC, R0, R1, R2>;
     static bool run(hipgp_plan* pl, ColsParams<T>& P, long n_outer, long B, cudaStream_t st) {
         // (measured, profiles/README.md r2c: a gain where the twiddle tables fit next to the tile -- fp32 --, a loss otherwise)
-        if constexpr (!Cfg::ok || !Cfg::tw_smem) { (void)pl; (void)P; (void)n_outer; (void)B; (void)st; return false; }
+        if constexpr (!Cfg::ok) { (void)pl; (void)P; (void)n_outer; (void)B; (void)st; return false; }
         else {
             static const char* env_blk = getenv("HIPGP_COLS_BLK");
             if (env_blk && env_blk[0] == '0') return false;
+            static const char* env_tws = getenv("HIPGP_BLK_NEEDS_TWS");      // A/B: restrict to lists whose twiddle tables fit in shared memory
+            if (!Cfg::tw_smem && env_tws && env_tws[0] == '1') return false;
             if ((long)((P.inner + C::NLC * C::LPT - 1) / (C::NLC * C::LPT)) * n_outer * B >= (1L << 31)) return false;
             using G = typename Cfg::G;
             constexpr int TBL = C::NLC * C::LPT;
