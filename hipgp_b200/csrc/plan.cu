@@ -338,7 +338,7 @@ static void build_spectrum(hipgp_plan* pl, bool wide, const double* col, DevBuf&
     // right-align the D active axes into the 3 slots of EmbedDims
     for (int d = 0; d < g.D; ++d) {
         const int slot = 3 - g.D + d;
-        e.m[slot] = pl->m[d]; e.N[slot] = pl->N[d]; e.L[slot] = g.L[d]; e.wide[slot] = wide ? 1 : 0;
+        e.m[slot] = pl->m[d]; e.N[slot] = pl->N[d]; e.L[slot] = g.L[d]; e.wide[slot] = wide ? (pl->wide_real ? 2 : 1) : 0;
         total *= g.L[d];
     }
     pl->tmpB.ensure(sizeof(double) * (size_t)total, &pl->dev_bytes);
@@ -416,7 +416,14 @@ template <class T>
 static void ensure_wide(hipgp_plan* pl, cudaStream_t s) {
     if (pl->have_wide) return;
     ensure_geoms<T>(pl, true);
-    build_spectrum<T>(pl, true, pl->colS.as<double>(), pl->specW, true, s);
+    // Where every axis of the wide embedding is at least 2N - 1 long (config 2: 4096 >= 3995, the length the cost model picks
+    // anyway) the taps are extended symmetrically and the spectrum of C^(1/2) is REAL: R^T and R then take the same staged
+    // real-spectrum column pass as K instead of reading a complex spectrum from global memory (HIPGP_WIDE_COMPLEX=1: A/B switch).
+    static const char* env_c = getenv("HIPGP_WIDE_COMPLEX");
+    bool real_ok = !env_c;
+    for (int d = 0; d < pl->D; ++d) if (pl->Lw[d] < 2 * pl->N[d] - 1) real_ok = false;
+    pl->wide_real = real_ok;
+    build_spectrum<T>(pl, true, pl->colS.as<double>(), pl->specW, !real_ok, s);
     pl->have_wide = true;
 }
 
@@ -514,8 +521,8 @@ static void matvec(hipgp_plan* pl, int mode, const void* in, void* out, long B, 
     switch (mode) {
         case HIPGP_MV_K: spec = pl->specK.p; kind = SPEC_REAL; break;
         case HIPGP_MV_CINV: spec = pl->specCinv.p; kind = SPEC_REAL; break;
-        case HIPGP_MV_RT: spec = pl->specW.p; kind = SPEC_CPLX; break;
-        case HIPGP_MV_R: spec = pl->specW.p; kind = SPEC_CPLX_CONJ; break;
+        case HIPGP_MV_RT: spec = pl->specW.p; kind = pl->wide_real ? SPEC_REAL : SPEC_CPLX; break;
+        case HIPGP_MV_R: spec = pl->specW.p; kind = pl->wide_real ? SPEC_REAL : SPEC_CPLX_CONJ; break;
         default: throw Error("unknown matvec mode");
     }
     run_pipeline<T>(pl, g, n_in, n_out, spec, kind, B, ff, fi, null_state(), false, s);

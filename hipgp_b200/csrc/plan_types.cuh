@@ -263,6 +263,7 @@ struct hipgp_plan {
     size_t dev_bytes = 0;
     long launches = 0;
     bool have_spec = false, have_wide = false;
+    bool wide_real = false;    // wide embedding long enough for symmetric taps: real spectrum for R^T / R
     double clampv = 1e-6;
     long nclamped = 0;
 

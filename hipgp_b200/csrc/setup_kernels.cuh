@@ -148,6 +148,14 @@ __host__ __device__ __forceinline__ int embed_index(int i, int m, int N, int L, 
         if (i > L - m) return L - i;
         return -1;
     }
+    if (wide == 2) {
+        // SYMMETRIC wide embedding (needs L >= 2N - 1): taps s[lag mod N] for every lag in (-N, N).  The rectangular product
+        // R^T v (outputs [0, N), inputs [0, m)) only reads lags in [-(m-1), N-1]; the mirrored taps at lags (-N, -m] land on
+        // circular positions that no (output, input) pair reaches, and they make the tap sequence even, i.e. the spectrum REAL.
+        const int lag = i < N ? i : (i > L - N ? L - i : -1);
+        if (lag < 0) return -1;
+        return lag < m ? lag : N - lag;
+    }
     if (i < N) return i < m ? i : N - i;
     if (i > L - m) return L - i;
     return -1;
