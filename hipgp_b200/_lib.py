@@ -56,6 +56,10 @@ SIGNATURES = {
     "hipgp_slab_stage1": (_i, [_vp, _vp, _vp, _vp]),
     "hipgp_slab_stage2": (_i, [_vp, _i, _vp, _vp]),
     "hipgp_slab_stage3": (_i, [_vp, _vp, _vp, _vp]),
+    "hipgp_slab2_sizes": (_i, [_vp, _pi64, _pi64]),
+    "hipgp_slab2_stage_a": (_i, [_vp, _vp, _vp, _vp]),
+    "hipgp_slab2_stage_b": (_i, [_vp, _i, _vp, _vp]),
+    "hipgp_slab2_stage_c": (_i, [_vp, _vp, _vp, _vp]),
     "hipgp_plan_device_bytes": (_i, [_vp, C.POINTER(_sz)]),
     "hipgp_plan_launch_count": (_i, [_vp, _pi64]),
     "hipgp_plan_profile": (_i, [_vp, _i]),

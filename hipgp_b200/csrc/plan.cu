@@ -409,7 +409,7 @@ static void set_first_row(hipgp_plan* pl, const void* column, double clampv, cud
     dct_all_axes(pl, pl->Dsqrt.as<double>(), pl->colS.as<double>(), pl->tmpB.as<double>(), true, s);
     build_spectrum<T>(pl, false, pl->colK.as<double>(), pl->specK, false, s);
     build_spectrum<T>(pl, false, pl->colG.as<double>(), pl->specCinv, false, s);
-    pl->have_spec = true; pl->have_wide = false;
+    pl->have_spec = true; pl->have_wide = false; pl->have_slabK = pl->have_slabCinv = false;
 }
 
 template <class T>
@@ -440,6 +440,7 @@ static PcgDev null_state() { PcgDev st{}; return st; }
 struct SlabGeo { long n0_loc, Lq, chunk, P3, exch_elems; };
 template <class T>
 static SlabGeo slab_geo(hipgp_plan* pl, Geom<T>& g) {
+    if (g.L[1] % pl->slab_nranks) throw Error("slab decomposition v1: embedding length of axis 1 must be divisible by the number of ranks");
     SlabGeo q;
     q.n0_loc = pl->m[0] / pl->slab_nranks;
     q.Lq = g.L[1] / pl->slab_nranks;
@@ -497,6 +498,119 @@ static void slab_stage3(hipgp_plan* pl, const void* recv_buf, void* out_slab, cu
     rows_geom(R, g);
     R.out = (T*)out_slab; R.W = W1; R.W_rows = (int)rows;
     R.mode = RI_PLAIN; R.do_fft = 1; R.total_rows = rows; R.nrows = (int)rows; R.n_real = pl->m[2]; R.st = null_state();
+    R.spec = nullptr; R.spec_kind = SPEC_NONE;
+    launch_rows<T>(pl, true, R, s, geom_allows_fast(g));
+}
+
+// ---- slab decomposition, version 2: exchange the UN-PADDED row-pass output, split along the last-axis BINS ------------------
+// stage A (local)  : rows r2c on this rank's n0/P planes -> W1[n0_loc m1][P3]; pack -> send[dest q][n0_loc m1][Pq]
+//                    (Pq = bins per rank; the zero-padded axis-1 transform is NOT part of what travels: half the bytes of v1)
+// (all-to-all)     : recv[src p][n0_loc m1][Pq] = [i0 (all m0)][i1][Pq]: every rank holds ALL planes for its Pq bins
+// stage B (local)  : axis-1 forward (pad m1 -> L1), axis-0 forward x spectrum slice x inverse, axis-1 inverse (crop) -- the
+//                    ordinary three column passes of the undecomposed pipeline on a [m0][.][Pq] array -- back into recv
+// (all-to-all back)
+// stage C (local)  : unpack -> W1, rows c2r, crop
+struct Slab2Geo { long n0_loc, rows, Pq, exch; };
+template <class T>
+static Slab2Geo slab2_geo(hipgp_plan* pl, Geom<T>& g) {
+    Slab2Geo q;
+    q.n0_loc = pl->m[0] / pl->slab_nranks;
+    q.rows = q.n0_loc * pl->m[1];
+    q.Pq = ((g.H + 1 + pl->slab_nranks - 1) / pl->slab_nranks + 1) / 2 * 2;      // bins per rank, even (16-byte lanes in fp32)
+    q.exch = (long)pl->slab_nranks * q.rows * q.Pq;
+    return q;
+}
+// send[(q rows + r) Pq + b] = W[r P + q Pq + b]  (zero past the row pitch) / the inverse; 16-byte units of `per` complex numbers
+template <class T>
+__global__ void slab_pack_kernel(const cplx<T>* __restrict__ W, cplx<T>* __restrict__ buf, long rows, long P, long Pq, int nranks, int unpack) {
+    const long total = (long)nranks * rows * Pq;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const long b = i % Pq, r = (i / Pq) % rows, q = i / (Pq * rows);
+        const long c = q * Pq + b;
+        if (unpack) { if (c < P) const_cast<cplx<T>*>(W)[r * P + c] = buf[i]; }
+        else buf[i] = c < P ? W[r * P + c] : mk<T>(0, 0);
+    }
+}
+template <class T>
+__global__ void slab_spec_slice_kernel(const T* __restrict__ spec, T* __restrict__ out, long lines, long P, long Pq, long c0) {
+    const long total = lines * Pq;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const long b = i % Pq, l = i / Pq;
+        out[i] = (c0 + b < P) ? spec[l * P + c0 + b] : (T)0;
+    }
+}
+
+template <class T>
+static void slab2_stageA(hipgp_plan* pl, const void* in_slab, void* send_buf, cudaStream_t s) {
+    Geom<T>& g = geom(pl, false, Tag<T>());
+    const Slab2Geo q = slab2_geo<T>(pl, g);
+    pl->W1.ensure(sizeof(cplx<T>) * (size_t)q.rows * g.P, &pl->dev_bytes);
+    cplx<T>* W1 = pl->W1.as<cplx<T>>();
+    RowsParams<T> R{};
+    rows_geom(R, g);
+    R.in = (const T*)in_slab; R.W = W1; R.W_rows = (int)q.rows;
+    R.mode = RF_PLAIN; R.do_fft = 1; R.total_rows = q.rows; R.nrows = (int)q.rows; R.n_real = pl->m[2]; R.st = null_state();
+    launch_rows<T>(pl, false, R, s, geom_allows_fast(g));
+    auto k = slab_pack_kernel<T>;
+    const unsigned nb = (unsigned)std::min<long>((q.exch + 255) / 256, 148L * 16);
+    HIPGP_LAUNCH(k, dim3(nb), dim3(256), 0, s, (const cplx<T>*)W1, (cplx<T>*)send_buf, q.rows, (long)g.P, q.Pq, pl->slab_nranks, 0);
+    CK_LAUNCH(); pl->launches++;
+}
+
+template <class T>
+static void slab2_stageB(hipgp_plan* pl, int mode, void* buf, cudaStream_t s) {
+    Geom<T>& g = geom(pl, false, Tag<T>());
+    const Slab2Geo q = slab2_geo<T>(pl, g);
+    const long L1 = g.L[1], L0 = g.L[0], Pq = q.Pq;
+    const int m0 = pl->m[0], m1 = pl->m[1];
+    const bool fast = geom_allows_fast(g);
+    // this rank's bins of the spectrum, repacked once per spectrum to [L0][L1][Pq]
+    DevBuf& slice = mode == HIPGP_MV_K ? pl->slabSpecK : pl->slabSpecCinv;
+    bool& have = mode == HIPGP_MV_K ? pl->have_slabK : pl->have_slabCinv;
+    if (!have) {
+        slice.ensure(sizeof(T) * (size_t)(L0 * L1 * Pq), &pl->dev_bytes);
+        auto k = slab_spec_slice_kernel<T>;
+        const long total = L0 * L1 * Pq;
+        const unsigned nb = (unsigned)std::min<long>((total + 255) / 256, 148L * 16);
+        HIPGP_LAUNCH(k, dim3(nb), dim3(256), 0, s, (mode == HIPGP_MV_K ? pl->specK.as<T>() : pl->specCinv.as<T>()), slice.as<T>(), L0 * L1, (long)g.P, Pq,
+                     (long)pl->slab_rank * Pq);
+        CK_LAUNCH(); pl->launches++;
+        have = true;
+    }
+    pl->W2.ensure(sizeof(cplx<T>) * (size_t)((long)m0 * L1 * Pq), &pl->dev_bytes);
+    cplx<T>* W2 = pl->W2.as<cplx<T>>();
+    ColsParams<T> C{};
+    C.spec = nullptr; C.spec_kind = SPEC_NONE;
+    // axis 1 forward: buf[i0][m1][Pq] -> W2[i0][L1][Pq]
+    C.in = (const cplx<T>*)buf; C.out = W2; C.n_in = m1; C.n_out = m1; C.inner = Pq; C.pitch = Pq;
+    C.in_ostride = (long)m1 * Pq; C.out_ostride = L1 * Pq; C.f = g.fcol[1].dev; C.mode = CM_FWD;
+    launch_cols<T>(pl, C, m0, 1, s, fast);
+    // axis 0 fused, in place on W2
+    C = ColsParams<T>{};
+    C.in = W2; C.out = W2; C.n_in = m0; C.n_out = m0; C.inner = L1 * Pq; C.pitch = L1 * Pq;
+    C.f = g.fcol[0].dev; C.mode = CM_FUSED; C.spec = slice.p; C.spec_kind = SPEC_REAL;
+    launch_cols<T>(pl, C, 1, 1, s, fast);
+    // axis 1 inverse: W2 -> buf[i0][m1][Pq]
+    C = ColsParams<T>{};
+    C.in = W2; C.out = (cplx<T>*)buf; C.n_in = m1; C.n_out = m1; C.inner = Pq; C.pitch = Pq;
+    C.in_ostride = L1 * Pq; C.out_ostride = (long)m1 * Pq; C.f = g.fcol[1].dev; C.mode = CM_INV; C.spec = nullptr; C.spec_kind = SPEC_NONE;
+    launch_cols<T>(pl, C, m0, 1, s, fast);
+}
+
+template <class T>
+static void slab2_stageC(hipgp_plan* pl, const void* recv_buf, void* out_slab, cudaStream_t s) {
+    Geom<T>& g = geom(pl, false, Tag<T>());
+    const Slab2Geo q = slab2_geo<T>(pl, g);
+    pl->W1.ensure(sizeof(cplx<T>) * (size_t)q.rows * g.P, &pl->dev_bytes);
+    cplx<T>* W1 = pl->W1.as<cplx<T>>();
+    auto k = slab_pack_kernel<T>;
+    const unsigned nb = (unsigned)std::min<long>((q.exch + 255) / 256, 148L * 16);
+    HIPGP_LAUNCH(k, dim3(nb), dim3(256), 0, s, (const cplx<T>*)W1, (cplx<T>*)const_cast<void*>(recv_buf), q.rows, (long)g.P, q.Pq, pl->slab_nranks, 1);
+    CK_LAUNCH(); pl->launches++;
+    RowsParams<T> R{};
+    rows_geom(R, g);
+    R.out = (T*)out_slab; R.W = W1; R.W_rows = (int)q.rows;
+    R.mode = RI_PLAIN; R.do_fft = 1; R.total_rows = q.rows; R.nrows = (int)q.rows; R.n_real = pl->m[2]; R.st = null_state();
     R.spec = nullptr; R.spec_kind = SPEC_NONE;
     launch_rows<T>(pl, true, R, s, geom_allows_fast(g));
 }
@@ -729,7 +843,7 @@ int hipgp_plan_destroy(hipgp_plan* pl) {
     for (DevBuf* b : {&pl->specK, &pl->specCinv, &pl->specW, &pl->Dm, &pl->Dinv, &pl->Dsqrt, &pl->colK, &pl->colG, &pl->colS,
                       &pl->tmpA, &pl->tmpB, &pl->costab, &pl->counts, &pl->W1, &pl->W2, &pl->vr, &pl->vp, &pl->vz, &pl->vAp,
                       &pl->partial, &pl->scal, &pl->cnt, &pl->flags, &pl->stage_in, &pl->stage_out, &pl->corrU, &pl->corrV, &pl->corrS,
-                      &pl->corrLag, &pl->gradA, &pl->costabs[0], &pl->costabs[1], &pl->costabs[2]})
+                      &pl->corrLag, &pl->gradA, &pl->slabSpecK, &pl->slabSpecCinv, &pl->costabs[0], &pl->costabs[1], &pl->costabs[2]})
         b->release(t);
     if (pl->pinned) cudaFreeHost(pl->pinned);
 #ifndef HIPGP_EMU
@@ -945,7 +1059,6 @@ int hipgp_plan_set_slab(hipgp_plan* pl, int rank, int nranks) {
     if (pl->D != 3) throw Error("slab decomposition needs a 3-D grid");
     if (nranks < 1 || rank < 0 || rank >= nranks) throw Error("bad rank / nranks");
     if (pl->m[0] % nranks) throw Error("grid extent of axis 0 must be divisible by the number of ranks");
-    if (pl->Ln[1] % nranks) throw Error("embedding length of axis 1 must be divisible by the number of ranks");
     pl->slab_rank = rank; pl->slab_nranks = nranks;
     API_END
 }
@@ -976,6 +1089,39 @@ int hipgp_slab_stage3(hipgp_plan* pl, const void* recv_buf, void* out_slab, void
     API_BEGIN
     set_device(pl);
     DISPATCH(pl, slab_stage3<float>(pl, recv_buf, out_slab, (cudaStream_t)stream), slab_stage3<double>(pl, recv_buf, out_slab, (cudaStream_t)stream));
+    API_END
+}
+int hipgp_slab2_sizes(const hipgp_plan* pl, int64_t* slab_reals, int64_t* exchange_complex) {
+    API_BEGIN
+    need_plan(pl);
+    if (pl->D != 3) throw Error("slab decomposition needs a 3-D grid");
+    const long n0 = pl->m[0] / pl->slab_nranks;
+    if (slab_reals) *slab_reals = n0 * pl->m[1] * pl->m[2];
+    const long H1 = (long)pl->Ln[2] / 2 + 1;
+    const long Pq = ((H1 + pl->slab_nranks - 1) / pl->slab_nranks + 1) / 2 * 2;
+    if (exchange_complex) *exchange_complex = (long)pl->slab_nranks * n0 * pl->m[1] * Pq;
+    API_END
+}
+int hipgp_slab2_stage_a(hipgp_plan* pl, const void* in_slab, void* send_buf, void* stream) {
+    API_BEGIN
+    set_device(pl);
+    if (!pl->have_spec) throw Error("plan has no spectrum");
+    if (pl->D != 3) throw Error("slab decomposition needs a 3-D grid");
+    DISPATCH(pl, slab2_stageA<float>(pl, in_slab, send_buf, (cudaStream_t)stream), slab2_stageA<double>(pl, in_slab, send_buf, (cudaStream_t)stream));
+    API_END
+}
+int hipgp_slab2_stage_b(hipgp_plan* pl, int mode, void* buf, void* stream) {
+    API_BEGIN
+    set_device(pl);
+    if (!pl->have_spec) throw Error("plan has no spectrum");
+    if (mode != HIPGP_MV_K && mode != HIPGP_MV_CINV) throw Error("slab mode supports K and C^-1");
+    DISPATCH(pl, slab2_stageB<float>(pl, mode, buf, (cudaStream_t)stream), slab2_stageB<double>(pl, mode, buf, (cudaStream_t)stream));
+    API_END
+}
+int hipgp_slab2_stage_c(hipgp_plan* pl, const void* recv_buf, void* out_slab, void* stream) {
+    API_BEGIN
+    set_device(pl);
+    DISPATCH(pl, slab2_stageC<float>(pl, recv_buf, out_slab, (cudaStream_t)stream), slab2_stageC<double>(pl, recv_buf, out_slab, (cudaStream_t)stream));
     API_END
 }
 int hipgp_plan_profile(hipgp_plan* pl, int enable) {

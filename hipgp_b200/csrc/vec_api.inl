@@ -9,6 +9,7 @@ static std::mutex g_scratch_mu;
 static std::map<std::pair<int, cudaStream_t>, DevBuf> g_scratch;
 static size_t g_scratch_total = 0;
 static const int kChunks = 64;
+static const long kFillBlocks = 148 * 8;
 static const long kMaxGridY = 65535;
 
 static double* scratch_for(cudaStream_t s, size_t bytes) {
@@ -28,8 +29,10 @@ template <class T>
 static void vec_op(int op, void* x, void* r, const void* a, const void* b2, const double* num, const double* den, double* out,
                    long B, long M, cudaStream_t s) {
     if (B <= 0 || M <= 0) return;
-    int nchunk = (int)std::min<long>(kChunks, std::max<long>(1, (M + 4095) / 4096));
-    double* scr = scratch_for(s, sizeof(double) * (size_t)B * kChunks);
+    // at least kChunks chunks per right-hand side; few long right-hand sides get enough chunks to fill the machine
+    const long want = std::max<long>(kChunks, (kFillBlocks + B - 1) / B);
+    int nchunk = (int)std::min<long>(want, std::max<long>(1, (M + 4095) / 4096));
+    double* scr = scratch_for(s, sizeof(double) * (size_t)B * (size_t)nchunk);
     auto k = vec_kernel<T>;
     for (long b0 = 0; b0 < B; b0 += kMaxGridY) {        // grid.y is limited to 65535 right-hand sides per launch
         const long nb = std::min(kMaxGridY, B - b0);

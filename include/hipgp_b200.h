@@ -171,6 +171,15 @@ int hipgp_slab_sizes(const hipgp_plan* plan, int64_t* slab_reals, int64_t* excha
 int hipgp_slab_stage1(hipgp_plan* plan, const void* in_slab_dev, void* send_buf_dev, void* stream);
 int hipgp_slab_stage2(hipgp_plan* plan, int mode, void* buf_dev, void* stream);
 int hipgp_slab_stage3(hipgp_plan* plan, const void* recv_buf_dev, void* out_slab_dev, void* stream);
+/* version 2 of the same decomposition: what travels is the UN-PADDED output of the row pass, split along the bins of the last
+ * axis (half the bytes of version 1, whose exchange carried the zero-padded axis-1 transform); after the exchange a rank owns
+ * all (i0, i1) for its bins and runs the three ordinary column passes locally:
+ *   stage_a(in_slab -> send) ; all-to-all(send -> buf) ; stage_b(mode, buf in place) ; all-to-all(buf -> recv) ; stage_c(recv -> out_slab)
+ * exchange buffers hold `exchange_complex` complex numbers = nranks equal blocks. */
+int hipgp_slab2_sizes(const hipgp_plan* plan, int64_t* slab_reals, int64_t* exchange_complex);
+int hipgp_slab2_stage_a(hipgp_plan* plan, const void* in_slab_dev, void* send_buf_dev, void* stream);
+int hipgp_slab2_stage_b(hipgp_plan* plan, int mode, void* buf_dev, void* stream);
+int hipgp_slab2_stage_c(hipgp_plan* plan, const void* recv_buf_dev, void* out_slab_dev, void* stream);
 
 /* bytes of device memory the plan currently owns (spectra, twiddles, workspace) */
 int hipgp_plan_device_bytes(const hipgp_plan* plan, size_t* bytes);

@@ -14,14 +14,16 @@ def mkplan(dims, dt, col, slab=None):
     ncl = C.c_int64()
     assert lib.hipgp_plan_set_first_row(plan, ptr(col), 1e-6, C.byref(ncl), None) == 0, lib.hipgp_last_error()
     return plan
-def run(dims, nranks, dt):
+def run(dims, nranks, dt, v2=False):
     g = np.meshgrid(*[np.linspace(0, 1 + d, k) for d, k in enumerate(dims)], indexing="ij")
     r = np.sqrt(sum((x - x.flat[0]) ** 2 for x in g)); col = ((1 + np.sqrt(3) * r / 0.4) * np.exp(-np.sqrt(3) * r / 0.4)).reshape(-1); col[0] += 1e-2
     col = col.astype(dt)
     full = mkplan(dims, dt, col)
     plans = [mkplan(dims, dt, col, (rk, nranks)) for rk in range(nranks)]
     a, b = C.c_int64(), C.c_int64()
-    lib.hipgp_slab_sizes(plans[0], C.byref(a), C.byref(b)); slab_elems, exch = a.value, b.value
+    st1, st2, st3, sz = ((lib.hipgp_slab2_stage_a, lib.hipgp_slab2_stage_b, lib.hipgp_slab2_stage_c, lib.hipgp_slab2_sizes) if v2 else
+                         (lib.hipgp_slab_stage1, lib.hipgp_slab_stage2, lib.hipgp_slab_stage3, lib.hipgp_slab_sizes))
+    assert sz(plans[0], C.byref(a), C.byref(b)) == 0, lib.hipgp_last_error(); slab_elems, exch = a.value, b.value
     rng = np.random.default_rng(0); M = int(np.prod(dims))
     v = rng.standard_normal((1, M)).astype(dt)
     n0 = dims[0] // nranks
@@ -36,17 +38,18 @@ def run(dims, nranks, dt):
         assert lib.hipgp_matvec(full, mode, ptr(v), ptr(ref), 1, None) == 0
         bufs = []
         for p, x in zip(plans, slabs):
-            send = np.zeros(exch, dtype=cdt); assert lib.hipgp_slab_stage1(p, ptr(x), ptr(send), None) == 0, lib.hipgp_last_error(); bufs.append(send)
+            send = np.zeros(exch, dtype=cdt); assert st1(p, ptr(x), ptr(send), None) == 0, lib.hipgp_last_error(); bufs.append(send)
         bufs = exchange(bufs)
-        for p, bb in zip(plans, bufs): assert lib.hipgp_slab_stage2(p, mode, ptr(bb), None) == 0, lib.hipgp_last_error()
+        for p, bb in zip(plans, bufs): assert st2(p, mode, ptr(bb), None) == 0, lib.hipgp_last_error()
         bufs = exchange(bufs)
         outs = []
         for p, bb in zip(plans, bufs):
-            o = np.zeros(slab_elems, dtype=dt); assert lib.hipgp_slab_stage3(p, ptr(bb), ptr(o), None) == 0, lib.hipgp_last_error(); outs.append(o)
+            o = np.zeros(slab_elems, dtype=dt); assert st3(p, ptr(bb), ptr(o), None) == 0, lib.hipgp_last_error(); outs.append(o)
         got = np.concatenate(outs).reshape(1, -1)
         e = np.linalg.norm(got - ref) / np.linalg.norm(ref)
-        print(dims, nranks, dt.__name__, "mode", mode, "err %.2e" % e); ok &= e < (1e-5 if dt == np.float32 else 1e-10)
+        print(dims, nranks, dt.__name__, "v2" if v2 else "v1", "mode", mode, "err %.2e" % e); ok &= e < (1e-5 if dt == np.float32 else 1e-10)
     return ok
 if __name__ == "__main__":
     ok = run((16, 12, 20), 2, np.float64) & run((16, 12, 20), 4, np.float32)
+    ok &= run((16, 12, 20), 2, np.float64, True) & run((16, 12, 20), 4, np.float32, True) & run((12, 10, 14), 3, np.float64, True)
     sys.exit(0 if ok else 1)

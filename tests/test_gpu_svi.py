@@ -90,8 +90,9 @@ def test_begin_step_pcg_matches_fused_solve(golden_dir):
     assert relerr(torch.cat(xs), x_ref.cpu().numpy()) < 1e-12
 
 
+@pytest.mark.parametrize("layout", ["bins", "axis1"])
 @pytest.mark.parametrize("dname,nranks", [("f64", 2), ("f32", 4)])
-def test_slab_decomposed_matvec_emulated(dname, nranks):
+def test_slab_decomposed_matvec_emulated(dname, nranks, layout):
     """Grid-sharded (slab) K and C^-1 matvecs: all ranks emulated on one GPU, the all-to-all done by tensor shuffling;
     must equal the undecomposed plan and the CPU oracle."""
     from hipgp_b200.slab import SlabToeplitz
@@ -102,7 +103,7 @@ def test_slab_decomposed_matvec_emulated(dname, nranks):
     dims = (16, 12, 20)
     xg = [torch.linspace(0, 1 + d, m, dtype=dtype, device=DEV) for d, m in enumerate(dims)]
     col = hk.first_row(xg, hk.Matern(nu=1.5, dtype=dtype), (1.0, 0.4), jitter=1e-2)
-    slab = SlabToeplitz(dims, col, dtype, DEV, emulate_ranks=nranks)
+    slab = SlabToeplitz(dims, col, dtype, DEV, emulate_ranks=nranks, layout=layout)
     full = Plan(dims, dtype, DEV).set_first_row(col)
     torch.manual_seed(0)
     v = torch.randn(1, int(np.prod(dims)), dtype=dtype, device=DEV)
@@ -114,6 +115,31 @@ def test_slab_decomposed_matvec_emulated(dname, nranks):
         got = torch.cat(slab.matvec(mode, slabs)).reshape(1, -1)
         assert relerr(got, full.matvec(mode, v).cpu().numpy()) < tol
         assert relerr(got, ref.numpy()) < (tol if mode == L.MV_K else 50 * tol)
+
+
+@pytest.mark.parametrize("precond", [True, False])
+def test_slab_solver_device_side_stopping_rule(precond):
+    """SlabToeplitz.solve keeps the reference's break (cg.py:66-67) as a device-side flag: on one rank it must stop at the
+    iteration the plan's PCG stops and return the same iterate, also when the host only looks every 5 iterations."""
+    from hipgp_b200.slab import SlabToeplitz
+    from hipgp_b200.plan import Plan
+    from hipgp_b200 import kernels as hk
+    dtype = torch.float64
+    dims = (12, 10, 14)
+    xg = [torch.linspace(0, 1 + d, m, dtype=dtype, device=DEV) for d, m in enumerate(dims)]
+    col = hk.first_row(xg, hk.Matern(nu=1.5, dtype=dtype), (1.0, 0.4), jitter=1e-2)
+    slab = SlabToeplitz(dims, col, dtype, DEV, rank=0, nranks=1)
+    full = Plan(dims, dtype, DEV).set_first_row(col)
+    torch.manual_seed(1)
+    b = torch.randn(1, int(np.prod(dims)), dtype=dtype, device=DEV)
+    x_ref, info = full.pcg(b, maxiter=400, tol=1e-8, precond=precond, return_info=True)
+    x = slab.solve(b, do_precond=precond, maxiter=400, tol=1e-8)
+    assert 3 < info["iters"] < 400
+    assert abs(slab.last_iters - info["iters"]) <= 1
+    assert relerr(x, x_ref.cpu().numpy()) < 1e-9
+    # stopping early must not depend on how often the host looks
+    x1 = slab.solve(b, do_precond=precond, maxiter=400, tol=1e-8, check_every=1)
+    assert torch.equal(x1, x)
 
 
 def test_batch_predict_streams_the_same_batches(golden_dir):
