@@ -127,14 +127,14 @@ def test_slab_solver_device_side_stopping_rule(precond):
     dtype = torch.float64
     dims = (12, 10, 14)
     xg = [torch.linspace(0, 1 + d, m, dtype=dtype, device=DEV) for d, m in enumerate(dims)]
-    col = hk.first_row(xg, hk.Matern(nu=1.5, dtype=dtype), (1.0, 0.4), jitter=1e-2)
+    col = hk.first_row(xg, hk.Matern(nu=1.5, dtype=dtype), (1.0, 0.15), jitter=1e-2)   # oracle: 21 preconditioned / 114 plain iterations
     slab = SlabToeplitz(dims, col, dtype, DEV, rank=0, nranks=1)
     full = Plan(dims, dtype, DEV).set_first_row(col)
     torch.manual_seed(1)
     b = torch.randn(1, int(np.prod(dims)), dtype=dtype, device=DEV)
     x_ref, info = full.pcg(b, maxiter=400, tol=1e-8, precond=precond, return_info=True)
     x = slab.solve(b, do_precond=precond, maxiter=400, tol=1e-8)
-    assert 3 < info["iters"] < 400
+    assert 3 < info["iters"] < 200
     assert abs(slab.last_iters - info["iters"]) <= 1
     assert relerr(x, x_ref.cpu().numpy()) < 1e-9
     # stopping early must not depend on how often the host looks
