@@ -59,6 +59,15 @@ SIGNATURES = {
     "hipgp_slab2_sizes": (_i, [_vp, _pi64, _pi64]),
     "hipgp_slab2_stage_a": (_i, [_vp, _vp, _vp, _vp]),
     "hipgp_slab2_stage_b": (_i, [_vp, _i, _vp, _vp]),
+    "hipgp_slab2_stage_b_chunk": (_i, [_vp, _i, _vp, _i, _vp]),
+    "hipgp_plan_set_slab_chunks": (_i, [_vp, _i]),
+    "hipgp_slab2_peer_alloc": (_i, [_vp, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), _vp, _vp]),
+    "hipgp_slab2_peer_open": (_i, [_vp, _vp, _vp]),
+    "hipgp_slab2_peer_set": (_i, [_vp, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
+    "hipgp_slab2_push_a": (_i, [_vp, _vp, _vp]),
+    "hipgp_slab2_push_b": (_i, [_vp, _i, _i, _vp]),
+    "hipgp_slab2_finish": (_i, [_vp, _vp, _vp]),
+    "hipgp_slab2_push_only": (_i, [_vp, _i, _vp]),
     "hipgp_slab2_stage_c": (_i, [_vp, _vp, _vp, _vp]),
     "hipgp_plan_device_bytes": (_i, [_vp, C.POINTER(_sz)]),
     "hipgp_plan_launch_count": (_i, [_vp, _pi64]),

@@ -282,6 +282,12 @@ struct hipgp_plan {
     void* pinned = nullptr;                // host flags mirror
     cudaStream_t copy_streams[2] = {nullptr, nullptr};   // H2D / D2H streams of hipgp_pcg_host_pipelined
     long pcg_B = 0;
+    // peer-memory exchange (bins layout): R1 receives the way there, R2 the way back; peerR*[q] = rank q's buffers as mapped here
+    DevBuf slabR1, slabR2;
+    void* peerR1[16] = {}; void* peerR2[16] = {};
+    void* ipc_opened[32] = {}; int n_ipc_opened = 0;
+    bool peers_ready = false;
+    int slab_chunks = 1;                     // bins layout: the exchange is cut into this many independent all-to-alls
     int slab_rank = 0, slab_nranks = 1;      // slab-decomposed grid (axis 0 split over ranks); 1 = not decomposed
     void* run_x = nullptr; long run_B = 0; bool run_precond = true; double run_tol = 0; bool run_active = false;   // begin/step state
     // optional per-kernel-class timing (bench.py roofline): CUDA events around every launch

@@ -180,6 +180,29 @@ int hipgp_slab2_sizes(const hipgp_plan* plan, int64_t* slab_reals, int64_t* exch
 int hipgp_slab2_stage_a(hipgp_plan* plan, const void* in_slab_dev, void* send_buf_dev, void* stream);
 int hipgp_slab2_stage_b(hipgp_plan* plan, int mode, void* buf_dev, void* stream);
 int hipgp_slab2_stage_c(hipgp_plan* plan, const void* recv_buf_dev, void* out_slab_dev, void* stream);
+/* Overlap: with `nchunks` > 1 (set before hipgp_slab2_sizes) the exchange buffer is laid out [chunk][rank][rows][bins/chunk], so
+ * every chunk is a contiguous all-to-all of its own (exchange_complex / nchunks numbers) and stage_b can run on chunk c while
+ * chunk c+1 is still on the wire and chunk c-1 already travels back. */
+int hipgp_plan_set_slab_chunks(hipgp_plan* plan, int nchunks);
+int hipgp_slab2_stage_b_chunk(hipgp_plan* plan, int mode, void* buf_dev, int chunk, void* stream);
+/* Peer-memory exchange (one process per GPU on one NVLink / NVSwitch node): no collective library on the data path.
+ * The plan owns two receive buffers; ranks swap their inter-process handles (64 bytes each, e.g. with an all-gather) and
+ * open them; then the packing kernel's 16-byte stores go straight into the peers' buffers over NVLink:
+ *   push_a(in_slab)      rows r2c, every destination's bins stored into ITS first buffer
+ *   -- barrier across ranks (any stream-ordered collective) --
+ *   push_b(mode, chunk)  the column passes in place on the own first buffer, results stored into the peers' second buffers
+ *   -- barrier --
+ *   finish(out_slab)     own second buffer -> rows c2r
+ * The two barriers also order the buffers' reuse by the next matvec.  peer_set takes raw addresses instead of handles for
+ * ranks that live in one process. */
+int hipgp_slab2_peer_alloc(hipgp_plan* plan, void** r1_out, void** r2_out, void* handle1_64, void* handle2_64);
+int hipgp_slab2_peer_open(hipgp_plan* plan, const void* handles1, const void* handles2);
+int hipgp_slab2_peer_set(hipgp_plan* plan, void* const* r1_all, void* const* r2_all);
+int hipgp_slab2_push_a(hipgp_plan* plan, const void* in_slab_dev, void* stream);
+int hipgp_slab2_push_b(hipgp_plan* plan, int mode, int chunk, void* stream);
+int hipgp_slab2_finish(hipgp_plan* plan, void* out_slab_dev, void* stream);
+/* measurement aid: the transfer kernel of push_a (back = 0) or push_b (back = 1) alone, on whatever the buffers hold */
+int hipgp_slab2_push_only(hipgp_plan* plan, int back, void* stream);
 
 /* bytes of device memory the plan currently owns (spectra, twiddles, workspace) */
 int hipgp_plan_device_bytes(const hipgp_plan* plan, size_t* bytes);

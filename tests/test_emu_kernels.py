@@ -289,11 +289,13 @@ def test_rt_column_gradient_against_autograd_of_the_reference_formula(lib, dims)
     lib.hipgp_plan_destroy(plan)
 
 
-@pytest.mark.parametrize("dims,nranks,dname,bins", [((16, 12, 20), 2, "f64", False), ((16, 12, 20), 4, "f32", True), ((12, 10, 14), 3, "f64", True)])
-def test_slab_stages_equal_the_undecomposed_matvec(lib, dims, nranks, dname, bins):
+@pytest.mark.parametrize("dims,nranks,dname,bins,chunks,peer", [((16, 12, 20), 2, "f64", False, 1, False), ((16, 12, 20), 4, "f32", True, 2, False),
+                                                               ((12, 10, 14), 3, "f64", True, 1, True)])
+def test_slab_stages_equal_the_undecomposed_matvec(lib, dims, nranks, dname, bins, chunks, peer):
     """the three local stages of the grid-sharded matvec (both exchange layouts; `bins` also for a rank count
-    that divides neither embedding length) with the all-to-all done in numpy equal the one-plan matvec."""
+    that divides neither embedding length) with the all-to-all done in numpy -- or by the packing kernels' own stores into the
+    other ranks' buffers (`peer`) -- equal the one-plan matvec."""
     import sys
     sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scripts", "dev"))
     import emu_slab
-    assert emu_slab.run(dims, nranks, np.float64 if dname == "f64" else np.float32, bins)
+    assert emu_slab.run(dims, nranks, np.float64 if dname == "f64" else np.float32, bins, chunks, peer)
