@@ -618,7 +618,9 @@ static void slab2_stageC(hipgp_plan* pl, const void* recv_buf, void* out_slab, c
     cplx<T>* W1 = pl->W1.as<cplx<T>>();
     auto k = slab_pack_kernel<T>;
     const unsigned nb = (unsigned)std::min<long>((q.exch + 255) / 256, 148L * 16);
+    PROF_BEGIN(pl, 3, s);
     HIPGP_LAUNCH(k, dim3(nb), dim3(256), 0, s, (const cplx<T>*)W1, (cplx<T>*)const_cast<void*>(recv_buf), q.rows, (long)g.P, q.Pq, q.Pqc, pl->slab_nranks, 1);
+    PROF_END(pl, s);
     CK_LAUNCH(); pl->launches++;
     RowsParams<T> R{};
     rows_geom(R, g);
@@ -657,12 +659,15 @@ __global__ void slab_push_pack_kernel(const cplx<T>* __restrict__ W, PeerPtrs ds
         for (int k = 0; k < U; ++k) if (out[k]) *out[k] = v[k];
     }
 }
-// the way back: local buffer [c][q][rows][Pqc] (block q belongs to rank q) -> peer q's buffer at block [c][me]
+// the way back: local buffer [c][q][rows][Pqc] (block q belongs to rank q) -> straight into rank q's ROW WORKSPACE
+// W[r P + me Pq + c Pqc + b], so the receiving side's inverse row pass starts without an unpack pass
 template <class T>
-__global__ void slab_push_back_kernel(const cplx<T>* __restrict__ buf, PeerPtrs dst, long rows, long Pqc, int nranks, int nch, int me, int ch0, int ch1) {
+__global__ void slab_push_back_kernel(const cplx<T>* __restrict__ buf, PeerPtrs dst, long rows, long P, long Pq, long Pqc, int nranks, int nch, int me,
+                                      int ch0, int ch1) {
     constexpr int PER = 16 / (int)sizeof(cplx<T>);
     constexpr int U = 4;
-    const long blk = rows * Pqc / PER;                    // units per (chunk, rank) block
+    const long upc = Pqc / PER;
+    const long blk = rows * upc;                          // units per (chunk, rank) block
     const long total = (long)(ch1 - ch0) * nranks * blk;
     const long step = (long)gridDim.x * blockDim.x;
     for (long i0 = (long)blockIdx.x * blockDim.x + threadIdx.x; i0 < total; i0 += U * step) {
@@ -672,9 +677,12 @@ __global__ void slab_push_back_kernel(const cplx<T>* __restrict__ buf, PeerPtrs 
             const long i = i0 + k * step;
             out[k] = nullptr;
             if (i < total) {
-                const long u = i % blk, q = (i / blk) % nranks, ch = ch0 + i / (blk * nranks);
-                v[k] = reinterpret_cast<const Unit16*>(buf)[((long)ch * nranks + q) * blk + u];
-                out[k] = reinterpret_cast<Unit16*>(dst.p[q]) + ((long)ch * nranks + me) * blk + u;
+                const long u = i % upc, r = (i / upc) % rows, q = (i / blk) % nranks, ch = ch0 + i / (blk * nranks);
+                const long c = (long)me * Pq + ch * Pqc + u * PER;
+                if (c + PER <= P) {
+                    v[k] = reinterpret_cast<const Unit16*>(buf)[((long)ch * nranks + q) * blk + r * upc + u];
+                    out[k] = reinterpret_cast<Unit16*>(reinterpret_cast<cplx<T>*>(dst.p[q]) + r * P + c);
+                }
             }
         }
 #pragma unroll
@@ -699,7 +707,9 @@ static void slab2_pushA(hipgp_plan* pl, const void* in_slab, cudaStream_t s) {
     R.mode = RF_PLAIN; R.do_fft = 1; R.total_rows = q.rows; R.nrows = (int)q.rows; R.n_real = pl->m[2]; R.st = null_state();
     launch_rows<T>(pl, false, R, s, geom_allows_fast(g));
     auto k = slab_push_pack_kernel<T>;
+    PROF_BEGIN(pl, 3, s);
     HIPGP_LAUNCH(k, dim3(148 * 8), dim3(256), 0, s, (const cplx<T>*)W1, peer_table(pl, false), q.rows, (long)g.P, q.Pq, q.Pqc, pl->slab_nranks, pl->slab_rank);
+    PROF_END(pl, s);
     CK_LAUNCH(); pl->launches++;
 }
 // the transfer kernels alone (measurement: bytes that leave the GPU / their duration = achieved NVLink rate)
@@ -713,7 +723,7 @@ static void slab2_push_only(hipgp_plan* pl, int back, cudaStream_t s) {
         HIPGP_LAUNCH(k, dim3(148 * 8), dim3(256), 0, s, (const cplx<T>*)pl->W1.p, peer_table(pl, false), q.rows, (long)g.P, q.Pq, q.Pqc, pl->slab_nranks, pl->slab_rank);
     } else {
         auto k = slab_push_back_kernel<T>;
-        HIPGP_LAUNCH(k, dim3(148 * 8), dim3(256), 0, s, (const cplx<T>*)pl->slabR1.p, peer_table(pl, true), q.rows, q.Pqc, pl->slab_nranks, q.nch, pl->slab_rank, 0, q.nch);
+        HIPGP_LAUNCH(k, dim3(148 * 8), dim3(256), 0, s, (const cplx<T>*)pl->slabR1.p, peer_table(pl, true), q.rows, (long)g.P, q.Pq, q.Pqc, pl->slab_nranks, q.nch, pl->slab_rank, 0, q.nch);
     }
     CK_LAUNCH(); pl->launches++;
 }
@@ -724,8 +734,22 @@ static void slab2_pushB(hipgp_plan* pl, int mode, int chunk, cudaStream_t s) {
     slab2_stageB<T>(pl, mode, pl->slabR1.p, chunk, s);
     auto k = slab_push_back_kernel<T>;
     const int c0 = chunk < 0 ? 0 : chunk, c1 = chunk < 0 ? q.nch : chunk + 1;
-    HIPGP_LAUNCH(k, dim3(148 * 8), dim3(256), 0, s, (const cplx<T>*)pl->slabR1.p, peer_table(pl, true), q.rows, q.Pqc, pl->slab_nranks, q.nch, pl->slab_rank, c0, c1);
+    PROF_BEGIN(pl, 3, s);
+    HIPGP_LAUNCH(k, dim3(148 * 8), dim3(256), 0, s, (const cplx<T>*)pl->slabR1.p, peer_table(pl, true), q.rows, (long)g.P, q.Pq, q.Pqc, pl->slab_nranks, q.nch, pl->slab_rank, c0, c1);
+    PROF_END(pl, s);
     CK_LAUNCH(); pl->launches++;
+}
+
+template <class T>
+static void slab2_finish(hipgp_plan* pl, void* out_slab, cudaStream_t s) {
+    Geom<T>& g = geom(pl, false, Tag<T>());
+    const Slab2Geo q = slab2_geo<T>(pl, g);
+    RowsParams<T> R{};
+    rows_geom(R, g);
+    R.out = (T*)out_slab; R.W = pl->slabR2.as<cplx<T>>(); R.W_rows = (int)q.rows;
+    R.mode = RI_PLAIN; R.do_fft = 1; R.total_rows = q.rows; R.nrows = (int)q.rows; R.n_real = pl->m[2]; R.st = null_state();
+    R.spec = nullptr; R.spec_kind = SPEC_NONE;
+    launch_rows<T>(pl, true, R, s, geom_allows_fast(g));
 }
 
 template <class T>
@@ -1262,7 +1286,10 @@ int hipgp_slab2_peer_alloc(hipgp_plan* pl, void** r1_out, void** r2_out, void* h
     if (hipgp_slab2_sizes(pl, &slab, &exch)) return -1;
     const size_t w = pl->dtype == HIPGP_F32 ? 8 : 16;
     slab_peer_close(pl);
-    pl->slabR1.ensure(w * (size_t)exch, &pl->dev_bytes); pl->slabR2.ensure(w * (size_t)exch, &pl->dev_bytes);
+    const long P3 = ((long)pl->Ln[2] / 2 + 1 + 7) / 8 * 8;
+    const size_t w1 = w * (size_t)(pl->m[0] / pl->slab_nranks) * (size_t)pl->m[1] * (size_t)P3;       // the row workspace itself
+    pl->slabR1.ensure(w * (size_t)exch, &pl->dev_bytes); pl->slabR2.ensure(w1, &pl->dev_bytes);
+    CK(cudaMemset(pl->slabR2.p, 0, w1));
     if (r1_out) *r1_out = pl->slabR1.p;
     if (r2_out) *r2_out = pl->slabR2.p;
 #ifndef HIPGP_EMU
@@ -1332,7 +1359,7 @@ int hipgp_slab2_finish(hipgp_plan* pl, void* out_slab, void* stream) {
     API_BEGIN
     set_device(pl);
     if (!pl->peers_ready) throw Error("slab peer buffers are not connected");
-    DISPATCH(pl, slab2_stageC<float>(pl, pl->slabR2.p, out_slab, (cudaStream_t)stream), slab2_stageC<double>(pl, pl->slabR2.p, out_slab, (cudaStream_t)stream));
+    DISPATCH(pl, slab2_finish<float>(pl, out_slab, (cudaStream_t)stream), slab2_finish<double>(pl, out_slab, (cudaStream_t)stream));
     API_END
 }
 int hipgp_plan_profile(hipgp_plan* pl, int enable) {

@@ -48,7 +48,25 @@ else:
         return t.item()
     ms_mv = timed(lambda: slab.matvec_K(mine), 10)
     ms_pcg = timed(lambda: slab.solve(mine, do_precond=True, maxiter=20, tol=1e-8), 2)
+    # where the time goes: per-class kernel times of one matvec (CUDA events around every launch), the barrier alone, host issue time
+    import ctypes as C, time
+    p0 = slab.plans[0]
+    L.check(p0.lib, p0.lib.hipgp_plan_profile(p0._h, 1))
+    slab.matvec_K(mine); torch.cuda.synchronize()
+    cls = {}
+    for i, nm in enumerate(("rows_fwd", "cols", "rows_inv", "push/pack")):
+        ms = C.c_double(); n = C.c_int64()
+        L.check(p0.lib, p0.lib.hipgp_plan_profile_read(p0._h, i, C.byref(ms), C.byref(n), 0))
+        cls[nm] = (round(ms.value, 4), n.value)
+    L.check(p0.lib, p0.lib.hipgp_plan_profile(p0._h, 0))
+    tok = torch.zeros(1, device=dev)
+    bar_ms = timed(lambda: dist.all_reduce(tok), 20) if world > 1 else 0.0
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    for _ in range(10): slab.matvec_K(mine)
+    issue_ms = (time.perf_counter() - t0) / 10 * 1e3
+    torch.cuda.synchronize()
     if rank == 0:
+        print(json.dumps({"kernel_ms_by_class": cls, "allreduce_barrier_ms": bar_ms, "host_issue_ms_per_matvec": issue_ms, "exchange": slab.exchange}))
         M = int(np.prod(dims)); E_h = (2 * dims[0] - 2) * (2 * dims[1] - 2) * (dims[2] - 1 + 1)
         print(json.dumps({"bench": "slab_matvec", "grid": dims, "n_gpus": world, "dtype": "f32", "matvec_ms": ms_mv,
                           "pcg20_s": ms_pcg / 1e3, "alg_GBps": 4 * (2 * M + E_h) / ms_mv / 1e6,
