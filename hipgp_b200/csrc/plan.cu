@@ -689,6 +689,11 @@ __global__ void slab_push_back_kernel(const cplx<T>* __restrict__ buf, PeerPtrs 
         for (int k = 0; k < U; ++k) if (out[k]) *out[k] = v[k];
     }
 }
+// grid of the transfer kernels: 8 CTAs per SM, fewer when the exchange is small (each thread moves four 16-byte units)
+static unsigned push_grid(long exch_complex, int per) {
+    const long units = exch_complex / per;
+    return (unsigned)std::max<long>(1, std::min<long>(148L * 8, (units + 4 * 256 - 1) / (4 * 256)));
+}
 static PeerPtrs peer_table(hipgp_plan* pl, bool back) {
     if (!pl->peers_ready) throw Error("slab peer buffers are not connected: call hipgp_slab2_peer_open / _peer_set first");
     PeerPtrs t{};
@@ -708,7 +713,7 @@ static void slab2_pushA(hipgp_plan* pl, const void* in_slab, cudaStream_t s) {
     launch_rows<T>(pl, false, R, s, geom_allows_fast(g));
     auto k = slab_push_pack_kernel<T>;
     PROF_BEGIN(pl, 3, s);
-    HIPGP_LAUNCH(k, dim3(148 * 8), dim3(256), 0, s, (const cplx<T>*)W1, peer_table(pl, false), q.rows, (long)g.P, q.Pq, q.Pqc, pl->slab_nranks, pl->slab_rank);
+    HIPGP_LAUNCH(k, dim3(push_grid(q.exch, 16 / (int)sizeof(cplx<T>))), dim3(256), 0, s, (const cplx<T>*)W1, peer_table(pl, false), q.rows, (long)g.P, q.Pq, q.Pqc, pl->slab_nranks, pl->slab_rank);
     PROF_END(pl, s);
     CK_LAUNCH(); pl->launches++;
 }
@@ -720,10 +725,10 @@ static void slab2_push_only(hipgp_plan* pl, int back, cudaStream_t s) {
     if (!back) {
         pl->W1.ensure(sizeof(cplx<T>) * (size_t)q.rows * g.P, &pl->dev_bytes);
         auto k = slab_push_pack_kernel<T>;
-        HIPGP_LAUNCH(k, dim3(148 * 8), dim3(256), 0, s, (const cplx<T>*)pl->W1.p, peer_table(pl, false), q.rows, (long)g.P, q.Pq, q.Pqc, pl->slab_nranks, pl->slab_rank);
+        HIPGP_LAUNCH(k, dim3(push_grid(q.exch, 16 / (int)sizeof(cplx<T>))), dim3(256), 0, s, (const cplx<T>*)pl->W1.p, peer_table(pl, false), q.rows, (long)g.P, q.Pq, q.Pqc, pl->slab_nranks, pl->slab_rank);
     } else {
         auto k = slab_push_back_kernel<T>;
-        HIPGP_LAUNCH(k, dim3(148 * 8), dim3(256), 0, s, (const cplx<T>*)pl->slabR1.p, peer_table(pl, true), q.rows, (long)g.P, q.Pq, q.Pqc, pl->slab_nranks, q.nch, pl->slab_rank, 0, q.nch);
+        HIPGP_LAUNCH(k, dim3(push_grid(q.exch, 16 / (int)sizeof(cplx<T>))), dim3(256), 0, s, (const cplx<T>*)pl->slabR1.p, peer_table(pl, true), q.rows, (long)g.P, q.Pq, q.Pqc, pl->slab_nranks, q.nch, pl->slab_rank, 0, q.nch);
     }
     CK_LAUNCH(); pl->launches++;
 }
@@ -735,7 +740,7 @@ static void slab2_pushB(hipgp_plan* pl, int mode, int chunk, cudaStream_t s) {
     auto k = slab_push_back_kernel<T>;
     const int c0 = chunk < 0 ? 0 : chunk, c1 = chunk < 0 ? q.nch : chunk + 1;
     PROF_BEGIN(pl, 3, s);
-    HIPGP_LAUNCH(k, dim3(148 * 8), dim3(256), 0, s, (const cplx<T>*)pl->slabR1.p, peer_table(pl, true), q.rows, (long)g.P, q.Pq, q.Pqc, pl->slab_nranks, q.nch, pl->slab_rank, c0, c1);
+    HIPGP_LAUNCH(k, dim3(push_grid(q.exch, 16 / (int)sizeof(cplx<T>))), dim3(256), 0, s, (const cplx<T>*)pl->slabR1.p, peer_table(pl, true), q.rows, (long)g.P, q.Pq, q.Pqc, pl->slab_nranks, q.nch, pl->slab_rank, c0, c1);
     PROF_END(pl, s);
     CK_LAUNCH(); pl->launches++;
 }

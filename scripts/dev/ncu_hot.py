@@ -3,7 +3,8 @@ rep=sys.argv[1]; reason=sys.argv[2]; topn=int(sys.argv[3]) if len(sys.argv)>3 el
 src=subprocess.run(['ncu','-i',rep,'--page','source','--csv'],capture_output=True,text=True).stdout
 rows=list(csv.reader(src.splitlines()))
 starts=[i for i,r in enumerate(rows) if r and r[0]=='Kernel Name']
-seg=rows[starts[0]:starts[1] if len(starts)>1 else None]
+KS=int(sys.argv[4]) if len(sys.argv)>4 else 0
+seg=rows[starts[KS]:starts[KS+1] if len(starts)>KS+1 else None]
 hdr=seg[1]
 iS=hdr.index('Source'); iE=hdr.index('Instructions Executed'); iSamp=hdr.index('# Samples'); iR=hdr.index(reason)
 recs=[(int(r[iR]),idx,r[iS].strip(),int(r[iE]),int(r[iSamp])) for idx,r in enumerate(seg[2:]) if len(r)>iR and r[iR].isdigit()]
