@@ -394,6 +394,12 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # several ranks on one node: keep this rank's pinned buffers on the GPU's NUMA node (N = 1 keeps every core for the CPU leg)
+    numa = None
+    if world > 1:
+        from hipgp_b200.hostmem import bind_to_gpu_numa_node
+        numa = bind_to_gpu_numa_node(local)
+
     dtype = torch.float32
     B = B_PER_GPU
     M = GRID[0] * GRID[1]
@@ -553,7 +559,8 @@ def run_gpu(args):
             "e2e": {"value": e2e_val, "unit": "GB/s", "h2d_bytes_per_step": int(b_host.numel() * 4) * world,
                     "d2h_bytes_per_step": int(x_host.numel() * 4) * world, "ms_per_step": ms_e2e / args.steps,
                     "how": "hipgp_pcg_host_pipelined: groups of %d / %d / %d right-hand sides, H2D / D2H of neighbouring groups on two copy streams behind the solves" % (E2E_GROUP, B_PER_GPU - 2 * E2E_GROUP, E2E_GROUP),
-                    "matches_device_path_bitwise": e2e_matches, "frac_of_value": e2e_val / value if value else None},
+                    "matches_device_path_bitwise": e2e_matches, "frac_of_value": e2e_val / value if value else None,
+                    "host_numa": numa},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",

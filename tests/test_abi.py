@@ -131,3 +131,16 @@ def test_new_entry_points_validate_before_touching_the_device():
     assert "null block index" in lib.hipgp_last_error().decode()
     assert lib.hipgp_block_lam(5, buf, buf, idx, 1, 8, 2, 4, 1.0, 1.0, buf, None) != 0 and "dtype" in lib.hipgp_last_error().decode()
     assert lib.hipgp_block_diag_multiply(0, buf, buf, idx, 0, 8, 2, 4, buf, None) == 0          # empty batch: no-op
+
+
+def test_numa_binding_helper_is_harmless_without_a_gpu():
+    """hostmem.bind_to_gpu_numa_node is an optimisation: it parses sysfs cpu lists and must never raise or change the
+    affinity when the device's node is unknown (no GPU here)."""
+    import os
+    from hipgp_b200 import hostmem
+    assert hostmem._parse_cpulist("0-3,8,10-11") == {0, 1, 2, 3, 8, 10, 11}
+    assert hostmem._parse_cpulist("") == set()
+    before = os.sched_getaffinity(0)
+    info = hostmem.bind_to_gpu_numa_node(0)
+    assert info["bound"] is False
+    assert os.sched_getaffinity(0) == before
