@@ -649,7 +649,9 @@ __global__ void slab_push_pack_kernel(const cplx<T>* __restrict__ W, PeerPtrs ds
             const long i = i0 + k * step;
             v[k] = Unit16{0ull, 0ull}; out[k] = nullptr;
             if (i < total) {
-                const long u = i % upc, r = (i / upc) % rows, q = (i / (upc * rows)) % nranks, ch = i / (upc * rows * nranks);
+                // destination varies fastest after the unit-in-row index and is rotated by the sender's rank: at any moment every
+                // rank writes to every peer, and no peer is everybody's target at once
+                const long u = i % upc, q = ((i / upc) % nranks + me) % nranks, r = (i / (upc * nranks)) % rows, ch = i / (upc * rows * nranks);
                 const long c = q * Pq + ch * Pqc + u * PER;
                 if (c + PER <= P) v[k] = *reinterpret_cast<const Unit16*>(W + r * P + c);      // P and c are even: no unit straddles the pitch
                 out[k] = reinterpret_cast<Unit16*>(reinterpret_cast<cplx<T>*>(dst.p[q]) + (((long)ch * nranks + me) * rows + r) * Pqc + u * PER);
@@ -677,7 +679,7 @@ __global__ void slab_push_back_kernel(const cplx<T>* __restrict__ buf, PeerPtrs 
             const long i = i0 + k * step;
             out[k] = nullptr;
             if (i < total) {
-                const long u = i % upc, r = (i / upc) % rows, q = (i / blk) % nranks, ch = ch0 + i / (blk * nranks);
+                const long u = i % upc, q = ((i / upc) % nranks + me) % nranks, r = (i / (upc * nranks)) % rows, ch = ch0 + i / (blk * nranks);
                 const long c = (long)me * Pq + ch * Pqc + u * PER;
                 if (c + PER <= P) {
                     v[k] = reinterpret_cast<const Unit16*>(buf)[((long)ch * nranks + q) * blk + r * upc + u];
