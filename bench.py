@@ -28,6 +28,7 @@ step) and `slab_cfg5` (512^3 grid sharded over the ranks, two all-to-all transpo
 """
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
@@ -204,6 +205,92 @@ def run_reference(args):
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+# The other BASELINE.json configurations, CPU (the reference itself, bounded samples) next to the GPU path at the full batch:
+# (tag, grid, dtype, GPU right-hand sides, CPU sample, with R^T) -- op = PCG(20) + preconditioner [+ R^T = compute_kn, hipgp.py:139-146]
+OTHER_CONFIGS = [("cfg1", (100, 100), "f32", 16, 16, False), ("cfg1", (100, 100), "f64", 16, 16, False),
+                 ("cfg2", (1000, 1000), "f64", 16, 2, False),
+                 ("cfg3", (300, 300), "f32", 200, 20, True),
+                 ("cfg4", (128, 128, 64), "f32", 200, 1, True)]
+
+
+def _other_grids(dims, dtype, device=None):
+    import torch
+    g = [torch.linspace(0, 1, m, dtype=dtype, device=device) for m in dims]
+    return g, 2.5 / (dims[0] - 1)
+
+
+def run_reference_other(args):
+    """`--impl reference --other-configs`: one JSON list, the reference's ToeplitzTensor._solve (+ _matmul_by_RT) per config"""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    import torch
+    cores = host_threads()
+    torch.set_num_threads(cores)
+    from oracle import ref_shim
+    kind = "reference" if ref_shim.reference_root() is not None else "port"
+    out = []
+    for tag, dims, dn, _, Bc, with_rt in OTHER_CONFIGS:
+        dtype = torch.float32 if dn == "f32" else torch.float64
+        grids, ell = _other_grids(dims, dtype)
+        torch.manual_seed(7)
+        v = torch.randn(Bc, math.prod(dims), dtype=dtype)
+        t0 = time.perf_counter()
+        if kind == "reference":
+            ref_shim.import_reference()
+            from ziggy.misc.toeplitz_tensor import ToeplitzTensor
+            from ziggy.kernels import Matern
+            kern = Matern(nu=2.5, length_scale=ell)
+            K = ToeplitzTensor(xgrids=grids, kernel=lambda x, y: kern.forward(x, y, params=(SIG2, ell)), batch_shape=None, jitter_val=JITTER)
+            solve = lambda u: K._solve(u, do_precond=True, maxiter=MAXITER, tol=TOL)
+            rt = lambda d: K._matmul_by_RT(d)
+        else:
+            from oracle import ziggy_oracle as zo
+            K = zo.OracleToeplitz(grids, lambda x, y: zo.matern(x, y, SIG2, ell, 2.5), jitter_val=JITTER)
+            solve = lambda u: K.solve(u, do_precond=True, maxiter=MAXITER, tol=TOL)
+            rt = lambda d: K.matmul_RT(d)
+        t_setup = time.perf_counter() - t0
+        solve(v[:1])                                   # untimed first call
+        t0 = time.perf_counter()
+        d = solve(v)
+        if with_rt:
+            rt(d)
+        t = time.perf_counter() - t0
+        out.append({"config": tag, "grid": list(dims), "dtype": dn, "op": "PCG(20) + preconditioner" + (" + R^T (compute_kn)" if with_rt else ""),
+                    "sample_rhs": Bc, "s": t, "s_per_rhs": t / Bc, "setup_s": t_setup, "cores": cores, "kind": kind})
+    print(json.dumps(out), flush=True)
+
+
+def other_configs_gpu(dev):
+    """the same operations through the C ABI at the configuration's full batch (device-resident, CUDA events)"""
+    import torch
+    from hipgp_b200.plan import Plan
+    from hipgp_b200 import _lib as L, kernels as hk
+    out = {}
+    for tag, dims, dn, Bg, _, with_rt in OTHER_CONFIGS:
+        dtype = torch.float32 if dn == "f32" else torch.float64
+        grids, ell = _other_grids(dims, dtype, dev)
+        plan = Plan(list(dims), dtype, dev)
+        plan.set_first_row(hk.first_row(grids, hk.Matern(nu=2.5, dtype=dtype), (SIG2, ell), jitter=JITTER))
+        gen = torch.Generator(device=dev); gen.manual_seed(7)
+        v = torch.randn(Bg, math.prod(dims), dtype=dtype, device=dev, generator=gen)
+
+        def op():
+            d = plan.pcg(v, maxiter=MAXITER, tol=TOL, precond=True)
+            if with_rt:
+                plan.matvec(L.MV_RT, d)
+        op(); torch.cuda.synchronize()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            op()
+        e1.record(); torch.cuda.synchronize()
+        t = e0.elapsed_time(e1) / 3e3
+        out[(tag, dn)] = {"rhs": Bg, "s": t, "s_per_rhs": t / Bg}
+        del plan, v
+        torch.cuda.empty_cache()
+    return out
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -535,6 +622,21 @@ def run_gpu(args):
                 cpu = json.loads(r.stdout.strip().splitlines()[-1])["cpu_baseline"]
             except Exception as e:
                 cpu = {"error": repr(e)[:200]}
+        # the other configurations: reference on the host cores (bounded samples) next to the CUDA path at the full batch
+        others = None
+        if world == 1 and not args.no_cpu and not args.quick:
+            try:
+                g_o = other_configs_gpu(dev)
+                r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--other-configs"],
+                                   capture_output=True, text=True, timeout=600)
+                others = json.loads(r.stdout.strip().splitlines()[-1])
+                for o in others:
+                    g = g_o[(o["config"], o["dtype"])]
+                    o["cpu"] = {k: o.pop(k) for k in ("sample_rhs", "s", "s_per_rhs", "setup_s", "cores", "kind")}
+                    o["gpu"] = g
+                    o["speedup_per_rhs"] = o["cpu"]["s_per_rhs"] / g["s_per_rhs"]
+            except Exception as e:
+                others = {"error": repr(e)[:200]}
         # per-pass streaming bytes (what each pass moves when its input / output do not stay on chip),
         # averaged over the launches of one PCG iteration, against the same HBM peak
         Mv = 4 * GRID[0] * GRID[1] * B                                   # one vector, all right-hand sides
@@ -571,6 +673,7 @@ def run_gpu(args):
                          "pcg_iteration_contract_frac": it_frac,
                          "note": "achieved = contract bytes w(2MB+E_h) of one matvec / (rows_fwd + cols_pass + rows_inv average launch durations), CUDA events around every launch in a second pass of the same steps; the contract figure assumes the half-spectrum never leaves the chip -- per_kernel_streaming gives each pass against the bytes it actually has to stream; pcg_iteration_contract_frac = 20 x w(13MB+2E_h) / step time / peak; the passes are bound by FP32 issue (2 cycles per packed op) + shared-memory exchange, not by HBM (DESIGN.md 4a, profiles/README.md r2)"},
             "cpu_baseline": cpu,
+            "cpu_baselines_other_configs": others,
         }
         line.update(extra)
 
@@ -615,11 +718,15 @@ def main():
     ap.add_argument("--quick", action="store_true", help="skip the companion measurements and the multi-GPU sections")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline sample")
     ap.add_argument("--no-multi", action="store_true", help="skip the svi_cfg3 / slab_cfg5 sections")
+    ap.add_argument("--other-configs", action="store_true", help="with --impl reference: time the other BASELINE configurations instead")
     ap.add_argument("--section-timeout", type=int, default=420, help="watchdog for the multi-GPU sections (seconds)")
     ap.add_argument("--cpu-sample-b", type=int, default=CPU_SAMPLE_B, help="right-hand sides per CPU step (bounded sample)")
     args = ap.parse_args()
     if args.impl == "reference":
-        run_reference(args)
+        if args.other_configs:
+            run_reference_other(args)
+        else:
+            run_reference(args)
         return
     import torch
     if not torch.cuda.is_available():
