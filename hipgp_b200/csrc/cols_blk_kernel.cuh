@@ -383,15 +383,20 @@ __global__ void __launch_bounds__(NT, MINB) cols_blk_kernel(const HIPGP_GRID_CON
 #pragma unroll
                 for (int r = 0; r < R0; ++r) v[r] = base[r * LEG0];
                 blk_twiddle_mul<R0, S0, TWS, true, TWCH>(v, tw0, j);
-                lbfly<R0, true, T>(v);
-                if (ok) {
-                    // (one 64-bit base per thread, 32-bit element offsets for the R0 / 2 row blocks: an embedded line spans < 2^31 elements)
-                    cplx<T>* gp = out + (size_t)((unsigned)j * (unsigned)P.pitch + (unsigned)(lane * LPT));
-                    const unsigned rs = (unsigned)S0 * (unsigned)P.pitch;
-                    if (out_lo) {
+                // (one 64-bit base per thread, 32-bit element offsets for the R0 / 2 row blocks: an embedded line spans < 2^31 elements)
+                cplx<T>* gp = out + (size_t)((unsigned)j * (unsigned)P.pitch + (unsigned)(lane * LPT));
+                const unsigned rs = (unsigned)S0 * (unsigned)P.pitch;
+                if (out_lo) {
+                    // the cropped result keeps at most the lower half of the line: the butterfly sits INSIDE the branch so that
+                    // the arithmetic feeding only outputs R0/2 .. R0-1 is dead code here
+                    lbfly<R0, true, T>(v);
+                    if (ok) {
 #pragma unroll
                         for (int r = 0; r < R0 / 2; ++r) if (j + r * S0 < n_out) lane_to_global(gp + (size_t)((unsigned)r * rs), v[r]);
-                    } else {
+                    }
+                } else {
+                    lbfly<R0, true, T>(v);
+                    if (ok) {
 #pragma unroll
                         for (int r = 0; r < R0; ++r) if (j + r * S0 < n_out) lane_to_global(gp + (size_t)((unsigned)r * rs), v[r]);
                     }
