@@ -240,3 +240,22 @@ def test_block_family(dname, golden_dir):
     assert relerr(kn2.numpy(), g["kn"]) < tol and relerr(qm2.numpy(), g["qm"]) < tol * 10
     assert abs(float(elbo) - float(g["elbo"])) <= tol * 10 * abs(float(g["elbo"]))
     assert relerr(g1.numpy(), g["g1"]) < tol * 10 and relerr(g2.numpy(), g["g2"]) < tol * 10
+
+
+def test_doubly_integrated_table_recomputation_agrees_with_the_reference_tables(golden_dir):
+    """`hipgp_b200.kernels.doubly_integrated_diag` evaluates the double line integral as ONE 1-D quadrature (to 1e-10); the
+    reference's 50-entry tables (kernels.py:266-287: 2-D quadrature with epsabs = 0.149) agree with it to THEIR accuracy --
+    smooth kernels to 1e-5, the kinked Matern-1/2 to 5e-4.  Callers that need the reference's table bit for bit pass it in
+    (`KernelDoublyDiagInterpolator(table=...)`, as every parity test does)."""
+    import torch
+    from hipgp_b200 import kernels as hk
+    g = np.load(os.path.join(golden_dir, "kernels_f64.npz"))
+    make = {"sqexp": lambda: hk.SqExp(dtype=torch.float64), "matern12": lambda: hk.Matern(nu=0.5, dtype=torch.float64),
+            "matern32": lambda: hk.Matern(nu=1.5, dtype=torch.float64), "matern52": lambda: hk.Matern(nu=2.5, dtype=torch.float64)}
+    bound = {"sqexp": 1e-6, "matern52": 1e-5, "matern32": 1e-4, "matern12": 5e-4}
+    for kname, mk in make.items():
+        dgrid, _, knn = g["table_%s" % kname]
+        mine = hk.doubly_integrated_diag(np.column_stack([dgrid, np.zeros(len(dgrid))]), mk()._host_eval)
+        assert mine[0] == 0.0 and knn[0] == 0.0
+        rel = np.max(np.abs(mine[1:] - knn[1:]) / np.abs(knn[1:]))
+        assert rel < bound[kname], (kname, rel)
