@@ -10,9 +10,11 @@ metric  : Toeplitz matvec GB/s = algorithmic bytes of the step's 41 structured m
           w (2 M B + E_h) each (SURVEY.md 8d contract figure, E_h = 1998*1000), divided by the step time.
           `pcg_solve_s` (the other half of BASELINE.json's metric) is reported beside it.
 value   : inputs resident in HBM (plan.pcg on device tensors).
-e2e     : the same step through the C-ABI host entry point (hipgp_pcg_host_pipelined): pinned host b -> H2D -> solve
-          -> D2H x, every step; the right-hand sides travel as a small first group, the bulk, and a small last
-          group, so that all copies but the first upload and the last download hide behind a solve.
+e2e     : the same steps through the C-ABI host entry points with HOST buffers: every step uploads its right-hand sides
+          from pinned memory and downloads its solution inside the timed region.  The steps are a stream of batches through
+          hipgp_pcg_host_submit / _wait with two in flight, so the copies of neighbouring steps run under the current solve.
+          `one_synchronous_call_per_step` is the same through ONE blocking call per step (hipgp_pcg_host_pipelined: the
+          right-hand sides travel as a small first group, the bulk, and a small last group).
 roofline: per-kernel-class CUDA-event timing inside this script (a second pass of the same steps with the
           library's event hooks on); achieved = matvec algorithmic bytes / (sum of the three pass kernels'
           average durations); the dominant kernel and its share of the matvec are named.
@@ -42,7 +44,7 @@ GRID = (1000, 1000)
 ELL, SIG2, JITTER = 0.01, 1.0, 1e-3
 MAXITER, TOL = 20, 1e-8
 B_PER_GPU = 64
-E2E_GROUP = 8
+E2E_GROUP = int(os.environ.get("HIPGP_E2E_GROUP", "8"))     # right-hand sides in the first and the last group of the pipelined host solve
 CPU_SAMPLE_B = 16
 N_MATVEC = 2 * MAXITER + 1
 METRIC = "toeplitz_matvec_GBps_in_pcg_1e6grid"
@@ -529,11 +531,39 @@ def run_gpu(args):
     launches = plan.launch_count() - l0
     m1 = sampler.mark() if sampler else 0
 
+    # e2e (headline): a stream of `steps` batches through the asynchronous host entry points, two in flight -- every step's
+    # right-hand sides are uploaded from pinned memory and its solution downloaded inside the timed region; the upload of step
+    # k+1 and the download of step k-1 travel under the solve of step k.  The end event is recorded after the host has waited
+    # for the last download.
+    x_hosts = [x_host, torch.empty_like(b_host).pin_memory()]
+
+    def stream_e2e(steps):
+        plan.pcg_host_submit(b_host, x_hosts[0], 0, maxiter=MAXITER, tol=TOL, precond=True)
+        for k in range(1, steps):
+            plan.pcg_host_submit(b_host, x_hosts[k % 2], k % 2, maxiter=MAXITER, tol=TOL, precond=True)
+            plan.pcg_host_wait((k - 1) % 2)
+        plan.pcg_host_wait((steps - 1) % 2)
+
+    stream_e2e(2)
+    barrier()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    stream_e2e(args.steps)
+    e1.record()
+    barrier()
+    ms_t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
+    ms_e2e = float(ms_t.item())
+    xd = step_dev()
+    xd_host = xd.cpu()
+    e2e_matches = bool(torch.equal(xd_host, x_hosts[0])) and bool(torch.equal(xd_host, x_hosts[1]))
+    # one synchronous call per step (hipgp_pcg_host_pipelined: the copies hide inside ONE step, groups of 8 / 48 / 8)
     for _ in range(2):
         step_e2e()
-    ms_e2e = timed(step_e2e, args.steps)
-    xd = step_dev()
-    e2e_matches = bool(torch.equal(xd.cpu(), x_host))       # the pipelined host path returns the device path's solution
+    ms_e2e_sync = timed(step_e2e, max(2, args.steps // 4))
+    ms_e2e_sync_step = ms_e2e_sync / max(2, args.steps // 4)
+    e2e_matches = e2e_matches and bool(torch.equal(xd_host, x_host))
 
     # roofline pass: same steps with per-kernel-class events on
     plan.profile(True)
@@ -660,8 +690,11 @@ def run_gpu(args):
             "embedding": list(plan.embedding()[0]),
             "e2e": {"value": e2e_val, "unit": "GB/s", "h2d_bytes_per_step": int(b_host.numel() * 4) * world,
                     "d2h_bytes_per_step": int(x_host.numel() * 4) * world, "ms_per_step": ms_e2e / args.steps,
-                    "how": "hipgp_pcg_host_pipelined: groups of %d / %d / %d right-hand sides, H2D / D2H of neighbouring groups on two copy streams behind the solves" % (E2E_GROUP, B_PER_GPU - 2 * E2E_GROUP, E2E_GROUP),
+                    "how": "hipgp_pcg_host_submit / _wait, two batches in flight: every step uploads its right-hand sides from pinned host memory "
+                           "and downloads its solution; the copies of neighbouring steps run on two copy streams under the current solve",
                     "matches_device_path_bitwise": e2e_matches, "frac_of_value": e2e_val / value if value else None,
+                    "one_synchronous_call_per_step": {"ms_per_step": ms_e2e_sync_step, "value": alg_step / (ms_e2e_sync_step / 1e3) / 1e9,
+                                                      "how": "hipgp_pcg_host_pipelined: groups of %d / %d / %d right-hand sides inside one call" % (E2E_GROUP, B_PER_GPU - 2 * E2E_GROUP, E2E_GROUP)},
                     "host_numa": numa},
             "gpu_launches": int(launches),
             "clocks": clocks,

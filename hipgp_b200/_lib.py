@@ -37,6 +37,8 @@ SIGNATURES = {
     "hipgp_pcg_step": (_i, [_vp, _i, _pi, _pi, _pd, _vp]),
     "hipgp_pcg_host": (_i, [_vp, _vp, _vp, _i64, _i, _d, _i, _pi, _pi, _pd, _vp]),
     "hipgp_pcg_host_pipelined": (_i, [_vp, _vp, _vp, _i64, _i, _d, _i, _i64, _pi, _vp]),
+    "hipgp_pcg_host_submit": (_i, [_vp, _vp, _vp, _i64, _i, _d, _i, _i, _vp]),
+    "hipgp_pcg_host_wait": (_i, [_vp, _i, _pi]),
     "hipgp_compute_kn": (_i, [_vp, _vp, _vp, _i64, _i, _d, _pi, _vp]),
     "hipgp_vec_dot": (_i, [_i, _vp, _vp, _vp, _i64, _i64, _vp]),
     "hipgp_vec_xr_update": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp]),

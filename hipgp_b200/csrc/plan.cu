@@ -843,8 +843,9 @@ static void pcg_begin(hipgp_plan* pl, const void* b, void* x, long B, double tol
     // x = 0 ; r = b - A(0) = b   (cg.py:58-59; the reference spends a matvec on the zero vector)
     CK(cudaMemsetAsync(x, 0, sizeof(T) * (size_t)(B * M), s));
     CK(cudaMemcpyAsync(r, b, sizeof(T) * (size_t)(B * M), cudaMemcpyDeviceToDevice, s));
-    const int init_flags[4] = {0, 0, 1, 0};
-    CK(cudaMemcpyAsync(st.flags, init_flags, sizeof(init_flags), cudaMemcpyHostToDevice, s));
+    // flags = {0, 0, 1, 0} without a pageable host copy (which would synchronise the stream): clear, then one byte
+    CK(cudaMemsetAsync(st.flags, 0, sizeof(int) * 4, s));
+    CK(cudaMemsetAsync(reinterpret_cast<char*>(st.flags) + 2 * sizeof(int), 1, 1, s));
     RowsFusion ff, fi;
     if (precond) {   // z = P r ; zr = z.r
         ff.mode = RF_PLAIN; ff.in = r; fi.mode = RI_DOT; fi.dot_kind = DOT_ZR; fi.out = z; fi.v0 = r;
@@ -994,9 +995,15 @@ int hipgp_plan_destroy(hipgp_plan* pl) {
     for (DevBuf* b : {&pl->specK, &pl->specCinv, &pl->specW, &pl->Dm, &pl->Dinv, &pl->Dsqrt, &pl->colK, &pl->colG, &pl->colS,
                       &pl->tmpA, &pl->tmpB, &pl->costab, &pl->counts, &pl->W1, &pl->W2, &pl->vr, &pl->vp, &pl->vz, &pl->vAp,
                       &pl->partial, &pl->scal, &pl->cnt, &pl->flags, &pl->stage_in, &pl->stage_out, &pl->corrU, &pl->corrV, &pl->corrS,
-                      &pl->corrLag, &pl->gradA, &pl->slabSpecK, &pl->slabSpecCinv, &pl->slabR1, &pl->slabR2, &pl->costabs[0], &pl->costabs[1], &pl->costabs[2]})
+                      &pl->corrLag, &pl->gradA, &pl->slabSpecK, &pl->slabSpecCinv, &pl->slabR1, &pl->slabR2, &pl->slot_in[0], &pl->slot_in[1], &pl->slot_out[0], &pl->slot_out[1], &pl->costabs[0], &pl->costabs[1], &pl->costabs[2]})
         b->release(t);
     slab_peer_close(pl);
+#ifndef HIPGP_EMU
+    for (auto& se : pl->slot_ev) for (auto& e : se) if (e) cudaEventDestroy(e);
+    if (pl->slot_flags) cudaFreeHost(pl->slot_flags);
+#else
+    delete[] pl->slot_flags;
+#endif
     if (pl->pinned) cudaFreeHost(pl->pinned);
 #ifndef HIPGP_EMU
     for (auto& cs : pl->copy_streams) if (cs) cudaStreamDestroy(cs);
@@ -1189,6 +1196,68 @@ int hipgp_pcg_host_pipelined(hipgp_plan* pl, const void* b_host, void* x_host, i
     cudaEventDestroy(start);
 #endif
     if (iters_out) *iters_out = iters_max;
+    API_END
+}
+
+// Asynchronous host-buffer solves for a STREAM of batches: submit returns as soon as the work is queued -- upload on the plan's
+// H2D stream, the whole solve (begin + maxiter iterations; kernels of a converged solve exit at their first instruction, so the
+// reference's stopping rule holds without the host looking) on the caller's stream, download on the D2H stream -- and wait blocks
+// until the slot's result is in x_host.  With two slots in flight the upload of batch k+1 and the download of batch k-1 run under
+// the solve of batch k.  Solves of one plan are ordered on the caller's stream (they share the solver's work vectors).
+int hipgp_pcg_host_submit(hipgp_plan* pl, const void* b_host, void* x_host, int64_t B, int maxiter, double tol, int precond, int slot,
+                          void* stream) {
+    API_BEGIN
+    set_device(pl);
+    if (slot < 0 || slot > 1) throw Error("slot must be 0 or 1");
+    if (B <= 0) throw Error("hipgp_pcg_host_submit needs at least one right-hand side");
+    if (!b_host || !x_host) throw Error("null vector pointer");
+    if (maxiter < 0) throw Error("negative maxiter");
+    cudaStream_t s = (cudaStream_t)stream;
+#ifndef HIPGP_EMU
+    if (!pl->copy_streams[0]) {
+        CK(cudaStreamCreateWithFlags(&pl->copy_streams[0], cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&pl->copy_streams[1], cudaStreamNonBlocking));
+    }
+    for (int e = 0; e < 3; ++e) if (!pl->slot_ev[slot][e]) CK(cudaEventCreateWithFlags(&pl->slot_ev[slot][e], cudaEventDisableTiming));
+    if (!pl->slot_flags) CK(cudaMallocHost((void**)&pl->slot_flags, sizeof(int) * 8));
+    if (pl->slot_busy[slot]) { CK(cudaEventSynchronize(pl->slot_ev[slot][2])); pl->slot_busy[slot] = false; }   // the slot's previous batch
+    cudaStream_t cin = pl->copy_streams[0], cout = pl->copy_streams[1];
+#else
+    if (!pl->slot_flags) pl->slot_flags = new int[8];
+    cudaStream_t cin = s, cout = s;
+#endif
+    const size_t n = (size_t)B * pl->M * elem_size(pl);
+    pl->slot_in[slot].ensure(n, &pl->dev_bytes); pl->slot_out[slot].ensure(n, &pl->dev_bytes);
+    CK(cudaMemcpyAsync(pl->slot_in[slot].p, b_host, n, cudaMemcpyHostToDevice, cin));
+#ifndef HIPGP_EMU
+    CK(cudaEventRecord(pl->slot_ev[slot][0], cin));
+    CK(cudaStreamWaitEvent(s, pl->slot_ev[slot][0], 0));
+#endif
+    if (pl->dtype == HIPGP_F32) { pcg_begin<float>(pl, pl->slot_in[slot].p, pl->slot_out[slot].p, (long)B, tol, precond != 0, s); pcg_iterate<float>(pl, maxiter, s); }
+    else { pcg_begin<double>(pl, pl->slot_in[slot].p, pl->slot_out[slot].p, (long)B, tol, precond != 0, s); pcg_iterate<double>(pl, maxiter, s); }
+    pl->run_active = false;
+    CK(cudaMemcpyAsync(pl->slot_flags + 4 * slot, pl->flags.p, sizeof(int) * 4, cudaMemcpyDeviceToHost, s));
+#ifndef HIPGP_EMU
+    CK(cudaEventRecord(pl->slot_ev[slot][1], s));
+    CK(cudaStreamWaitEvent(cout, pl->slot_ev[slot][1], 0));
+#endif
+    CK(cudaMemcpyAsync(x_host, pl->slot_out[slot].p, n, cudaMemcpyDeviceToHost, cout));
+#ifndef HIPGP_EMU
+    CK(cudaEventRecord(pl->slot_ev[slot][2], cout));
+#endif
+    pl->slot_busy[slot] = true;
+    API_END
+}
+int hipgp_pcg_host_wait(hipgp_plan* pl, int slot, int* iters_out) {
+    API_BEGIN
+    set_device(pl);
+    if (slot < 0 || slot > 1) throw Error("slot must be 0 or 1");
+    if (!pl->slot_busy[slot]) throw Error("hipgp_pcg_host_wait: nothing was submitted on this slot");
+#ifndef HIPGP_EMU
+    CK(cudaEventSynchronize(pl->slot_ev[slot][2]));
+#endif
+    pl->slot_busy[slot] = false;
+    if (iters_out) *iters_out = pl->slot_flags[4 * slot + 1];
     API_END
 }
 

@@ -281,6 +281,11 @@ struct hipgp_plan {
     DevBuf corrU, corrV, corrS, corrLag;   // Toeplitz-column quadratic form (corr_api.inl): spectra of a chunk of pairs, their sum, lags
     void* pinned = nullptr;                // host flags mirror
     cudaStream_t copy_streams[2] = {nullptr, nullptr};   // H2D / D2H streams of hipgp_pcg_host_pipelined
+    // asynchronous host solves (hipgp_pcg_host_submit / _wait): two slots, each with its own device staging and events
+    DevBuf slot_in[2], slot_out[2];
+    cudaEvent_t slot_ev[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};     // upload done, solved, download done
+    bool slot_busy[2] = {false, false};
+    int* slot_flags = nullptr;             // pinned: 4 ints per slot
     long pcg_B = 0;
     // peer-memory exchange (bins layout): R1 receives the way there, R2 the way back; peerR*[q] = rank q's buffers as mapped here
     DevBuf slabR1, slabR2;

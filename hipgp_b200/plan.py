@@ -182,6 +182,23 @@ class Plan:
                                                        C.byref(iters), C.byref(ncb), None, _stream_ptr(self.device)))
         return x_host, iters.value
 
+    def pcg_host_submit(self, b_host, x_host, slot, maxiter=20, tol=1e-10, precond=True):
+        """Queue one host-buffer solve on `slot` (0 or 1) and return at once (hipgp_pcg_host_submit): with two slots in flight the
+        copies of neighbouring batches hide under the current solve.  Both buffers must be pinned and stay untouched until
+        `pcg_host_wait(slot)`."""
+        assert not b_host.is_cuda and not x_host.is_cuda and b_host.is_contiguous() and x_host.is_contiguous()
+        assert b_host.is_pinned() and x_host.is_pinned(), "asynchronous host solves need pinned buffers"
+        with torch.cuda.device(self.device):
+            L.check(self.lib, self.lib.hipgp_pcg_host_submit(self._h, C.c_void_p(b_host.data_ptr()), C.c_void_p(x_host.data_ptr()),
+                                                              b_host.shape[0], int(maxiter), float(tol), 1 if precond else 0, int(slot),
+                                                              _stream_ptr(self.device)))
+
+    def pcg_host_wait(self, slot):
+        """Block until the solve submitted on `slot` has delivered x_host; returns its iteration count."""
+        iters = C.c_int()
+        L.check(self.lib, self.lib.hipgp_pcg_host_wait(self._h, int(slot), C.byref(iters)))
+        return iters.value
+
     def device_bytes(self):
         n = C.c_size_t()
         L.check(self.lib, self.lib.hipgp_plan_device_bytes(self._h, C.byref(n)))

@@ -65,6 +65,15 @@ int hipgp_matvec(hipgp_plan* plan, int mode, const void* in_dev, void* out_dev, 
 /* same, host buffers in and out (H2D + D2H inside the call) */
 int hipgp_matvec_host(hipgp_plan* plan, int mode, const void* in_host, void* out_host, int64_t B, void* stream);
 
+/* Asynchronous variant for a stream of batches (two slots): submit queues upload (plan's H2D stream) -> whole solve (caller's
+ * stream; the stopping rule of cg.py:70 lives on the device, so nothing polls) -> download (plan's D2H stream) and returns;
+ * wait blocks until x_host of that slot is complete and reports the iteration count.  With both slots in flight the copies of
+ * neighbouring batches run under the current solve.  Re-submitting a busy slot waits for it first.  Host buffers must be pinned
+ * and must stay untouched between submit and wait. */
+int hipgp_pcg_host_submit(hipgp_plan* plan, const void* b_host, void* x_host, int64_t B, int maxiter, double tol, int precond,
+                          int slot, void* stream);
+int hipgp_pcg_host_wait(hipgp_plan* plan, int slot, int* iters_out);
+
 /* ---- PCG: replaces conj_grad2/conj_grad driven by ToeplitzTensor._solve / gram_solve
  *      (ziggy/misc/cg.py:5-80, toeplitz_tensor.py:54-68, toeplitz_expanded.py:17-58).
  * b, x: (B, M).  precond != 0 uses the HIP-GP preconditioner (upper-left block of C^-1).

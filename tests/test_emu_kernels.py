@@ -299,3 +299,24 @@ def test_slab_stages_equal_the_undecomposed_matvec(lib, dims, nranks, dname, bin
     sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scripts", "dev"))
     import emu_slab
     assert emu_slab.run(dims, nranks, np.float64 if dname == "f64" else np.float32, bins, chunks, peer)
+
+
+def test_async_host_solve_entry_points(lib):
+    """hipgp_pcg_host_submit / _wait (two slots) return what hipgp_pcg returns, with its iteration count."""
+    g = np.load(os.path.join(GOLD, "toeplitz_1d_m100_sqexp_f64.npz"), allow_pickle=True)
+    plan = make_plan(lib, g, np.float64)
+    v = np.ascontiguousarray(g["v"]); B, M = v.shape
+    maxiter, tol = g["solve_pcg_args"]
+    want = np.zeros((B, M)); it = C.c_int(); ncb = C.c_int()
+    assert lib.hipgp_pcg(plan, ptr(v), ptr(want), B, int(maxiter), float(tol), 1, C.byref(it), C.byref(ncb), None, L.ITER_CB(0), None, None) == 0
+    xs = [np.zeros((B, M)), np.zeros((B, M))]
+    for slot in (0, 1):
+        assert lib.hipgp_pcg_host_submit(plan, ptr(v), ptr(xs[slot]), B, int(maxiter), float(tol), 1, slot, None) == 0, lib.hipgp_last_error()
+    for slot in (0, 1):
+        n = C.c_int()
+        assert lib.hipgp_pcg_host_wait(plan, slot, C.byref(n)) == 0, lib.hipgp_last_error()
+        assert n.value == it.value
+        assert np.array_equal(xs[slot], want)
+    assert lib.hipgp_pcg_host_wait(plan, 0, None) != 0          # nothing pending
+    assert lib.hipgp_pcg_host_submit(plan, ptr(v), ptr(xs[0]), B, int(maxiter), float(tol), 1, 2, None) != 0   # bad slot
+    lib.hipgp_plan_destroy(plan)

@@ -156,3 +156,34 @@ def test_more_than_2_31_elements_in_a_batch():
     assert abs(lhs - rhs) / abs(rhs) < 1e-4
     del kn, v, plan, one, Kv
     _free()
+
+
+@pytest.mark.gpu
+def test_async_host_solves_equal_the_device_path():
+    """hipgp_pcg_host_submit / _wait: a stream of batches with two in flight returns, for every batch, exactly what the
+    device-resident solve returns (bitwise), reports the iteration count, and keeps slot order under re-submission."""
+    import torch
+    from hipgp_b200.plan import Plan
+    from hipgp_b200 import kernels as hk
+    dev = torch.device("cuda:0")
+    dims = (96, 80)
+    dtype = torch.float32
+    xg = [torch.linspace(0, 1 + d, m, dtype=dtype, device=dev) for d, m in enumerate(dims)]
+    col = hk.first_row(xg, hk.Matern(nu=2.5, dtype=dtype), (1.0, 0.05), jitter=1e-3)
+    plan = Plan(list(dims), dtype, dev).set_first_row(col)
+    torch.manual_seed(3)
+    M = dims[0] * dims[1]
+    batches = [torch.randn(5, M, dtype=dtype).pin_memory() for _ in range(5)]
+    outs = [torch.empty(5, M, dtype=dtype).pin_memory() for _ in range(5)]
+    iters = [None] * 5
+    plan.pcg_host_submit(batches[0], outs[0], 0, maxiter=20, tol=1e-8)
+    for k in range(1, 5):
+        plan.pcg_host_submit(batches[k], outs[k], k % 2, maxiter=20, tol=1e-8)
+        iters[k - 1] = plan.pcg_host_wait((k - 1) % 2)
+    iters[4] = plan.pcg_host_wait(0)
+    for k in range(5):
+        want, info = plan.pcg(batches[k].to(dev), maxiter=20, tol=1e-8, return_info=True)
+        assert torch.equal(outs[k], want.cpu()), k
+        assert iters[k] == info["iters"]
+    with pytest.raises(RuntimeError):
+        plan.pcg_host_wait(1)           # nothing pending on that slot
