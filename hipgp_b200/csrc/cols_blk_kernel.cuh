@@ -42,28 +42,74 @@ template <int GS> __device__ __forceinline__ void blk_sync(int b) {
     if (GS == 32) warp_sync_all(); else nbar_sync(1 + b, GS);
 }
 
-// twiddles w^{j r}, r = 1..R-1, of a stage: from the shared-memory copy of the [r][j] table or from global memory
-template <int R, int S, bool SM, class T>
-__device__ __forceinline__ void blk_twiddles(cplx<T>* w, const cplx<T>* tab, int j) {
-#pragma unroll
-    for (int r = 1; r < R; ++r) w[r] = SM ? tab[(r - 1) * S + j] : ldg_c(tab + (r - 1) * S + j);
+// Shared-memory twiddle tables hold PAIRS: entry [p][j] = (w^{j (2p+1)}, w^{j (2p+2)}), one 16-byte load (fp32) for two
+// twiddles -- the tables are 28 % of the kernel's shared-memory INSTRUCTIONS when every twiddle is its own 8-byte load.
+template <class T> struct alignas(16) TwPair { cplx<T> a, b; };
+template <int R> struct TwPairs { static constexpr int n = R / 2; };            // ceil((R - 1) / 2) for even R
+template <int R, int S, class T>
+__device__ __forceinline__ void blk_fill_pairs(TwPair<T>* dst, const cplx<T>* tab, int tid, int nt) {
+    for (int i = tid; i < TwPairs<R>::n * S; i += nt) {
+        const int p = i / S, j = i - p * S;
+        TwPair<T> e;
+        e.a = ldg_c(tab + (2 * p) * S + j);
+        e.b = 2 * p + 1 < R - 1 ? ldg_c(tab + (2 * p + 1) * S + j) : mk<T>(1, 0);
+        dst[i] = e;
+    }
 }
 
-// v[r] *= w^{j r} (or its conjugate), r = 1..R-1, with the table loads issued in chunks of CH: at radix 16 the 15 twiddles of
-// a butterfly would otherwise all be live next to its 16 lanes (94 of 128 registers) and the kernel spills -- and a spill
+// twiddles w^{j r}, r = 1..R-1, of a stage: from the shared-memory copy (pairs) or the [r][j] table in global memory
+template <int R, int S, bool SM, class T>
+__device__ __forceinline__ void blk_twiddles(cplx<T>* w, const cplx<T>* tab, int j) {
+    if (SM) {
+        const TwPair<T>* tp = reinterpret_cast<const TwPair<T>*>(tab);
+#pragma unroll
+        for (int p = 0; p < TwPairs<R>::n; ++p) {
+            const TwPair<T> e = tp[p * S + j];
+            w[2 * p + 1] = e.a;
+            if (2 * p + 2 < R) w[2 * p + 2] = e.b;
+        }
+    } else {
+#pragma unroll
+        for (int r = 1; r < R; ++r) w[r] = ldg_c(tab + (r - 1) * S + j);
+    }
+}
+
+// v[r] *= w^{j r} (or its conjugate), r = 1..R-1, with the table loads issued in chunks: at radix 16 the 15 twiddles of a
+// butterfly would otherwise all be live next to its 16 lanes (94 of 128 registers) and the kernel spills -- and a spill
 // reload is an L2 round trip here, because with 225 KB of the SM carved out for shared memory there is no L1 to speak of.
+// (CH twiddles per chunk from global memory; CH / 2 pairs per chunk from shared memory.)
 template <int R, int S, bool SM, bool CONJ, int CH, class T>
 __device__ __forceinline__ void blk_twiddle_mul(Lane<T>* v, const cplx<T>* tab, int j) {
+    if (SM) {
+        constexpr int PC = CH / 2 > 0 ? CH / 2 : 1;                 // pairs per chunk
+        const TwPair<T>* tp = reinterpret_cast<const TwPair<T>*>(tab);
 #pragma unroll
-    for (int r0 = 1; r0 < R; r0 += CH) {
-        cplx<T> w[CH];
+        for (int p0 = 0; p0 < TwPairs<R>::n; p0 += PC) {
+            TwPair<T> e[PC];
 #pragma unroll
-        for (int c = 0; c < CH; ++c) if (r0 + c < R) w[c] = SM ? tab[(r0 + c - 1) * S + j] : ldg_c(tab + (r0 + c - 1) * S + j);
+            for (int c = 0; c < PC; ++c) if (p0 + c < TwPairs<R>::n) e[c] = tp[(p0 + c) * S + j];
 #pragma unroll
-        for (int c = 0; c < CH; ++c) if (r0 + c < R) v[r0 + c] = CONJ ? lmulc(v[r0 + c], w[c]) : lmul(v[r0 + c], w[c]);
+            for (int c = 0; c < PC; ++c) if (p0 + c < TwPairs<R>::n) {
+                const int r = 2 * (p0 + c) + 1;
+                v[r] = CONJ ? lmulc(v[r], e[c].a) : lmul(v[r], e[c].a);
+                if (r + 1 < R) v[r + 1] = CONJ ? lmulc(v[r + 1], e[c].b) : lmul(v[r + 1], e[c].b);
+            }
 #ifndef HIPGP_EMU
-        if (r0 + CH < R) asm volatile("" ::: "memory");       // keeps the next chunk's loads behind this chunk's arithmetic
+            if (p0 + PC < TwPairs<R>::n) asm volatile("" ::: "memory");   // keeps the next chunk's loads behind this chunk's arithmetic
 #endif
+        }
+    } else {
+#pragma unroll
+        for (int r0 = 1; r0 < R; r0 += CH) {
+            cplx<T> w[CH];
+#pragma unroll
+            for (int c = 0; c < CH; ++c) if (r0 + c < R) w[c] = ldg_c(tab + (r0 + c - 1) * S + j);
+#pragma unroll
+            for (int c = 0; c < CH; ++c) if (r0 + c < R) v[r0 + c] = CONJ ? lmulc(v[r0 + c], w[c]) : lmul(v[r0 + c], w[c]);
+#ifndef HIPGP_EMU
+            if (r0 + CH < R) asm volatile("" ::: "memory");
+#endif
+        }
     }
 }
 
@@ -74,7 +120,7 @@ struct ColsBlkCfg {
     static constexpr int IB2 = (BS / R1) * NL, IB3 = (BS / R2) * NL;         // items of one block in the middle / last stage
     static constexpr bool ok = (NT % R0 == 0) && (GS % 32 == 0) && (GS == 32 || R0 <= 15) && (IB2 % GS == 0) && (IB3 % GS == 0) &&
                                ((IB2 / GS) * R1 <= 16) && ((IB3 / GS) * R2 <= 16) && (BS % R2 == 0);
-    static constexpr size_t tw_bytes = sizeof(cplx<T>) * (size_t)((R0 - 1) * (Ln / R0) + (R1 - 1) * (BS / R1));
+    static constexpr size_t tw_bytes = 2 * sizeof(cplx<T>) * (size_t)((R0 / 2) * (Ln / R0) + (R1 / 2) * (BS / R1));   // pairs
     static constexpr size_t side_bytes = (size_t)(Ln + Ln / R2) * NL * 8;
     // (MINB resident CTAs per SM must keep fitting: 228 KB per SM, 1 KB reserved per CTA)
     static constexpr bool tw_smem = (size_t)MINB * (G::smem_bytes() + side_bytes + tw_bytes + 1024) <= 228 * 1024;
@@ -109,11 +155,11 @@ __global__ void __launch_bounds__(NT, MINB) cols_blk_kernel(const HIPGP_GRID_CON
     if ((tma_in || tma_spec) && tid == 0) { tma_bar_init(&s_bar[0]); tma_bar_init(&s_bar[1]); warps_bar_init(&s_bar[2], NT / 32); tma_fence_before_issue(); }
     if (tma_in || tma_spec) __syncthreads();
     if (TWS) {
-        cplx<T>* t0 = reinterpret_cast<cplx<T>*>(side + Cfg::side_bytes);
-        cplx<T>* t1 = t0 + (R0 - 1) * S0;
-        for (int i = tid; i < (R0 - 1) * S0; i += NT) t0[i] = ldg_c(tw0 + i);
-        for (int i = tid; i < (R1 - 1) * S1; i += NT) t1[i] = ldg_c(tw1 + i);
-        tw0 = t0; tw1 = t1;
+        TwPair<T>* t0 = reinterpret_cast<TwPair<T>*>(side + Cfg::side_bytes);
+        TwPair<T>* t1 = t0 + TwPairs<R0>::n * S0;
+        blk_fill_pairs<R0, S0, T>(t0, tw0, tid, NT);
+        blk_fill_pairs<R1, S1, T>(t1, tw1, tid, NT);
+        tw0 = reinterpret_cast<const cplx<T>*>(t0); tw1 = reinterpret_cast<const cplx<T>*>(t1);
         __syncthreads();
     }
 
