@@ -42,74 +42,48 @@ template <int GS> __device__ __forceinline__ void blk_sync(int b) {
     if (GS == 32) warp_sync_all(); else nbar_sync(1 + b, GS);
 }
 
-// Shared-memory twiddle tables hold PAIRS: entry [p][j] = (w^{j (2p+1)}, w^{j (2p+2)}), one 16-byte load (fp32) for two
-// twiddles -- the tables are 28 % of the kernel's shared-memory INSTRUCTIONS when every twiddle is its own 8-byte load.
-template <class T> struct alignas(16) TwPair { cplx<T> a, b; };
-template <int R> struct TwPairs { static constexpr int n = R / 2; };            // ceil((R - 1) / 2) for even R
+// Twiddle tables are PAIRED (fft_engine.cuh: TwPair, one 16-byte load for two fp32 twiddles) in global AND in shared memory:
+// single 8-byte loads made the tables 28 % of the kernel's shared-memory INSTRUCTIONS.
 template <int R, int S, class T>
 __device__ __forceinline__ void blk_fill_pairs(TwPair<T>* dst, const cplx<T>* tab, int tid, int nt) {
-    for (int i = tid; i < TwPairs<R>::n * S; i += nt) {
-        const int p = i / S, j = i - p * S;
-        TwPair<T> e;
-        e.a = ldg_c(tab + (2 * p) * S + j);
-        e.b = 2 * p + 1 < R - 1 ? ldg_c(tab + (2 * p + 1) * S + j) : mk<T>(1, 0);
-        dst[i] = e;
-    }
+    const TwPair<T>* src = reinterpret_cast<const TwPair<T>*>(tab);
+    for (int i = tid; i < TwPairs<R>::n * S; i += nt) dst[i] = ldg_pair(src + i);
 }
+template <bool SM, class T> __device__ __forceinline__ TwPair<T> blk_pair(const TwPair<T>* p) { return SM ? *p : ldg_pair(p); }
 
-// twiddles w^{j r}, r = 1..R-1, of a stage: from the shared-memory copy (pairs) or the [r][j] table in global memory
+// twiddles w^{j r}, r = 1..R-1, of a stage: from the shared-memory copy or from global memory
 template <int R, int S, bool SM, class T>
 __device__ __forceinline__ void blk_twiddles(cplx<T>* w, const cplx<T>* tab, int j) {
-    if (SM) {
-        const TwPair<T>* tp = reinterpret_cast<const TwPair<T>*>(tab);
+    const TwPair<T>* tp = reinterpret_cast<const TwPair<T>*>(tab);
 #pragma unroll
-        for (int p = 0; p < TwPairs<R>::n; ++p) {
-            const TwPair<T> e = tp[p * S + j];
-            w[2 * p + 1] = e.a;
-            if (2 * p + 2 < R) w[2 * p + 2] = e.b;
-        }
-    } else {
-#pragma unroll
-        for (int r = 1; r < R; ++r) w[r] = ldg_c(tab + (r - 1) * S + j);
+    for (int p = 0; p < TwPairs<R>::n; ++p) {
+        const TwPair<T> e = blk_pair<SM>(tp + p * S + j);
+        w[2 * p + 1] = e.a;
+        if (2 * p + 2 < R) w[2 * p + 2] = e.b;
     }
 }
 
-// v[r] *= w^{j r} (or its conjugate), r = 1..R-1, with the table loads issued in chunks: at radix 16 the 15 twiddles of a
-// butterfly would otherwise all be live next to its 16 lanes (94 of 128 registers) and the kernel spills -- and a spill
-// reload is an L2 round trip here, because with 225 KB of the SM carved out for shared memory there is no L1 to speak of.
-// (CH twiddles per chunk from global memory; CH / 2 pairs per chunk from shared memory.)
+// v[r] *= w^{j r} (or its conjugate), r = 1..R-1, with the table loads issued in chunks of CH / 2 pairs: at radix 16 the 15
+// twiddles of a butterfly would otherwise all be live next to its 16 lanes (94 of 128 registers) and the kernel spills -- and a
+// spill reload is an L2 round trip here, because with 225 KB of the SM carved out for shared memory there is no L1 to speak of.
 template <int R, int S, bool SM, bool CONJ, int CH, class T>
 __device__ __forceinline__ void blk_twiddle_mul(Lane<T>* v, const cplx<T>* tab, int j) {
-    if (SM) {
-        constexpr int PC = CH / 2 > 0 ? CH / 2 : 1;                 // pairs per chunk
-        const TwPair<T>* tp = reinterpret_cast<const TwPair<T>*>(tab);
+    constexpr int PC = CH / 2 > 0 ? CH / 2 : 1;                 // pairs per chunk
+    const TwPair<T>* tp = reinterpret_cast<const TwPair<T>*>(tab);
 #pragma unroll
-        for (int p0 = 0; p0 < TwPairs<R>::n; p0 += PC) {
-            TwPair<T> e[PC];
+    for (int p0 = 0; p0 < TwPairs<R>::n; p0 += PC) {
+        TwPair<T> e[PC];
 #pragma unroll
-            for (int c = 0; c < PC; ++c) if (p0 + c < TwPairs<R>::n) e[c] = tp[(p0 + c) * S + j];
+        for (int c = 0; c < PC; ++c) if (p0 + c < TwPairs<R>::n) e[c] = blk_pair<SM>(tp + (p0 + c) * S + j);
 #pragma unroll
-            for (int c = 0; c < PC; ++c) if (p0 + c < TwPairs<R>::n) {
-                const int r = 2 * (p0 + c) + 1;
-                v[r] = CONJ ? lmulc(v[r], e[c].a) : lmul(v[r], e[c].a);
-                if (r + 1 < R) v[r + 1] = CONJ ? lmulc(v[r + 1], e[c].b) : lmul(v[r + 1], e[c].b);
-            }
-#ifndef HIPGP_EMU
-            if (p0 + PC < TwPairs<R>::n) asm volatile("" ::: "memory");   // keeps the next chunk's loads behind this chunk's arithmetic
-#endif
+        for (int c = 0; c < PC; ++c) if (p0 + c < TwPairs<R>::n) {
+            const int r = 2 * (p0 + c) + 1;
+            v[r] = CONJ ? lmulc(v[r], e[c].a) : lmul(v[r], e[c].a);
+            if (r + 1 < R) v[r + 1] = CONJ ? lmulc(v[r + 1], e[c].b) : lmul(v[r + 1], e[c].b);
         }
-    } else {
-#pragma unroll
-        for (int r0 = 1; r0 < R; r0 += CH) {
-            cplx<T> w[CH];
-#pragma unroll
-            for (int c = 0; c < CH; ++c) if (r0 + c < R) w[c] = ldg_c(tab + (r0 + c - 1) * S + j);
-#pragma unroll
-            for (int c = 0; c < CH; ++c) if (r0 + c < R) v[r0 + c] = CONJ ? lmulc(v[r0 + c], w[c]) : lmul(v[r0 + c], w[c]);
 #ifndef HIPGP_EMU
-            if (r0 + CH < R) asm volatile("" ::: "memory");
+        if (p0 + PC < TwPairs<R>::n) asm volatile("" ::: "memory");   // keeps the next chunk's loads behind this chunk's arithmetic
 #endif
-        }
     }
 }
 

@@ -56,6 +56,23 @@ __device__ __forceinline__ cplx<double> ldg_c(const cplx<double>* p) {
 }
 #endif
 
+// Stage twiddle tables hold PAIRS: entry [p][j] = (w^{j (2p+1)}, w^{j (2p+2)}), p < R / 2 -- one 16-byte load (fp32) brings two
+// twiddles; an unused second half (R even) is 1.
+template <class T> struct alignas(16) TwPair { cplx<T> a, b; };
+template <int R> struct TwPairs { static constexpr int n = R / 2; };            // = ceil((R - 1) / 2)
+#ifdef HIPGP_EMU
+template <class T> __device__ __forceinline__ TwPair<T> ldg_pair(const TwPair<T>* p) { return *p; }
+#else
+__device__ __forceinline__ TwPair<float> ldg_pair(const TwPair<float>* p) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(p));
+    TwPair<float> e; e.a = mk<float>(v.x, v.y); e.b = mk<float>(v.z, v.w); return e;
+}
+__device__ __forceinline__ TwPair<double> ldg_pair(const TwPair<double>* p) {
+    const double2 u = __ldg(reinterpret_cast<const double2*>(p)), v = __ldg(reinterpret_cast<const double2*>(p) + 1);
+    TwPair<double> e; e.a = mk<double>(u.x, u.y); e.b = mk<double>(v.x, v.y); return e;
+}
+#endif
+
 constexpr int kMaxStages = 24;
 
 // Device-side description of one line-FFT length.
@@ -67,7 +84,7 @@ struct LineFft {
     const cplx<T>* tw;      // Ln entries, exp(-2 pi i k / Ln)
     const int* rev;         // Ln entries: rev[p] = frequency index k stored at position p after DIF
     const int* pos;         // Ln entries: pos[k] = position p (inverse permutation)
-    const cplx<T>* twst;    // per-stage twiddles, stage s at twst + twoff[s], layout [(r-1) * S + j] = w_Nt^{j r}
+    const cplx<T>* twst;    // per-stage twiddles, stage s at twst + twoff[s]: TwPair [p * S + j] = (w_Nt^{j (2p+1)}, w_Nt^{j (2p+2)})
     int twoff[kMaxStages];
 };
 

@@ -389,11 +389,16 @@ struct TileGeo {
     __host__ __device__ static constexpr int leg(int S) { return (S == 1 ? 1 : (PAD ? S + (S >> LOGRL) : S)) * NL; }
 };
 
-// per-stage twiddles w^{j r}, r = 1..R-1, from the [r][j] table of the stage
+// per-stage twiddles w^{j r}, r = 1..R-1, from the paired table of the stage (fft_engine.cuh: TwPair)
 template <int R, int S, class T>
 __device__ __forceinline__ void lane_twiddles(cplx<T>* w, const cplx<T>* __restrict__ tab, int j) {
+    const TwPair<T>* tp = reinterpret_cast<const TwPair<T>*>(tab);
 #pragma unroll
-    for (int r = 1; r < R; ++r) w[r] = ldg_c(tab + (r - 1) * S + j);
+    for (int p = 0; p < TwPairs<R>::n; ++p) {
+        const TwPair<T> e = ldg_pair(tp + p * S + j);
+        w[2 * p + 1] = e.a;
+        if (2 * p + 2 < R) w[2 * p + 2] = e.b;
+    }
 }
 
 // one in-place shared-memory stage of sub-transform length Nt, radix R, over the whole tile
