@@ -70,3 +70,81 @@ def test_single_process_is_a_noop():
     assert hdist.allreduce_packed(t)[0].tolist() == [1.0, 1.0, 1.0]
     assert hdist.world() == (0, 1)
     assert hdist.global_converged(1e-9, 1e-8, "cpu") is True
+
+
+def _slab_worker(rank, world, port, out):
+    """grid-sharded matvec across two PROCESSES: the library's three local stages (CPU emulation build of the same kernel
+    sources) around torch.distributed all_to_all_single, exactly as hipgp_b200/slab.py orders them (bins layout, two chunks)"""
+    import ctypes as C
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import emu_build
+    from hipgp_b200 import _lib as L
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        lib = emu_build.load()
+        ptr = lambda a: a.ctypes.data_as(C.c_void_p)
+        dims = (8, 6, 10)
+        g = np.meshgrid(*[np.linspace(0, 1 + d, k) for d, k in enumerate(dims)], indexing="ij")
+        r = np.sqrt(sum((x - x.flat[0]) ** 2 for x in g))
+        col = ((1 + np.sqrt(3) * r / 0.4) * np.exp(-np.sqrt(3) * r / 0.4)).reshape(-1); col[0] += 1e-2
+
+        def mkplan(slab):
+            plan = C.c_void_p(); mm = np.array(dims, dtype=np.int64)
+            assert lib.hipgp_plan_create(3, mm.ctypes.data_as(L._pi64), L.F64, 0, C.byref(plan)) == 0
+            if slab:
+                assert lib.hipgp_plan_set_slab(plan, rank, world) == 0
+                assert lib.hipgp_plan_set_slab_chunks(plan, 2) == 0
+            assert lib.hipgp_plan_set_first_row(plan, ptr(col), 1e-6, None, None) == 0, lib.hipgp_last_error()
+            return plan
+        plan = mkplan(True)
+        a, b = C.c_int64(), C.c_int64()
+        assert lib.hipgp_slab2_sizes(plan, C.byref(a), C.byref(b)) == 0
+        slab_elems, exch = a.value, b.value
+        M = int(np.prod(dims)); n0 = dims[0] // world
+        v = np.random.default_rng(0).standard_normal((1, M))                     # same on both ranks
+        mine = np.ascontiguousarray(v.reshape(dims)[rank * n0:(rank + 1) * n0]).reshape(-1)
+
+        def exchange(buf):                                                       # per chunk, like SlabToeplitz._exchange
+            recv = np.empty_like(buf); per = exch // 2
+            for c in range(2):
+                s = torch.view_as_real(torch.from_numpy(buf[c * per:(c + 1) * per]))
+                t = torch.view_as_real(torch.from_numpy(recv[c * per:(c + 1) * per]))
+                dist.all_to_all_single(t, s)
+            return recv
+        errs = []
+        for mode in (L.MV_K, L.MV_CINV):
+            send = np.zeros(exch, dtype=np.complex128)
+            assert lib.hipgp_slab2_stage_a(plan, ptr(mine), ptr(send), None) == 0, lib.hipgp_last_error()
+            buf = exchange(send)
+            for c in range(2):
+                assert lib.hipgp_slab2_stage_b_chunk(plan, mode, ptr(buf), c, None) == 0, lib.hipgp_last_error()
+            back = exchange(buf)
+            o = np.zeros(slab_elems)
+            assert lib.hipgp_slab2_stage_c(plan, ptr(back), ptr(o), None) == 0, lib.hipgp_last_error()
+            parts = [torch.empty(slab_elems, dtype=torch.float64) for _ in range(world)]
+            dist.all_gather(parts, torch.from_numpy(o))
+            if rank == 0:
+                full = mkplan(False)
+                ref = np.zeros((1, M))
+                assert lib.hipgp_matvec(full, mode, ptr(v), ptr(ref), 1, None) == 0
+                got = torch.cat(parts).numpy().reshape(1, -1)
+                errs.append(float(np.linalg.norm(got - ref) / np.linalg.norm(ref)))
+        out[rank] = errs
+    finally:
+        dist.destroy_process_group()
+
+
+def test_slab_matvec_across_two_processes_gloo():
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import emu_build
+    emu_build.load()                       # build once in the parent, the workers only load it
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    port = 29400 + (os.getpid() % 150)
+    mp.spawn(_slab_worker, args=(world, port, out), nprocs=world, join=True)
+    assert len(out[0]) == 2 and all(e < 1e-12 for e in out[0]), out[0]
