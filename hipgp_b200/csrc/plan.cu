@@ -287,6 +287,22 @@ static const double* axis_costab(hipgp_plan* pl, int d) {
     return b.as<double>();
 }
 
+// the parity-split weighted cosine matrix of an axis (m <= 2048: at most 16 MB), built once per plan on the caller's stream
+static const double* axis_cosmat(hipgp_plan* pl, int d, cudaStream_t s) {
+    const int md = pl->m[d];
+    if (md > 2048) return nullptr;
+    DevBuf& b = pl->cosmats[d];
+    if (!b.p) {
+        const double* tab = axis_costab(pl, d);
+        const size_t h = (size_t)(md + 1) / 2;
+        b.ensure(sizeof(double) * 2 * h * h, &pl->dev_bytes);              // parity-split: Cw2[p][j < h][k' < h]
+        auto k = dct1_cosmat_sym_kernel;
+        HIPGP_LAUNCH(k, dim3(148 * 4), dim3(256), 0, s, tab, b.as<double>(), md);
+        CK_LAUNCH(); pl->launches++;
+    }
+    return b.as<double>();
+}
+
 static void dct_all_axes(hipgp_plan* pl, const double* in, double* out, double* tmp, bool normalise, cudaStream_t s) {
     // separable DCT-I over the active axes; result always lands in `out`
     const double* src = in;
@@ -312,15 +328,23 @@ static void dct_all_axes(hipgp_plan* pl, const double* in, double* out, double* 
             auto k = dct1_axis_kernel;
             HIPGP_LAUNCH(k, grid, block, 0, s, src, dst, tab, md, inner, scale, nx);
         } else if (inner == 1) {
-            dim3 grid((unsigned)((md + 63) / 64), (unsigned)((outer + 63) / 64), 1);
-            auto k = dct1_tile_kernel<true>;
-            HIPGP_LAUNCH(k, grid, dim3(256), 0, s, src, dst, tab, md, inner, outer, scale);
+            dim3 grid((unsigned)((md + 63) / 64), (unsigned)((outer + 127) / 128), 1);      // 128 x 64 output tile per block
+            const double* cw = md > 2 ? axis_cosmat(pl, d, s) : nullptr;
+            if (cw) {      // reflection symmetry folded in: two half-size products, one per output parity (grid.z)
+                const int hk0 = (md + 1) / 2;
+                dim3 gs((unsigned)((hk0 + 63) / 64), (unsigned)((outer + 127) / 128), 2);
+                auto k = dct1_sym_kernel<true>; HIPGP_LAUNCH(k, gs, dim3(256), 0, s, src, dst, cw, md, inner, outer, scale, 0);
+            } else { auto k = dct1_tile_kernel<true>; HIPGP_LAUNCH(k, grid, dim3(256), 0, s, src, dst, tab, md, inner, outer, scale); }
         } else {
             // grid.z = outer index (<= 65535 for every supported grid: at most two leading axes of a 3-D grid)
             if (outer > 65535) throw Error("DCT set-up: more than 65535 outer slices");
-            dim3 grid((unsigned)((inner + 63) / 64), (unsigned)((md + 63) / 64), (unsigned)outer);
-            auto k = dct1_tile_kernel<false>;
-            HIPGP_LAUNCH(k, grid, dim3(256), 0, s, src, dst, tab, md, inner, outer, scale);
+            dim3 grid((unsigned)((inner + 63) / 64), (unsigned)((md + 127) / 128), (unsigned)outer);
+            const double* cw = md > 2 ? axis_cosmat(pl, d, s) : nullptr;
+            if (cw) {
+                const int hk0 = (md + 1) / 2, nty = (hk0 + 127) / 128;
+                dim3 gs((unsigned)((inner + 63) / 64), (unsigned)(2 * nty), (unsigned)outer);
+                auto k = dct1_sym_kernel<false>; HIPGP_LAUNCH(k, gs, dim3(256), 0, s, src, dst, cw, md, inner, outer, scale, nty);
+            } else { auto k = dct1_tile_kernel<false>; HIPGP_LAUNCH(k, grid, dim3(256), 0, s, src, dst, tab, md, inner, outer, scale); }
         }
         CK_LAUNCH();
         pl->launches++;
@@ -406,7 +430,7 @@ static void set_first_row(hipgp_plan* pl, const void* column, double clampv, cud
     if (pl->nclamped != 0 || sizeof(T) == 4)
         dct_all_axes(pl, pl->Dm.as<double>(), pl->colK.as<double>(), pl->tmpB.as<double>(), true, s);
     dct_all_axes(pl, pl->Dinv.as<double>(), pl->colG.as<double>(), pl->tmpB.as<double>(), true, s);
-    dct_all_axes(pl, pl->Dsqrt.as<double>(), pl->colS.as<double>(), pl->tmpB.as<double>(), true, s);
+    // (the first column of C'^1/2 belongs to the wide embedding: ensure_wide builds it on the first R^T / R)
     build_spectrum<T>(pl, false, pl->colK.as<double>(), pl->specK, false, s);
     build_spectrum<T>(pl, false, pl->colG.as<double>(), pl->specCinv, false, s);
     pl->have_spec = true; pl->have_wide = false; pl->have_slabK = pl->have_slabCinv = false;
@@ -423,6 +447,7 @@ static void ensure_wide(hipgp_plan* pl, cudaStream_t s) {
     bool real_ok = !env_c;
     for (int d = 0; d < pl->D; ++d) if (pl->Lw[d] < 2 * pl->N[d] - 1) real_ok = false;
     pl->wide_real = real_ok;
+    dct_all_axes(pl, pl->Dsqrt.as<double>(), pl->colS.as<double>(), pl->tmpB.as<double>(), true, s);
     build_spectrum<T>(pl, true, pl->colS.as<double>(), pl->specW, !real_ok, s);
     pl->have_wide = true;
 }
@@ -995,7 +1020,7 @@ int hipgp_plan_destroy(hipgp_plan* pl) {
     for (DevBuf* b : {&pl->specK, &pl->specCinv, &pl->specW, &pl->Dm, &pl->Dinv, &pl->Dsqrt, &pl->colK, &pl->colG, &pl->colS,
                       &pl->tmpA, &pl->tmpB, &pl->costab, &pl->counts, &pl->W1, &pl->W2, &pl->vr, &pl->vp, &pl->vz, &pl->vAp,
                       &pl->partial, &pl->scal, &pl->cnt, &pl->flags, &pl->stage_in, &pl->stage_out, &pl->corrU, &pl->corrV, &pl->corrS,
-                      &pl->corrLag, &pl->gradA, &pl->slabSpecK, &pl->slabSpecCinv, &pl->slabR1, &pl->slabR2, &pl->slot_in[0], &pl->slot_in[1], &pl->slot_out[0], &pl->slot_out[1], &pl->costabs[0], &pl->costabs[1], &pl->costabs[2]})
+                      &pl->corrLag, &pl->gradA, &pl->slabSpecK, &pl->slabSpecCinv, &pl->slabR1, &pl->slabR2, &pl->slot_in[0], &pl->slot_in[1], &pl->slot_out[0], &pl->slot_out[1], &pl->costabs[0], &pl->costabs[1], &pl->costabs[2], &pl->cosmats[0], &pl->cosmats[1], &pl->cosmats[2]})
         b->release(t);
     slab_peer_close(pl);
 #ifndef HIPGP_EMU

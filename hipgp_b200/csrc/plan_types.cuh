@@ -281,7 +281,7 @@ struct hipgp_plan {
     DevBuf stage_in, stage_out;            // device staging for the *_host entry points
     DevBuf slabSpecK, slabSpecCinv;        // this rank's bins of the spectra, [L0][L1][Pq] (slab decomposition v2)
     bool have_slabK = false, have_slabCinv = false;
-    DevBuf costabs[3];                     // DCT-I cosine tables per active axis (built once per plan)
+    DevBuf costabs[3], cosmats[3];                     // DCT-I cosine tables per active axis (built once per plan)
     DevBuf gradA;                          // R^T column gradient (corr_api.inl): one M-sized fp64 work array
     DevBuf corrU, corrV, corrS, corrLag;   // Toeplitz-column quadratic form (corr_api.inl): spectra of a chunk of pairs, their sum, lags
     void* pinned = nullptr;                // host flags mirror

@@ -43,13 +43,15 @@ __global__ void __launch_bounds__(256) dct1_axis_kernel(const double* __restrict
 // path -- (m x m cosine matrix) x (m x inner) per outer index -- and at config 2 the one-output-per-thread kernel above spent
 // 1.13 ms per launch, 8 launches per spectrum set-up).  64 x 64 output tile per CTA, 16-deep k tiles in shared memory,
 // 16 x 16 threads with 4 x 4 fp64 accumulators each; the cosine operand is generated from the length-N table (index
-// (j k) mod N) while its tile is staged, so no m x m matrix is ever stored.
+// (j k) mod N) while its tile is staged, so no m x m matrix is stored (axes longer than 2048 points; shorter axes take
+// dct1_sym_kernel below).
 //   LAST == false: out[o][k][i] = scale * sum_j w_j cos(pi j k / (m-1)) in[o][j][i]      (tile rows = k, tile columns = i)
 //   LAST == true : inner == 1:  out[o][k]   = scale * sum_j in[o][j] w_j cos(pi j k / (m-1))  (tile rows = o, tile columns = k)
 template <bool LAST>
 __global__ void __launch_bounds__(256) dct1_tile_kernel(const double* __restrict__ in, double* __restrict__ out,
                                                         const double* __restrict__ costab, int m, long inner, long outer, double scale) {
-    constexpr int TM = 64, TN = 64, TK = 16;
+    constexpr int RM = 8;                   // rows per thread: 8 x 4 outputs per thread, 12 shared-memory loads per 32 DFMA
+    constexpr int TM = 16 * RM, TN = 64, TK = 16;
     __shared__ double As[TK][TM + 2];      // As[jj][row]
     __shared__ double Bs[TK][TN + 2];      // Bs[jj][col]
     const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
@@ -58,9 +60,9 @@ __global__ void __launch_bounds__(256) dct1_tile_kernel(const double* __restrict
     const long o = LAST ? 0 : (long)blockIdx.z;
     const long nrows = LAST ? outer : m, ncols = LAST ? m : inner;
     const double* inb = in + (LAST ? 0 : (size_t)o * m * inner);
-    double acc[4][4];
+    double acc[RM][4];
 #pragma unroll
-    for (int a = 0; a < 4; ++a)
+    for (int a = 0; a < RM; ++a)
 #pragma unroll
         for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
     for (int j0 = 0; j0 < m; j0 += TK) {
@@ -91,11 +93,13 @@ __global__ void __launch_bounds__(256) dct1_tile_kernel(const double* __restrict
         __syncthreads();
 #pragma unroll
         for (int jj = 0; jj < TK; ++jj) {
-            double a[4], b[4];
+            double a[RM], b[4];
 #pragma unroll
-            for (int t = 0; t < 4; ++t) { a[t] = As[jj][ty * 4 + t]; b[t] = Bs[jj][tx * 4 + t]; }
+            for (int t = 0; t < RM; ++t) a[t] = As[jj][ty * RM + t];
 #pragma unroll
-            for (int x = 0; x < 4; ++x)
+            for (int t = 0; t < 4; ++t) b[t] = Bs[jj][tx * 4 + t];
+#pragma unroll
+            for (int x = 0; x < RM; ++x)
 #pragma unroll
                 for (int y = 0; y < 4; ++y) acc[x][y] += a[x] * b[y];
         }
@@ -103,13 +107,114 @@ __global__ void __launch_bounds__(256) dct1_tile_kernel(const double* __restrict
     }
     double* outb = out + (LAST ? 0 : (size_t)o * m * inner);
 #pragma unroll
-    for (int x = 0; x < 4; ++x) {
-        const long row = r0 + ty * 4 + x;
+    for (int x = 0; x < RM; ++x) {
+        const long row = r0 + ty * RM + x;
         if (row >= nrows) continue;
 #pragma unroll
         for (int y = 0; y < 4; ++y) {
             const long col = c0 + tx * 4 + y;
             if (col < ncols) outb[(size_t)row * (LAST ? m : inner) + col] = acc[x][y] * scale;
+        }
+    }
+}
+
+// ---- DCT-I with the reflection symmetry of the cosine matrix folded in: HALF the multiply-adds -------------------------
+// w_j cos(pi (m-1-j) k / (m-1)) = (-1)^k w_j cos(pi j k / (m-1)), so with hj = ceil(m / 2) folded inputs
+//   out[2k'+p] = sum_{j < hj} Cw[j][2k'+p] (x[j] + (-1)^p x[m-1-j])          (the unpaired middle input of an odd m counts once)
+// i.e. two products of half the size, one per output parity p.  The parity-split matrix Cw2[p][j][k'] = Cw[j][2k'+p] (row pitch
+// hk0 = ceil(m / 2)) is cached per axis; the fold happens while the input tile is staged.  Same tile shape as dct1_tile_kernel.
+__global__ void dct1_cosmat_sym_kernel(const double* __restrict__ costab, double* __restrict__ cw2, int m) {
+    const unsigned N = m > 1 ? 2u * (unsigned)(m - 1) : 1u;
+    const int hj = (m + 1) / 2, hk0 = (m + 1) / 2;
+    const long total = 2L * hj * hk0;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const int kp = (int)(i % hk0), j = (int)((i / hk0) % hj), p = (int)(i / ((long)hk0 * hj));
+        const int k = 2 * kp + p;
+        const double w = (j == 0 || j == m - 1) ? 1.0 : 2.0;
+        cw2[i] = (k < m && m > 1) ? w * costab[((unsigned)j * (unsigned)k) % N] : (m > 1 ? 0.0 : 1.0);
+    }
+}
+template <bool LAST>
+__global__ void __launch_bounds__(256) dct1_sym_kernel(const double* __restrict__ in, double* __restrict__ out, const double* __restrict__ cw2,
+                                                       int m, long inner, long outer, double scale, int nty) {
+    constexpr int RM = 8;
+    constexpr int TM = 16 * RM, TN = 64, TK = 16;
+    __shared__ double As[TK][TM + 2];
+    __shared__ double Bs[TK][TN + 2];
+    const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
+    const int hj = (m + 1) / 2, hk0 = (m + 1) / 2;
+    // parity and tile coordinates:  !LAST: grid (inner tiles, 2 * nty, outer);  LAST: grid (k' tiles, outer tiles, 2)
+    const int p = LAST ? (int)blockIdx.z : (int)(blockIdx.y / nty);
+    const long r0 = (LAST ? (long)blockIdx.y : (long)(blockIdx.y - p * nty)) * TM, c0 = (long)blockIdx.x * TN;
+    const int hk = (m - p + 1) / 2;                             // outputs of this parity
+    const long o = LAST ? 0 : (long)blockIdx.z;
+    const long nrows = LAST ? outer : hk, ncols = LAST ? hk : inner;
+    const double* inb = in + (LAST ? 0 : (size_t)o * m * inner);
+    const double* cwp = cw2 + (size_t)p * hj * hk0;
+    const double sgn = p ? -1.0 : 1.0;
+    double acc[RM][4];
+#pragma unroll
+    for (int a = 0; a < RM; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+    for (int j0 = 0; j0 < hj; j0 += TK) {
+        for (int e = threadIdx.x; e < TK * TM; e += 256) {
+            if (LAST) {          // A(row = o, j) = in[o][j] +- in[o][m-1-j]
+                const int jj = e % TK, rr = e / TK;
+                const long row = r0 + rr; const int j = j0 + jj;
+                double v = 0.0;
+                if (row < nrows && j < hj) {
+                    const int jm = m - 1 - j;
+                    v = inb[(size_t)row * m + j];
+                    v = jm == j ? (p ? 0.0 : v) : v + sgn * inb[(size_t)row * m + jm];
+                }
+                As[jj][rr] = v;
+            } else {             // A(row = k', j) = Cw2[p][j][k']
+                const int rr = e % TM, jj = e / TM;
+                const long k = r0 + rr; const int j = j0 + jj;
+                As[jj][rr] = (k < nrows && j < hj) ? cwp[(size_t)j * hk0 + k] : 0.0;
+            }
+        }
+        for (int e = threadIdx.x; e < TK * TN; e += 256) {
+            const int cc = e % TN, jj = e / TN;
+            const long col = c0 + cc; const int j = j0 + jj;
+            double v = 0.0;
+            if (col < ncols && j < hj) {
+                if (LAST) v = cwp[(size_t)j * hk0 + col];
+                else {
+                    const int jm = m - 1 - j;
+                    v = inb[(size_t)j * inner + col];
+                    v = jm == j ? (p ? 0.0 : v) : v + sgn * inb[(size_t)jm * inner + col];
+                }
+            }
+            Bs[jj][cc] = v;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int jj = 0; jj < TK; ++jj) {
+            double a[RM], b[4];
+#pragma unroll
+            for (int t = 0; t < RM; ++t) a[t] = As[jj][ty * RM + t];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) b[t] = Bs[jj][tx * 4 + t];
+#pragma unroll
+            for (int x = 0; x < RM; ++x)
+#pragma unroll
+                for (int y = 0; y < 4; ++y) acc[x][y] += a[x] * b[y];
+        }
+        __syncthreads();
+    }
+    double* outb = out + (LAST ? 0 : (size_t)o * m * inner);
+#pragma unroll
+    for (int x = 0; x < RM; ++x) {
+        const long row = r0 + ty * RM + x;
+        if (row >= nrows) continue;
+#pragma unroll
+        for (int y = 0; y < 4; ++y) {
+            const long col = c0 + tx * 4 + y;
+            if (col >= ncols) continue;
+            if (LAST) outb[(size_t)row * m + (2 * col + p)] = acc[x][y] * scale;
+            else outb[(size_t)(2 * row + p) * inner + col] = acc[x][y] * scale;
         }
     }
 }
