@@ -42,22 +42,22 @@ template <int GS> __device__ __forceinline__ void blk_sync(int b) {
     if (GS == 32) warp_sync_all(); else nbar_sync(1 + b, GS);
 }
 
-// Twiddle tables are PAIRED (fft_engine.cuh: TwPair, one 16-byte load for two fp32 twiddles) in global AND in shared memory:
-// single 8-byte loads made the tables 28 % of the kernel's shared-memory INSTRUCTIONS.
+// The SHARED-memory twiddle tables are always PAIRED (fft_engine.cuh: TwPair, one 16-byte load for two fp32 twiddles): single
+// 8-byte loads made the tables 28 % of the kernel's shared-memory INSTRUCTIONS.  The global tables are paired in fp32 only.
 template <int R, int S, class T>
 __device__ __forceinline__ void blk_fill_pairs(TwPair<T>* dst, const cplx<T>* tab, int tid, int nt) {
-    const TwPair<T>* src = reinterpret_cast<const TwPair<T>*>(tab);
-    for (int i = tid; i < TwPairs<R>::n * S; i += nt) dst[i] = ldg_pair(src + i);
+    for (int i = tid; i < TwPairs<R>::n * S; i += nt) { const int p = i / S; dst[i] = tw_pair_global<R, S, T>(tab, p, i - p * S); }
 }
-template <bool SM, class T> __device__ __forceinline__ TwPair<T> blk_pair(const TwPair<T>* p) { return SM ? *p : ldg_pair(p); }
+template <int R, int S, bool SM, class T> __device__ __forceinline__ TwPair<T> blk_pair(const cplx<T>* tab, int p, int j) {
+    return SM ? reinterpret_cast<const TwPair<T>*>(tab)[p * S + j] : tw_pair_global<R, S, T>(tab, p, j);
+}
 
 // twiddles w^{j r}, r = 1..R-1, of a stage: from the shared-memory copy or from global memory
 template <int R, int S, bool SM, class T>
 __device__ __forceinline__ void blk_twiddles(cplx<T>* w, const cplx<T>* tab, int j) {
-    const TwPair<T>* tp = reinterpret_cast<const TwPair<T>*>(tab);
 #pragma unroll
     for (int p = 0; p < TwPairs<R>::n; ++p) {
-        const TwPair<T> e = blk_pair<SM>(tp + p * S + j);
+        const TwPair<T> e = blk_pair<R, S, SM, T>(tab, p, j);
         w[2 * p + 1] = e.a;
         if (2 * p + 2 < R) w[2 * p + 2] = e.b;
     }
@@ -69,12 +69,11 @@ __device__ __forceinline__ void blk_twiddles(cplx<T>* w, const cplx<T>* tab, int
 template <int R, int S, bool SM, bool CONJ, int CH, class T>
 __device__ __forceinline__ void blk_twiddle_mul(Lane<T>* v, const cplx<T>* tab, int j) {
     constexpr int PC = CH / 2 > 0 ? CH / 2 : 1;                 // pairs per chunk
-    const TwPair<T>* tp = reinterpret_cast<const TwPair<T>*>(tab);
 #pragma unroll
     for (int p0 = 0; p0 < TwPairs<R>::n; p0 += PC) {
         TwPair<T> e[PC];
 #pragma unroll
-        for (int c = 0; c < PC; ++c) if (p0 + c < TwPairs<R>::n) e[c] = blk_pair<SM>(tp + (p0 + c) * S + j);
+        for (int c = 0; c < PC; ++c) if (p0 + c < TwPairs<R>::n) e[c] = blk_pair<R, S, SM, T>(tab, p0 + c, j);
 #pragma unroll
         for (int c = 0; c < PC; ++c) if (p0 + c < TwPairs<R>::n) {
             const int r = 2 * (p0 + c) + 1;

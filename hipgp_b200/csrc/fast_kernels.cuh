@@ -872,10 +872,12 @@ __global__ void __launch_bounds__(NT, MINB) rows_inv_fast_kernel(RowsParams<T> P
         }
     }
 #ifndef HIPGP_EMU
-    const bool tma_out = !want_dot && P.tma_ok && P.vec16_ok && SROW == n;
-    if (tma_out) fence_proxy_async();        // this thread's shared-memory writes become visible to the async proxy
+    const bool tma_any = P.tma_ok && P.vec16_ok && SROW == n;
+    const bool tma_out = !want_dot && tma_any;
+    const bool tma_dot = want_dot && tma_any;       // fused dot: the rows still leave with ONE bulk store; the warps only read
+    if (tma_any) fence_proxy_async();        // this thread's shared-memory writes become visible to the async proxy
 #else
-    const bool tma_out = false;
+    const bool tma_out = false, tma_dot = false;
 #endif
     __syncthreads();
 #ifndef HIPGP_EMU
@@ -883,6 +885,7 @@ __global__ void __launch_bounds__(NT, MINB) rows_inv_fast_kernel(RowsParams<T> P
         if (tid == 0) bulk_s2g(P.out + (size_t)g0 * n, side, (unsigned)((size_t)nl * n * sizeof(T)));
         return;
     }
+    if (tma_dot && tid == 0) bulk_s2g_issue(P.out + (size_t)g0 * n, side, (unsigned)((size_t)nl * n * sizeof(T)));
 #endif
     // ---- streaming phase: one warp per row, 16-byte accesses: store (crop) and the fused dot product ----
     {
@@ -920,7 +923,7 @@ __global__ void __launch_bounds__(NT, MINB) rows_inv_fast_kernel(RowsParams<T> P
 #pragma unroll
                                 for (int e = 0; e < CH; ++e) acc += (double)(y.v[e] * ov[k].v[e]);
                             }
-                            stv_stream(P.out + off + (size_t)c * CH, y);
+                            if (!tma_dot) stv_stream(P.out + off + (size_t)c * CH, y);
                         }
                     }
                 }
@@ -947,6 +950,9 @@ __global__ void __launch_bounds__(NT, MINB) rows_inv_fast_kernel(RowsParams<T> P
             }
         }
     }
+#ifndef HIPGP_EMU
+    if (tma_dot && tid == 0) bulk_s2g_wait();       // the bulk store has read the side buffer
+#endif
     if (want_dot) {
         __syncthreads();
         constexpr int WPR2 = (NT / 32) > NROW ? (NT / 32) / NROW : 1;

@@ -56,10 +56,12 @@ __device__ __forceinline__ cplx<double> ldg_c(const cplx<double>* p) {
 }
 #endif
 
-// Stage twiddle tables hold PAIRS: entry [p][j] = (w^{j (2p+1)}, w^{j (2p+2)}), p < R / 2 -- one 16-byte load (fp32) brings two
-// twiddles; an unused second half (R even) is 1.
+// fp32 stage twiddle tables hold PAIRS: entry [p][j] = (w^{j (2p+1)}, w^{j (2p+2)}), p < R / 2 -- one 16-byte load brings two
+// twiddles; an unused second half (R even) is 1.  fp64 tables stay [r-1][j]: a pair would be 32 bytes, i.e. two loads that each use
+// half of every sector (measured: +4 % on the fp64 matvec).
 template <class T> struct alignas(16) TwPair { cplx<T> a, b; };
 template <int R> struct TwPairs { static constexpr int n = R / 2; };            // = ceil((R - 1) / 2)
+template <class T> struct TwLayout { static constexpr bool paired = sizeof(T) == 4; };
 #ifdef HIPGP_EMU
 template <class T> __device__ __forceinline__ TwPair<T> ldg_pair(const TwPair<T>* p) { return *p; }
 #else
@@ -72,6 +74,15 @@ __device__ __forceinline__ TwPair<double> ldg_pair(const TwPair<double>* p) {
     TwPair<double> e; e.a = mk<double>(u.x, u.y); e.b = mk<double>(v.x, v.y); return e;
 }
 #endif
+// pair p of butterfly position j from the GLOBAL table of a stage, whatever its layout
+template <int R, int S, class T>
+__device__ __forceinline__ TwPair<T> tw_pair_global(const cplx<T>* tab, int p, int j) {
+    if (TwLayout<T>::paired) return ldg_pair(reinterpret_cast<const TwPair<T>*>(tab) + p * S + j);
+    TwPair<T> e;
+    e.a = ldg_c(tab + (2 * p) * S + j);
+    e.b = 2 * p + 2 < R ? ldg_c(tab + (2 * p + 1) * S + j) : mk<T>(1, 0);
+    return e;
+}
 
 constexpr int kMaxStages = 24;
 
@@ -84,7 +95,7 @@ struct LineFft {
     const cplx<T>* tw;      // Ln entries, exp(-2 pi i k / Ln)
     const int* rev;         // Ln entries: rev[p] = frequency index k stored at position p after DIF
     const int* pos;         // Ln entries: pos[k] = position p (inverse permutation)
-    const cplx<T>* twst;    // per-stage twiddles, stage s at twst + twoff[s]: TwPair [p * S + j] = (w_Nt^{j (2p+1)}, w_Nt^{j (2p+2)})
+    const cplx<T>* twst;    // per-stage twiddles, stage s at twst + twoff[s]: fp32 TwPair [p * S + j] = (w_Nt^{j (2p+1)}, w_Nt^{j (2p+2)}); fp64 [(r-1) * S + j]
     int twoff[kMaxStages];
 };
 

@@ -254,6 +254,12 @@ __device__ __forceinline__ void bulk_s2g(void* gmem_dst, const void* smem_src, u
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
+// the same in two halves: the issuing thread may do other work (and other threads may READ the source) before it waits
+__device__ __forceinline__ void bulk_s2g_issue(void* gmem_dst, const void* smem_src, unsigned bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"((unsigned)__cvta_generic_to_shared(smem_src)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_s2g_wait() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 #endif
 
 // ---------------------------------------------------------------------------------------------------------
@@ -389,15 +395,19 @@ struct TileGeo {
     __host__ __device__ static constexpr int leg(int S) { return (S == 1 ? 1 : (PAD ? S + (S >> LOGRL) : S)) * NL; }
 };
 
-// per-stage twiddles w^{j r}, r = 1..R-1, from the paired table of the stage (fft_engine.cuh: TwPair)
+// per-stage twiddles w^{j r}, r = 1..R-1, from the table of the stage (fft_engine.cuh: paired in fp32, [r-1][j] in fp64)
 template <int R, int S, class T>
 __device__ __forceinline__ void lane_twiddles(cplx<T>* w, const cplx<T>* __restrict__ tab, int j) {
-    const TwPair<T>* tp = reinterpret_cast<const TwPair<T>*>(tab);
+    if (TwLayout<T>::paired) {
 #pragma unroll
-    for (int p = 0; p < TwPairs<R>::n; ++p) {
-        const TwPair<T> e = ldg_pair(tp + p * S + j);
-        w[2 * p + 1] = e.a;
-        if (2 * p + 2 < R) w[2 * p + 2] = e.b;
+        for (int p = 0; p < TwPairs<R>::n; ++p) {
+            const TwPair<T> e = tw_pair_global<R, S, T>(tab, p, j);
+            w[2 * p + 1] = e.a;
+            if (2 * p + 2 < R) w[2 * p + 2] = e.b;
+        }
+    } else {
+#pragma unroll
+        for (int r = 1; r < R; ++r) w[r] = ldg_c(tab + (r - 1) * S + j);
     }
 }
 

@@ -145,24 +145,31 @@ struct LineFftHost {
         CK(cudaMemcpy(pos.p, hpos.data(), sizeof(int) * Ln, cudaMemcpyHostToDevice));
         dev.tw = tw.as<cplx<T>>(); dev.rev = rev.as<int>(); dev.pos = pos.as<int>();
         hrev_ = hrev; hpos_ = hpos;
-        // per-stage twiddle tables, PAIRED: [(p * S + j) * 2 + e] = exp(-2 pi i j (2p + 1 + e) / Nt), p < R / 2 (unused half = 1)
+        // per-stage twiddle tables.  fp32, PAIRED: [(p * S + j) * 2 + e] = exp(-2 pi i j (2p + 1 + e) / Nt), p < R / 2 (unused half = 1);
+        // fp64: [(r - 1) * S + j] = exp(-2 pi i j r / Nt)   (fft_engine.cuh: TwLayout)
         std::vector<cplx<T>> st;
         int Nt = Ln;
+        auto tw_entry = [](int j, int rr, int Nt_) {
+            const long num = ((long)j * rr) % Nt_;
+            const double a = -2.0 * M_PI * (double)num / (double)Nt_;
+            cplx<T> wv; wv.x = (T)std::cos(a); wv.y = (T)std::sin(a);
+            return wv;
+        };
         for (size_t i = 0; i < r.size(); ++i) {
             const int R = r[i], S = Nt / R;
             dev.twoff[i] = (int)st.size();
-            for (int p = 0; p < R / 2; ++p)
-                for (int j = 0; j < S; ++j)
-                    for (int e = 0; e < 2; ++e) {
-                        const int rr = 2 * p + 1 + e;
-                        cplx<T> wv; wv.x = (T)1; wv.y = (T)0;
-                        if (rr < R) {
-                            const long num = ((long)j * rr) % Nt;
-                            const double a = -2.0 * M_PI * (double)num / (double)Nt;
-                            wv.x = (T)std::cos(a); wv.y = (T)std::sin(a);
+            if (TwLayout<T>::paired) {
+                for (int p = 0; p < R / 2; ++p)
+                    for (int j = 0; j < S; ++j)
+                        for (int e = 0; e < 2; ++e) {
+                            const int rr = 2 * p + 1 + e;
+                            cplx<T> one; one.x = (T)1; one.y = (T)0;
+                            st.push_back(rr < R ? tw_entry(j, rr, Nt) : one);
                         }
-                        st.push_back(wv);
-                    }
+            } else {
+                for (int rr = 1; rr < R; ++rr)
+                    for (int j = 0; j < S; ++j) st.push_back(tw_entry(j, rr, Nt));
+            }
             Nt = S;
         }
         if (st.empty()) st.resize(1);
