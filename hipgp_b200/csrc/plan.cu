@@ -297,7 +297,7 @@ static const double* axis_cosmat(hipgp_plan* pl, int d, cudaStream_t s) {
         const size_t h = (size_t)(md + 1) / 2;
         b.ensure(sizeof(double) * 2 * h * h, &pl->dev_bytes);              // parity-split: Cw2[p][j < h][k' < h]
         auto k = dct1_cosmat_sym_kernel;
-        HIPGP_LAUNCH(k, dim3(148 * 4), dim3(256), 0, s, tab, b.as<double>(), md);
+        HIPGP_LAUNCH(k, dim3((unsigned)std::min<size_t>(148 * 4, (2 * h * h + 255) / 256)), dim3(256), 0, s, tab, b.as<double>(), md);
         CK_LAUNCH(); pl->launches++;
     }
     return b.as<double>();

@@ -289,7 +289,7 @@ def test_rt_column_gradient_against_autograd_of_the_reference_formula(lib, dims)
     lib.hipgp_plan_destroy(plan)
 
 
-@pytest.mark.parametrize("dims,nranks,dname,bins,chunks,peer", [((16, 12, 20), 2, "f64", False, 1, False), ((16, 12, 20), 4, "f32", True, 2, False),
+@pytest.mark.parametrize("dims,nranks,dname,bins,chunks,peer", [((16, 12, 20), 2, "f64", False, 1, False), ((8, 6, 10), 4, "f32", True, 2, False),
                                                                ((12, 10, 14), 3, "f64", True, 1, True)])
 def test_slab_stages_equal_the_undecomposed_matvec(lib, dims, nranks, dname, bins, chunks, peer):
     """the three local stages of the grid-sharded matvec (both exchange layouts; `bins` also for a rank count
