@@ -55,7 +55,8 @@ int hipgp_plan_embedding(const hipgp_plan* plan, int64_t* L_narrow, int64_t* L_w
 
 /* first row of K_uu (M values of the plan dtype, device; jitter already added -- toeplitz_tensor.py:127-133)
  * -> D = max(Re FFT(embed(column)), clamp) and the spectra of K, C^-1 (and lazily C^1/2).
- * `clamped_out` (host, optional) receives the number of clamped eigenvalues. */
+ * `clamped_out` (host, optional) receives the number of clamped values among the M DISTINCT spectrum entries (the DCT-I of the
+ * column; an interior entry stands for up to 2^ndim equal eigenvalues of the embedding). */
 int hipgp_plan_set_first_row(hipgp_plan* plan, const void* column_dev, double clamp, int64_t* clamped_out, void* stream);
 /* writes Mprime reals in the reference's (N_1..N_D) layout */
 int hipgp_plan_spectrum(hipgp_plan* plan, int which, void* out_dev, void* stream);

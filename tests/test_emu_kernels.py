@@ -320,3 +320,35 @@ def test_async_host_solve_entry_points(lib):
     assert lib.hipgp_pcg_host_wait(plan, 0, None) != 0          # nothing pending
     assert lib.hipgp_pcg_host_submit(plan, ptr(v), ptr(xs[0]), B, int(maxiter), float(tol), 1, 2, None) != 0   # bad slot
     lib.hipgp_plan_destroy(plan)
+
+
+@pytest.mark.parametrize("dims", [(3,), (4,), (5,), (8,), (65,), (130,), (5, 6), (33, 3), (4, 7, 3)])
+def test_spectrum_setup_equals_the_fft_of_the_even_extension(lib, dims):
+    """Set-up DCT-I (reflection-folded contraction, odd and even extents, unpaired middle input, extents down to 3): the spectrum
+    the plan reports is Re FFT of the circulant embedding of the first row (toeplitz_tensor.py:21-33), clamped at 1e-6; and the
+    K matvec on a unit vector returns the first row itself."""
+    rng = np.random.default_rng(sum(dims))
+    g = np.meshgrid(*[np.linspace(0, 1 + d, k) for d, k in enumerate(dims)], indexing="ij")
+    r = np.sqrt(sum((x - x.flat[0]) ** 2 for x in g))
+    col = (np.exp(-0.5 * (r / 0.35) ** 2)).reshape(-1); col[0] += 1e-3
+    emb = col.reshape(dims)
+    for ax in range(len(dims)):                                          # even extension per axis (circulant_embed)
+        mid = np.flip(emb, axis=ax)
+        sl = [slice(None)] * len(dims); sl[ax] = slice(1, -1)
+        emb = np.concatenate([emb, mid[tuple(sl)]], axis=ax)
+    want = np.maximum(np.real(np.fft.fftn(emb)), 1e-6).reshape(-1)
+    plan = C.c_void_p(); mm = np.array(dims, dtype=np.int64)
+    assert lib.hipgp_plan_create(len(dims), mm.ctypes.data_as(L._pi64), L.F64, 0, C.byref(plan)) == 0
+    ncl = C.c_int64()
+    assert lib.hipgp_plan_set_first_row(plan, ptr(np.ascontiguousarray(col)), 1e-6, C.byref(ncl), None) == 0, lib.hipgp_last_error()
+    D = np.zeros(want.size)
+    assert lib.hipgp_plan_spectrum(plan, 0, ptr(D), None) == 0, lib.hipgp_last_error()
+    assert np.abs(D - want).max() / np.abs(want).max() < 1e-12
+    corner = np.real(np.fft.fftn(emb))[tuple(slice(0, k) for k in dims)]          # the M distinct values (DCT-I of the column)
+    assert ncl.value == int(np.sum(corner < 1e-6))
+    if ncl.value == 0:
+        e0 = np.zeros((1, col.size)); e0[0, 0] = 1.0
+        out = np.zeros((1, col.size))
+        assert lib.hipgp_matvec(plan, 0, ptr(e0), ptr(out), 1, None) == 0, lib.hipgp_last_error()
+        assert rel(out[0], col) < 1e-12
+    lib.hipgp_plan_destroy(plan)
