@@ -20,7 +20,7 @@ roofline: per-kernel-class CUDA-event timing inside this script (a second pass o
           average durations); the dominant kernel and its share of the matvec are named.
 cpu_baseline / --impl reference: the UNMODIFIED reference (`oracle/_ref/ziggy`, staged byte for byte by
           oracle/make_ref.py; ToeplitzTensor._solve under the legacy-torch shim oracle/ref_shim.py) on the host cores,
-          same configuration, each step a bounded sample (16 of the step's 64 right-hand sides); falls back to the CPU
+          same configuration, each step a bounded sample (8 of the step's 64 right-hand sides); falls back to the CPU
           oracle port (oracle/ziggy_oracle.py) when the staged reference is absent.
 
 N > 1 (torchrun): right-hand sides are independent, so each rank solves its own B = 64 shard with no data-path
@@ -45,7 +45,7 @@ ELL, SIG2, JITTER = 0.01, 1.0, 1e-3
 MAXITER, TOL = 20, 1e-8
 B_PER_GPU = 64
 E2E_GROUP = int(os.environ.get("HIPGP_E2E_GROUP", "8"))     # right-hand sides in the first and the last group of the pipelined host solve
-CPU_SAMPLE_B = 16
+CPU_SAMPLE_B = 8       # right-hand sides per CPU step: ~7 s per step on 16 cores, so that --steps 20 --warmup 5 ends in ~3 minutes
 N_MATVEC = 2 * MAXITER + 1
 METRIC = "toeplitz_matvec_GBps_in_pcg_1e6grid"
 
