@@ -352,3 +352,18 @@ def test_spectrum_setup_equals_the_fft_of_the_even_extension(lib, dims):
         assert lib.hipgp_matvec(plan, 0, ptr(e0), ptr(out), 1, None) == 0, lib.hipgp_last_error()
         assert rel(out[0], col) < 1e-12
     lib.hipgp_plan_destroy(plan)
+
+
+def test_empty_shard_statistics_are_zero_not_uninitialised(lib):
+    """A rank whose shard of the minibatch is empty (3 observations on 8 GPUs) all-reduces its column statistics like everybody
+    else: hipgp_meanfield_colstats must WRITE zeros for B = 0 (the buffers come from torch.empty), and the row-wise entry points
+    must accept B = 0 as a no-op."""
+    E = 37
+    dm = np.full(E, 7.0); lam = np.full(E, 7.0)
+    kn = np.zeros((1, E)); w = np.zeros(1)
+    assert lib.hipgp_meanfield_colstats(L.F64, ptr(kn), ptr(w), ptr(w), 0, E, ptr(dm), ptr(lam), None) == 0, lib.hipgp_last_error()
+    assert not dm.any() and not lam.any()
+    out = np.full(3, 7.0)
+    assert lib.hipgp_meanfield_rowstats(L.F64, ptr(kn), ptr(kn), ptr(kn), 0, E, ptr(out), None) == 0
+    assert lib.hipgp_vec_dot(L.F64, ptr(kn), ptr(kn), out.ctypes.data_as(L._pd), 0, E, None) == 0
+    assert (out == 7.0).all()
